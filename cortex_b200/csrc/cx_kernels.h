@@ -1,0 +1,84 @@
+// cx_kernels.h -- host-side launch interface of the scan kernels (internal).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "cx_common.cuh"
+
+namespace cx {
+
+// Device view of the embedding store.
+struct StoreView {
+  const float* E;          // [n_rows][ld] fp32, rows 16 B aligned, zero padded to ld
+  const float* norm;       // [n_rows] sqrt(sum x^2) in reference order (index.rs:174)
+  const float* rnorm;      // [n_rows] 1/norm (fast passes only)
+  const uint32_t* meta;    // [n_rows] META_* word
+  const uint32_t* agent;   // [n_rows] interned agent id
+  const uint8_t* ids;      // [n_rows][16]
+  const void* E16;         // [n_rows][ld16] bf16 shadow (tensor pass) or nullptr
+  uint32_t n_rows, dim, ld, ld16;
+};
+
+// Queries prepared on device for one call.
+struct QueryView {
+  const float* Q;     // [nq][ldq] fp32 zero padded (ldq >= max(ld, qlen rounded to 4))
+  const float* qnorm; // [nq] reference-order norm over qlen elements
+  const float* rqnorm;// [nq] 1/qnorm
+  uint32_t nq, qlen, ldq;
+};
+
+// Per-(query, producer group) candidate lists written by a fast pass.
+struct CandView {
+  uint64_t* keys;   // [nq][G][KP] descending, 0 padded
+  uint64_t* bound;  // [nq][G] upper bound (key) of anything the group dropped; 0 = nothing dropped
+  uint32_t G, KP;
+};
+
+struct ResultView {
+  uint32_t* rows;   // [nq][k]
+  float* score;     // [nq][k]
+  float* dist;      // [nq][k]
+  uint8_t* ids;     // [nq][k][16]
+  uint32_t* n;      // [nq]
+  uint32_t* ok;     // [nq] 1 = verified exact, 0 = caller must fall back
+  uint32_t k;
+};
+
+// K4: norms (reference order), reciprocal norms, bf16 shadow rows for rows [r0, r0+n)
+void launch_prepare_rows(float* E, float* norm, float* rnorm, void* E16, uint32_t dim, uint32_t ld,
+                         uint32_t ld16, uint32_t r0, uint32_t n, cudaStream_t s);
+// queries: reference-order norm over qlen, reciprocal
+void launch_prepare_queries(const float* Q, float* qnorm, float* rqnorm, uint32_t nq, uint32_t qlen,
+                            uint32_t ldq, cudaStream_t s);
+
+// K1: streaming fp32 pass.  Handles queries [q0, q0+nq_pass) with nq_pass <= 8.
+// Returns the number of producer groups it will write (G) for a store of n_rows.
+uint32_t stream_scan_groups(uint32_t n_rows, int sm_count);
+size_t stream_scan_smem(uint32_t ld, uint32_t nq_pass, uint32_t KP);
+cudaError_t launch_stream_scan(const StoreView& st, const QueryView& qv, uint32_t q0, uint32_t nq_pass,
+                               const DevFilter& flt, const CandView& cv, int sm_count, cudaStream_t s);
+
+// K5 + K3: merge candidate lists, exact rescore, verify, emit results.
+// eps_cos: bound on |approx - reference| cosine for the pass that produced the candidates.
+size_t select_smem(uint32_t G, uint32_t KP, uint32_t ld);
+cudaError_t launch_select_rescore(const StoreView& st, const QueryView& qv, uint32_t q0, uint32_t nq,
+                                  const CandView& cv, const ResultView& rv, float eps_cos, cudaStream_t s);
+
+// Exact path: every row scored with reference arithmetic -> keys[n_rows] for one query
+void launch_exact_keys(const StoreView& st, const QueryView& qv, uint32_t q, const DevFilter& flt,
+                       uint64_t* keys, cudaStream_t s);
+// sort keys descending (cub radix sort); tmp sized by exact_sort_tmp_bytes
+size_t exact_sort_tmp_bytes(uint32_t n);
+cudaError_t exact_sort(uint64_t* keys_in, uint64_t* keys_out, uint32_t n, void* tmp, size_t tmp_bytes,
+                       cudaStream_t s);
+// emit the first min(k, #keys >= min_ord) results of a sorted key array for query q
+void launch_exact_emit(const StoreView& st, const QueryView& qv, uint32_t q, const uint64_t* sorted,
+                       uint32_t n_keys, uint32_t k, uint32_t min_ord, uint32_t* rows, float* score,
+                       float* dist, uint8_t* ids, uint32_t* n_out, uint32_t* n_total, cudaStream_t s);
+
+// compaction helper for rebuild(): dst[i] = src[live[i]] for all per-row arrays
+void launch_gather_rows(const StoreView& src, float* E, float* norm, float* rnorm, uint32_t* meta,
+                        uint32_t* agent, uint8_t* ids, void* E16, const uint32_t* live, uint32_t n_live,
+                        cudaStream_t s);
+
+}  // namespace cx

@@ -1,0 +1,209 @@
+// cx_select.cu -- K5 + K3: merge per-group candidate lists, rescore the head with
+// reference arithmetic, order, verify, emit.
+//
+// One CTA per query.
+//   1. gather the G x KP approximate keys, block-wide bitonic sort (descending)
+//   2. the KS = min(#candidates, KP) best are rescored exactly: rows are staged
+//      into shared memory with coalesced loads, then one thread per row runs the
+//      reference's strict left-to-right fp32 fold (index.rs:172) -- so scores and
+//      distances that leave here are bit-identical to the reference's
+//   3. the rescored rows are ordered by (score desc, NaN last, row asc) -- the
+//      stable descending sort of index.rs:287-292 with row order as the
+//      (reference-unspecified) tie order -- and the first k are emitted
+//   4. verification: U = best approximate cosine among everything NOT rescored
+//      (the next merged key and every group's drop bound).  The result is exact if
+//      sim_k > U + eps, where eps bounds |approximate - reference| for the pass that
+//      nominated the candidates, and score_k > 0 (below that the clamp of
+//      index.rs:255 creates ties the approximate order cannot see).  Otherwise
+//      ok[q] = 0 and the host reruns the query on the exact path.
+#include "cx_kernels.h"
+
+namespace cx {
+
+constexpr int SEL_THREADS = 512;
+constexpr int SEL_BATCH = 32;    // rows rescored per staging round
+constexpr int SEL_MAX_KS = 256;
+
+struct SelectParams {
+  StoreView st;
+  const float* Q;
+  const float* qnorm;
+  uint32_t ldq, qlen;
+  const uint64_t* keys;   // [nq][G][KP]
+  const uint64_t* bound;  // [nq][G]
+  uint32_t G, KP, NK;     // NK = pow2 >= G*KP
+  ResultView rv;          // pointers already offset to the first query of this launch
+  float eps;
+};
+
+static uint32_t pow2_at_least(uint32_t x) {
+  uint32_t p = 1;
+  while (p < x) p <<= 1;
+  return p;
+}
+
+__host__ __device__ inline size_t select_layout(uint32_t NK, uint32_t ld, size_t* off_q, size_t* off_stage,
+                                                size_t* off_e) {
+  size_t o = (size_t)NK * 8;
+  *off_q = o;
+  o += (size_t)ld * 4;
+  *off_stage = o;
+  o += (size_t)SEL_BATCH * (ld + 1) * 4;
+  o = (o + 7) & ~(size_t)7;
+  *off_e = o;
+  o += (size_t)SEL_MAX_KS * (8 + 4 + 4 + 4);
+  return o;
+}
+
+__global__ void __launch_bounds__(SEL_THREADS, 1) select_rescore_kernel(const SelectParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  size_t off_q, off_stage, off_e;
+  select_layout(p.NK, p.st.ld, &off_q, &off_stage, &off_e);
+  uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
+  float* q_s = reinterpret_cast<float*>(smem_raw + off_q);
+  float* stage = reinterpret_cast<float*>(smem_raw + off_stage);
+  uint64_t* ekey = reinterpret_cast<uint64_t*>(smem_raw + off_e);
+  float* esim = reinterpret_cast<float*>(ekey + SEL_MAX_KS);
+  float* edist = esim + SEL_MAX_KS;
+  float* escore = edist + SEL_MAX_KS;
+  __shared__ unsigned long long s_bound;
+  __shared__ uint32_t s_M;
+  __shared__ float s_simk, s_scorek;
+
+  const uint32_t q = blockIdx.x, tid = threadIdx.x;
+  const uint32_t ld = p.st.ld, dim = p.st.dim;
+  const uint32_t total = p.G * p.KP;
+  const uint64_t* src = p.keys + (size_t)q * total;
+
+  if (tid == 0) {
+    s_bound = 0ull;
+    s_M = 0;
+    s_simk = 0.0f;
+    s_scorek = 0.0f;
+  }
+  for (uint32_t i = tid; i < p.NK; i += SEL_THREADS) keys[i] = i < total ? src[i] : 0ull;
+  for (uint32_t d = tid; d < ld; d += SEL_THREADS) q_s[d] = d < p.qlen ? p.Q[(size_t)q * p.ldq + d] : 0.0f;
+  __syncthreads();
+  {
+    unsigned long long b = 0;
+    for (uint32_t g = tid; g < p.G; g += SEL_THREADS) {
+      unsigned long long v = p.bound[(size_t)q * p.G + g];
+      b = v > b ? v : b;
+    }
+    if (b) atomicMax(&s_bound, b);
+  }
+  bitonic_sort_desc(keys, p.NK, tid, SEL_THREADS, [] { __syncthreads(); });
+  // number of real candidates (keys are > 0, sorted descending)
+  for (uint32_t i = tid; i < p.NK; i += SEL_THREADS)
+    if (keys[i] != 0ull && (i + 1 == p.NK || keys[i + 1] == 0ull)) s_M = i + 1;
+  __syncthreads();
+  const uint32_t M = s_M;
+  const uint32_t KS = min(min(M, p.KP), (uint32_t)SEL_MAX_KS);
+  unsigned long long U = s_bound;
+  if (M > KS && keys[KS] > U) U = keys[KS];
+  const float na = p.qnorm[q];
+
+  // exact rescore, SEL_BATCH rows per round
+  const uint32_t warp = tid >> 5, lane = tid & 31, nwarps = SEL_THREADS / 32;
+  const uint32_t sstride = ld + 1;
+  for (uint32_t base = 0; base < KS; base += SEL_BATCH) {
+    const uint32_t nb = min((uint32_t)SEL_BATCH, KS - base);
+    for (uint32_t j = warp; j < nb; j += nwarps) {
+      const uint32_t row = key_row(keys[base + j]);
+      const float* g = p.st.E + (size_t)row * ld;
+      for (uint32_t d = lane; d < ld; d += 32) stage[j * sstride + d] = __ldg(g + d);
+    }
+    __syncthreads();
+    if (tid < nb) {
+      const uint32_t row = key_row(keys[base + tid]);
+      const float* r = stage + tid * sstride;
+      const uint32_t n = p.qlen < dim ? p.qlen : dim;
+      float dot = 0.0f;
+      for (uint32_t d = 0; d < n; ++d) dot = ref_fold(dot, q_s[d], r[d]);
+      const float nbm = __ldg(p.st.norm + row);
+      const float sim = __fdiv_rn(dot, __fmul_rn(na, nbm));
+      const float dist = __fsub_rn(1.0f, sim);
+      const float sc = ref_score_from_distance(dist);
+      ekey[base + tid] = make_key(ord_from_score(sc), row);
+      esim[base + tid] = sim;
+      edist[base + tid] = dist;
+      escore[base + tid] = sc;
+    }
+    __syncthreads();
+  }
+
+  // order by exact key (all distinct: the row is part of the key), emit the first k
+  const uint32_t k = p.rv.k;
+  const uint32_t n_out = min(k, KS);
+  if (tid < KS) {
+    const uint64_t mine = ekey[tid];
+    uint32_t rank = 0;
+    for (uint32_t j = 0; j < KS; ++j) rank += ekey[j] > mine;
+    if (rank < n_out) {
+      const size_t o = (size_t)q * k + rank;
+      const uint32_t row = key_row(mine);
+      p.rv.rows[o] = row;
+      p.rv.score[o] = escore[tid];
+      p.rv.dist[o] = edist[tid];
+      if (p.rv.ids)
+        *reinterpret_cast<uint4*>(p.rv.ids + o * 16) =
+            *reinterpret_cast<const uint4*>(p.st.ids + (size_t)row * 16);
+    }
+    if (rank + 1 == k) {
+      s_simk = esim[tid];
+      s_scorek = escore[tid];
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    p.rv.n[q] = n_out;
+    bool ok = KS >= k;
+    if (ok) {
+      const float sk = s_scorek, simk = s_simk;
+      if (sk != sk) ok = false;
+      else if (U != 0ull) {
+        const float u = float_from_ord(key_ord(U));
+        ok = (sk > 0.0f) && (simk > u + p.eps);
+      }
+    }
+    p.rv.ok[q] = ok ? 1u : 0u;
+  }
+}
+
+size_t select_smem(uint32_t G, uint32_t KP, uint32_t ld) {
+  size_t a, b, c;
+  return select_layout(pow2_at_least(G * KP), ld, &a, &b, &c);
+}
+
+cudaError_t launch_select_rescore(const StoreView& st, const QueryView& qv, uint32_t q0, uint32_t nq,
+                                  const CandView& cv, const ResultView& rv, float eps_cos, cudaStream_t s) {
+  if (!nq) return cudaSuccess;
+  SelectParams p;
+  p.st = st;
+  p.Q = qv.Q + (size_t)q0 * qv.ldq;
+  p.qnorm = qv.qnorm + q0;
+  p.ldq = qv.ldq;
+  p.qlen = qv.qlen;
+  p.keys = cv.keys + (size_t)q0 * cv.G * cv.KP;
+  p.bound = cv.bound + (size_t)q0 * cv.G;
+  p.G = cv.G;
+  p.KP = cv.KP;
+  p.NK = pow2_at_least(cv.G * cv.KP);
+  p.rv = rv;
+  p.rv.rows += (size_t)q0 * rv.k;
+  p.rv.score += (size_t)q0 * rv.k;
+  p.rv.dist += (size_t)q0 * rv.k;
+  if (p.rv.ids) p.rv.ids += (size_t)q0 * rv.k * 16;
+  p.rv.n += q0;
+  p.rv.ok += q0;
+  p.eps = eps_cos;
+  size_t smem = select_smem(cv.G, cv.KP, st.ld);
+  if (smem > 227 * 1024 || cv.KP > SEL_MAX_KS) return cudaErrorInvalidConfiguration;
+  cudaError_t e =
+      cudaFuncSetAttribute(select_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  select_rescore_kernel<<<nq, SEL_THREADS, smem, s>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace cx

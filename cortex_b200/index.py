@@ -1,0 +1,288 @@
+"""Host-side mirror of cortex-core's vector-index surface over the C ABI.
+
+Names, argument meaning and error behaviour follow
+/root/reference/crates/cortex-core/src/vector/index.rs:
+    SimilarityResult   :9-15      VectorFilter      :17-47
+    trait VectorIndex  :50-99     HnswIndex::new    :204-211
+    set_metadata       :219-222
+`GpuVectorIndex` is what `impl VectorIndex for GpuVectorIndex` looks like from
+Python; every method is one call into libcortex_gpu.so.  There is no fallback:
+if the library or a CUDA device is missing the constructor raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _capi
+
+
+class CortexError(Exception):
+    """cortex_core::CortexError (error.rs:7-50).  The index only ever raises the
+    Validation variant (index.rs:299-305, 438-459)."""
+
+    def __init__(self, message: str, status: int = _capi.CX_ERR_VALIDATION):
+        super().__init__(f"Validation error: {message}")
+        self.message = message
+        self.status = status
+
+
+def _check(st: int) -> None:
+    if st != _capi.CX_OK:
+        raise CortexError(_capi.load().cx_last_error().decode(errors="replace"), st)
+
+
+def validate_kind(kind: str) -> str:
+    """NodeKind::new (types.rs:76-90): non-empty, lowercase alphanumeric + hyphens."""
+    if not kind:
+        raise CortexError("NodeKind cannot be empty")
+    if not all((c.isascii() and (c.islower() or c.isdigit())) or c == "-" for c in kind):
+        raise CortexError(f"NodeKind '{kind}' must be lowercase alphanumeric + hyphens only")
+    return kind
+
+
+@dataclass
+class SimilarityResult:
+    node_id: bytes      # 16 raw uuid bytes
+    score: float        # cosine similarity clamped to [0, 1]
+    distance: float     # 1 - similarity, unclamped
+
+
+@dataclass
+class VectorFilter:
+    kinds: Optional[List[str]] = None
+    exclude: Optional[List[bytes]] = None
+    source_agent: Optional[str] = None
+
+    @classmethod
+    def new(cls) -> "VectorFilter":
+        return cls()
+
+    def with_kinds(self, kinds: Sequence[str]) -> "VectorFilter":
+        self.kinds = [validate_kind(k) for k in kinds]
+        return self
+
+    def excluding(self, ids: Sequence[bytes]) -> "VectorFilter":
+        self.exclude = [bytes(i) for i in ids]
+        return self
+
+    def with_source_agent(self, agent: str) -> "VectorFilter":
+        self.source_agent = agent
+        return self
+
+
+@dataclass
+class _CFilter:
+    struct: _capi.CxFilter
+    keep: list = field(default_factory=list)
+
+    @property
+    def ptr(self):
+        return C.addressof(self.struct)
+
+
+def _c_filter(f: Optional[VectorFilter]) -> Optional[_CFilter]:
+    if f is None:
+        return None
+    cf = _CFilter(_capi.CxFilter())
+    s = cf.struct
+    if f.kinds is not None:
+        arr = (C.c_char_p * max(1, len(f.kinds)))(*[k.encode() for k in f.kinds])
+        cf.keep.append(arr)
+        s.has_kinds, s.kinds, s.n_kinds = 1, C.cast(arr, C.POINTER(C.c_char_p)), len(f.kinds)
+    if f.exclude is not None:
+        ex = np.frombuffer(b"".join(bytes(e) for e in f.exclude), dtype=np.uint8).copy()
+        if ex.size != 16 * len(f.exclude):
+            raise CortexError("exclude ids must be 16 bytes each")
+        cf.keep.append(ex)
+        s.has_exclude, s.exclude_ids, s.n_exclude = 1, (ex.ctypes.data if ex.size else None), len(f.exclude)
+    if f.source_agent is not None:
+        b = f.source_agent.encode()
+        cf.keep.append(b)
+        s.has_source_agent, s.source_agent = 1, b
+    return cf
+
+
+def _id16(node_id) -> np.ndarray:
+    a = np.frombuffer(bytes(node_id), dtype=np.uint8)
+    if a.size != 16:
+        raise CortexError("node id must be 16 bytes")
+    return a.copy()
+
+
+class GpuVectorIndex:
+    """B200-resident exact-scan index behind the reference's VectorIndex surface."""
+
+    def __init__(self, dimension: int, device: int = 0, _handle: Optional[int] = None):
+        self._L = _capi.load()
+        self.dimension = int(dimension)
+        self.device = device
+        if _handle is None:
+            h = C.c_void_p()
+            _check(self._L.cx_index_create(self.dimension, device, C.byref(h)))
+            self._h = h
+        else:
+            self._h = C.c_void_p(_handle)
+
+    # HnswIndex::with_metadata (index.rs:214-216) is an alias of new()
+    @classmethod
+    def with_metadata(cls, dimension: int, device: int = 0) -> "GpuVectorIndex":
+        return cls(dimension, device)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._L.cx_index_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- mutation -----------------------------------------------------------
+    def insert(self, node_id, embedding) -> None:
+        v = np.ascontiguousarray(embedding, dtype=np.float32).reshape(-1)
+        i = _id16(node_id)
+        _check(self._L.cx_insert(self._h, i.ctypes.data, v.ctypes.data, v.size))
+
+    def insert_batch(self, ids: np.ndarray, rows: np.ndarray) -> None:
+        rows = np.ascontiguousarray(rows, dtype=np.float32)
+        ids = np.ascontiguousarray(ids, dtype=np.uint8).reshape(-1, 16)
+        if rows.ndim != 2 or ids.shape[0] != rows.shape[0]:
+            raise CortexError("insert_batch needs ids [n,16] and rows [n,dim]")
+        _check(self._L.cx_insert_batch(self._h, ids.ctypes.data, rows.ctypes.data, rows.shape[0], rows.shape[1]))
+
+    def remove(self, node_id) -> None:
+        _check(self._L.cx_remove(self._h, _id16(node_id).ctypes.data))
+
+    def set_metadata(self, node_id, kind: str, source_agent: str) -> None:
+        validate_kind(kind)
+        _check(self._L.cx_set_metadata(self._h, _id16(node_id).ctypes.data, kind.encode(), source_agent.encode()))
+
+    def reserve(self, n_rows: int) -> None:
+        _check(self._L.cx_reserve(self._h, n_rows))
+
+    def rebuild(self) -> None:
+        _check(self._L.cx_rebuild(self._h))
+
+    # ---- queries ------------------------------------------------------------
+    def __len__(self) -> int:
+        return int(self._L.cx_len(self._h))
+
+    def len(self) -> int:
+        return len(self)
+
+    def is_empty(self) -> bool:
+        return len(self) == 0
+
+    def search(self, query, k: int, filter: Optional[VectorFilter] = None) -> List[SimilarityResult]:
+        q = np.ascontiguousarray(query, dtype=np.float32).reshape(-1)
+        kk = max(1, min(int(k), max(1, len(self))))
+        ids = np.zeros((kk, 16), np.uint8)
+        sc = np.zeros(kk, np.float32)
+        di = np.zeros(kk, np.float32)
+        n = C.c_uint64(0)
+        cf = _c_filter(filter)
+        _check(self._L.cx_search(self._h, q.ctypes.data, q.size, min(int(k), kk), cf.ptr if cf else None,
+                                 ids.ctypes.data, sc.ctypes.data, di.ctypes.data, C.byref(n)))
+        return [SimilarityResult(ids[i].tobytes(), float(sc[i]), float(di[i])) for i in range(n.value)]
+
+    def search_threshold(self, query, threshold: float,
+                         filter: Optional[VectorFilter] = None) -> List[SimilarityResult]:
+        q = np.ascontiguousarray(query, dtype=np.float32).reshape(-1)
+        cf = _c_filter(filter)
+        cap = min(max(1, len(self)), 4096)
+        while True:
+            ids = np.zeros((cap, 16), np.uint8)
+            sc = np.zeros(cap, np.float32)
+            di = np.zeros(cap, np.float32)
+            n, total = C.c_uint64(0), C.c_uint64(0)
+            _check(self._L.cx_search_threshold(self._h, q.ctypes.data, q.size, C.c_float(threshold),
+                                               cf.ptr if cf else None, cap, ids.ctypes.data, sc.ctypes.data,
+                                               di.ctypes.data, C.byref(n), C.byref(total)))
+            if total.value <= cap:
+                break
+            cap = int(total.value)
+        return [SimilarityResult(ids[i].tobytes(), float(sc[i]), float(di[i])) for i in range(n.value)]
+
+    def search_batch_arrays(self, queries: np.ndarray, k: int, filter: Optional[VectorFilter] = None
+                            ) -> Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]:
+        """Array form: ids [B,k,16], score [B,k], distance [B,k], n [B]."""
+        Q = np.ascontiguousarray(queries, dtype=np.float32)
+        if Q.ndim != 2:
+            raise CortexError("queries must be [B, dim]")
+        B, qlen = Q.shape
+        kk = max(1, int(k))
+        ids = np.zeros((B, kk, 16), np.uint8)
+        sc = np.zeros((B, kk), np.float32)
+        di = np.zeros((B, kk), np.float32)
+        n = np.zeros(B, np.uint64)
+        cf = _c_filter(filter)
+        _check(self._L.cx_search_batch(self._h, Q.ctypes.data, B, qlen, int(k), cf.ptr if cf else None,
+                                       ids.ctypes.data, sc.ctypes.data, di.ctypes.data, n.ctypes.data))
+        return ids, sc, di, n
+
+    def search_batch(self, queries: Iterable[Tuple[bytes, Sequence[float]]], k: int,
+                     filter: Optional[VectorFilter] = None) -> Dict[bytes, List[SimilarityResult]]:
+        """index.rs:390-410: map keyed by the query's node id."""
+        queries = list(queries)
+        if not queries:
+            return {}
+        Q = np.stack([np.asarray(e, dtype=np.float32) for _, e in queries])
+        ids, sc, di, n = self.search_batch_arrays(Q, k, filter)
+        out: Dict[bytes, List[SimilarityResult]] = {}
+        for b, (qid, _) in enumerate(queries):
+            out[bytes(qid)] = [SimilarityResult(ids[b, i].tobytes(), float(sc[b, i]), float(di[b, i]))
+                               for i in range(int(n[b]))]
+        return out
+
+    def search_batch_device(self, d_queries, k: int, filter: Optional[VectorFilter] = None, stream: int = 0,
+                            out=None):
+        """Queries and results stay in HBM.  d_queries: torch.float32 CUDA tensor [B, dim].
+        Returns (rows int32 [B,k], score [B,k], distance [B,k], n int32 [B]) CUDA tensors."""
+        import torch
+
+        assert d_queries.is_cuda and d_queries.dtype == torch.float32 and d_queries.is_contiguous()
+        B = d_queries.shape[0]
+        if out is None:
+            dev = d_queries.device
+            out = (torch.empty((B, k), dtype=torch.int32, device=dev),
+                   torch.empty((B, k), dtype=torch.float32, device=dev),
+                   torch.empty((B, k), dtype=torch.float32, device=dev),
+                   torch.empty((B,), dtype=torch.int32, device=dev))
+        rows, sc, di, n = out
+        cf = _c_filter(filter)
+        _check(self._L.cx_search_batch_device(self._h, d_queries.data_ptr(), B, int(k), cf.ptr if cf else None,
+                                              rows.data_ptr(), sc.data_ptr(), di.data_ptr(), None,
+                                              n.data_ptr(), C.c_void_p(stream)))
+        return out
+
+    def row_id(self, row: int) -> bytes:
+        buf = np.zeros(16, np.uint8)
+        _check(self._L.cx_row_id(self._h, int(row), buf.ctypes.data))
+        return buf.tobytes()
+
+    # ---- persistence ----------------------------------------------------------
+    def save(self, path: str) -> None:
+        _check(self._L.cx_save(self._h, str(path).encode()))
+
+    @classmethod
+    def load(cls, path: str, device: int = 0) -> "GpuVectorIndex":
+        L = _capi.load()
+        h = C.c_void_p()
+        _check(L.cx_load(str(path).encode(), device, C.byref(h)))
+        dim = int(L.cx_dimension(h))
+        return cls(dim, device, _handle=h.value)
+
+    # ---- instrumentation ------------------------------------------------------
+    def stats(self) -> dict:
+        s = _capi.CxStats()
+        _check(self._L.cx_get_stats(self._h, C.byref(s)))
+        return {k: int(getattr(s, k)) for k, _ in s._fields_}
+
+    def set_option(self, key: str, value: int) -> None:
+        _check(self._L.cx_set_option(self._h, key.encode(), int(value)))

@@ -1,0 +1,83 @@
+"""Row-sharded search: one process per GPU, each holding a contiguous block of the
+corpus; every rank scans its shard for the same query batch, the fixed-size local
+top-k lists are exchanged with ONE all_gather (NCCL over NVLink on GPUs, gloo in
+the CPU tests) and merged identically on every rank.
+
+The reference is single-process (ARCHITECTURE.md:38); sharding is listed there as
+future work (ARCHITECTURE.md:365-368).  Scores are independent per (query,row) and
+top-k is mergeable, so the exchange is only B*k*16 bytes per rank.
+
+Merge order = the single-index order: score descending, NaN last, then global row
+ascending, where global row = shard offset + local row (shards are contiguous
+blocks in insertion order).
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+_ROW_BITS = 31
+_ROW_MASK = (1 << _ROW_BITS) - 1
+_INVALID = -(1 << 62)
+
+
+def pack_keys(rows: torch.Tensor, score: torch.Tensor, n: torch.Tensor, row_offset: int) -> torch.Tensor:
+    """(score, global row) -> sortable int64; larger = better.  rows/score [B,k], n [B]."""
+    sbits = score.contiguous().view(torch.int32).to(torch.int64)
+    sbits = torch.where(torch.isnan(score), torch.full_like(sbits, -1), sbits)  # NaN last
+    sbits = torch.where(score == 0, torch.zeros_like(sbits), sbits)             # -0.0 ties with +0.0
+    grow = rows.to(torch.int64) + int(row_offset)
+    key = (sbits << _ROW_BITS) | (_ROW_MASK - grow)
+    k = rows.shape[1]
+    valid = torch.arange(k, device=rows.device)[None, :] < n.to(torch.int64)[:, None]
+    return torch.where(valid, key, torch.full_like(key, _INVALID))
+
+
+def unpack_keys(key: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """-> (global_row int64, score_bits int32 (only for non-NaN), valid bool)"""
+    valid = key > _INVALID
+    grow = _ROW_MASK - (key & _ROW_MASK)
+    sbits = (key >> _ROW_BITS).to(torch.int32)
+    return grow, sbits, valid
+
+
+def merge_gathered(keys: torch.Tensor, dists: torch.Tensor, k: int):
+    """keys/dists [W,B,k] -> merged (global_rows [B,k], score [B,k], dist [B,k], n [B])."""
+    W, B, kk = keys.shape
+    flat = keys.permute(1, 0, 2).reshape(B, W * kk)
+    dflat = dists.permute(1, 0, 2).reshape(B, W * kk)
+    top, idx = torch.sort(flat, dim=1, descending=True, stable=True)
+    top, idx = top[:, :k], idx[:, :k]
+    grow, sbits, valid = unpack_keys(top)
+    d = torch.gather(dflat, 1, idx)
+    # the score is recomputed from its own bits except for NaN rows, whose distance is NaN too
+    score = sbits.view(torch.float32) if sbits.is_contiguous() else sbits.contiguous().view(torch.float32)
+    score = torch.where(sbits < 0, torch.full_like(score, float("nan")), score)
+    n = valid.sum(dim=1).to(torch.int32)
+    return grow, score, d, n
+
+
+class ShardedSearch:
+    """local_search(d_queries, k) -> (rows int32 [B,k], score f32 [B,k], dist f32 [B,k], n int32 [B])"""
+
+    def __init__(self, local_search: Callable, row_offset: int, group: Optional[dist.ProcessGroup] = None):
+        self.local_search = local_search
+        self.row_offset = int(row_offset)
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+
+    def search(self, queries: torch.Tensor, k: int):
+        rows, score, d, n = self.local_search(queries, k)
+        key = pack_keys(rows, score, n, self.row_offset)
+        if self.world == 1:
+            return merge_gathered(key[None], d[None], k)
+        payload = torch.stack([key, d.contiguous().view(torch.int32).to(torch.int64)], dim=0)  # [2,B,k]
+        flat = torch.empty((self.world * 2,) + tuple(payload.shape[1:]), dtype=payload.dtype,
+                           device=payload.device)
+        dist.all_gather_into_tensor(flat, payload, group=self.group)  # concatenated along dim 0
+        gathered = flat.view((self.world, 2) + tuple(payload.shape[1:]))
+        keys = gathered[:, 0]
+        dists = gathered[:, 1].to(torch.int32).view(torch.float32)
+        return merge_gathered(keys, dists, k)

@@ -1,0 +1,140 @@
+/*
+ * cortex_gpu.h -- C ABI of the B200-native similarity-scan engine.
+ *
+ * This is the drop-in boundary for cortex-core's vector layer: one exported
+ * function per method of `trait VectorIndex`
+ * (/root/reference/crates/cortex-core/src/vector/index.rs:50-99) plus
+ * `HnswIndex::new` / `set_metadata` (index.rs:204-222).  A Rust FFI crate
+ * (rust/cortex-gpu-sys) binds exactly these symbols and
+ * implements `VectorIndex for GpuVectorIndex` on top of them.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; ids are 16 raw bytes (uuid::Uuid::as_bytes,
+ *    types.rs:9); embeddings are contiguous f32 (types.rs:22).
+ *  - every function returns a cx_status; on failure cx_last_error() returns a
+ *    thread-local message.  The Rust side maps any non-zero status to
+ *    CortexError::Validation(msg) (error.rs:48-49), the only error the reference
+ *    index ever raises (index.rs:299-305, 438-459).
+ *  - search* functions are re-entrant from many host threads (the reference
+ *    shares the index as Arc<RwLock<_>> and searches under read guards,
+ *    serve.rs:101, routes.rs:906); mutators (insert/remove/set_metadata/rebuild)
+ *    must be externally serialised against everything else, which the caller's
+ *    write guard already does.
+ *  - there is no CPU fallback: without a CUDA device cx_index_create fails with
+ *    CX_ERR_CUDA.
+ */
+#ifndef CORTEX_GPU_H
+#define CORTEX_GPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum cx_status {
+  CX_OK = 0,
+  CX_ERR_VALIDATION = 1, /* dimension mismatch, bad argument (index.rs:299-305) */
+  CX_ERR_CUDA = 2,
+  CX_ERR_NCCL = 3,
+  CX_ERR_IO = 4          /* save/load (index.rs:438-459) */
+} cx_status;
+
+typedef struct cx_index cx_index;
+
+/* VectorFilter, index.rs:17-26.  A NULL filter pointer == None. */
+typedef struct cx_filter {
+  int32_t has_kinds;            /* kinds: Option<Vec<NodeKind>> */
+  const char* const* kinds;
+  uint32_t n_kinds;
+  int32_t has_exclude;          /* exclude: Option<Vec<NodeId>> */
+  const uint8_t* exclude_ids;   /* n_exclude x 16 bytes */
+  uint32_t n_exclude;
+  int32_t has_source_agent;     /* source_agent: Option<String> */
+  const char* source_agent;
+} cx_filter;
+
+/* Counters for tests / bench (gpu_launches, which pass served a query). */
+typedef struct cx_stats {
+  uint64_t kernel_launches;     /* kernels launched by this index since creation */
+  uint64_t queries_stream;      /* queries answered by the fp32 streaming pass (K1) */
+  uint64_t queries_tensor;      /* queries answered by the tcgen05 pass (K2) */
+  uint64_t queries_exact;       /* queries answered by the exact path */
+  uint64_t fallbacks;           /* queries whose fast-pass result failed verification */
+  uint64_t h2d_bytes;
+  uint64_t d2h_bytes;
+  uint64_t pass_kernel_ns;      /* with option "profile"=1: CUDA-event time of the scan-pass kernels */
+  uint64_t pass_kernel_launches;/* ... and how many of them that time covers */
+} cx_stats;
+
+/* HnswIndex::new(dimension), index.rs:204-211.  device = CUDA ordinal. */
+cx_status cx_index_create(uint32_t dimension, int device, cx_index** out);
+void cx_index_destroy(cx_index* h);
+
+/* VectorIndex::insert, index.rs:298-314.  len != dimension -> CX_ERR_VALIDATION
+ * "Embedding dimension mismatch: expected D, got L".  Same id overwrites. */
+cx_status cx_insert(cx_index* h, const uint8_t id[16], const float* embedding, uint32_t len);
+/* Bulk form of the startup loop serve.rs:111-117 / api.rs:55-69: n rows, row-major. */
+cx_status cx_insert_batch(cx_index* h, const uint8_t* ids, const float* rows, uint64_t n, uint32_t len);
+/* VectorIndex::remove, index.rs:316-323.  Unknown id is not an error. */
+cx_status cx_remove(cx_index* h, const uint8_t id[16]);
+/* HnswIndex::set_metadata, index.rs:219-222. */
+cx_status cx_set_metadata(cx_index* h, const uint8_t id[16], const char* kind, const char* source_agent);
+/* VectorIndex::len, index.rs:412-414. */
+uint64_t cx_len(const cx_index* h);
+uint32_t cx_dimension(const cx_index* h);
+/* VectorIndex::rebuild, index.rs:416-435: there is no graph to build; this
+ * compacts removed rows out of the device matrix (order preserving). */
+cx_status cx_rebuild(cx_index* h);
+/* Reserve capacity for n rows up front (no reference counterpart). */
+cx_status cx_reserve(cx_index* h, uint64_t n_rows);
+
+/* VectorIndex::search, index.rs:325-374 (exact scan semantics of :259-294).
+ * Outputs hold up to k entries; *out_n = number written.  qlen may differ from
+ * the dimension (the reference never checks it; zip truncates, index.rs:172). */
+cx_status cx_search(cx_index* h, const float* query, uint32_t qlen, uint64_t k, const cx_filter* filter,
+                    uint8_t* out_ids, float* out_score, float* out_distance, uint64_t* out_n);
+/* VectorIndex::search_threshold, index.rs:376-388: all rows with score >= threshold,
+ * best first.  At most cap entries are written; *out_total = how many qualify. */
+cx_status cx_search_threshold(cx_index* h, const float* query, uint32_t qlen, float threshold,
+                              const cx_filter* filter, uint64_t cap, uint8_t* out_ids, float* out_score,
+                              float* out_distance, uint64_t* out_n, uint64_t* out_total);
+/* VectorIndex::search_batch, index.rs:390-410.  queries is [B][qlen] row-major;
+ * outputs are [B][k] (ids [B][k][16]); out_n[b] = results of query b.  The caller
+ * keys the result map by its own query ids. */
+cx_status cx_search_batch(cx_index* h, const float* queries, uint64_t B, uint32_t qlen, uint64_t k,
+                          const cx_filter* filter, uint8_t* out_ids, float* out_score, float* out_distance,
+                          uint64_t* out_n);
+
+/* Device-resident form of search_batch for callers that keep queries and results
+ * in HBM (sharded merge over NCCL, benchmarks).  d_queries: [B][qlen] f32 device
+ * memory; outputs are device buffers [B][k] (rows are shard-local row numbers),
+ * d_out_n [B] u32.  Runs on `stream` (a cudaStream_t) and returns after
+ * enqueueing; queries whose fast-pass result could not be verified are redone on
+ * the exact path before return (that part synchronises the stream). */
+cx_status cx_search_batch_device(cx_index* h, const float* d_queries, uint64_t B, uint64_t k,
+                                 const cx_filter* filter, uint32_t* d_out_rows, float* d_out_score,
+                                 float* d_out_distance, uint8_t* d_out_ids, uint32_t* d_out_n, void* stream);
+
+/* VectorIndex::save / load, index.rs:437-472: bincode 1.3 layout of
+ * (HashMap<Uuid,Vec<f32>>, HashMap<Uuid,NodeMetadata>, usize). */
+cx_status cx_save(const cx_index* h, const char* path);
+cx_status cx_load(const char* path, int device, cx_index** out);
+
+/* id of shard-local row r (16 bytes) -- used when merging device results */
+cx_status cx_row_id(const cx_index* h, uint32_t row, uint8_t out_id[16]);
+
+cx_status cx_get_stats(const cx_index* h, cx_stats* out);
+/* Tuning / test hooks: "force_path" 0 auto, 1 stream (K1), 2 tensor (K2), 3 exact;
+ * "stream_max_batch" largest query group K1 serves before K2 takes over;
+ * "profile" 1 = bracket the scan-pass kernels with CUDA events on their stream. */
+cx_status cx_set_option(cx_index* h, const char* key, int64_t value);
+
+const char* cx_last_error(void);
+const char* cx_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CORTEX_GPU_H */

@@ -1,0 +1,66 @@
+"""CPU-side checks of the C ABI: the library loads without a GPU, exports every
+symbol include/cortex_gpu.h declares, and refuses to compute without a device."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from cortex_b200 import _capi, build
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build.build()
+    return _capi.load()
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "cortex_gpu.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return set(re.findall(r"\b(cx_[a-z_0-9]+)\s*\(", src))
+
+
+def test_every_header_symbol_is_exported_and_bound(lib):
+    syms = header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in cortex_gpu.h but not exported"
+    assert syms == set(_capi.SYMBOLS), "ctypes table and header disagree"
+
+
+def test_version_and_error_strings(lib):
+    assert b"sm_100a" in lib.cx_version()
+    assert isinstance(lib.cx_last_error(), bytes)
+
+
+def test_argument_validation_needs_no_device(lib):
+    h = C.c_void_p()
+    assert lib.cx_index_create(0, 0, C.byref(h)) == _capi.CX_ERR_VALIDATION
+    assert b"dimension" in lib.cx_last_error()
+    assert lib.cx_len(None) == 0
+
+
+def test_no_cpu_fallback_without_device(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    h = C.c_void_p()
+    st = lib.cx_index_create(384, 0, C.byref(h))
+    assert st == _capi.CX_ERR_CUDA
+    assert b"no CPU fallback" in lib.cx_last_error()
+    from cortex_b200 import CortexError, GpuVectorIndex
+    with pytest.raises(CortexError):
+        GpuVectorIndex(384)
+
+
+def test_product_never_imports_oracle():
+    """The oracle is test infrastructure; nothing under cortex_b200/ may reference it."""
+    pkg = os.path.join(ROOT, "cortex_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")):
+                txt = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "oracle" not in txt.lower() or f == "build.py" and False, f"{f} mentions the oracle"
