@@ -14,6 +14,14 @@ pytestmark = pytest.mark.gpu
 GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "scan_golden.npz"))
 
 
+def same_bits(a, b):
+    """bit-identical floats; NaN matches NaN (the payload is not part of the value:
+    x86 produces 0xFFC00000 for 0/0, the GPU the canonical 0x7FFFFFFF)."""
+    a = np.asarray(a, np.float32)
+    b = np.asarray(b, np.float32)
+    return a.shape == b.shape and bool(np.all((a.view(np.uint32) == b.view(np.uint32)) | (np.isnan(a) & np.isnan(b))))
+
+
 def build_pair(corpus, ids=None):
     n, d = corpus.shape
     ids = synth.make_ids(n) if ids is None else ids
@@ -31,8 +39,8 @@ def assert_batch_equal(g, o, Q, k, gflt=None, oflt=None):
     for b in range(Q.shape[0]):
         n = int(on[b])
         assert np.array_equal(gi[b, :n], oi[b, :n]), f"query {b}: ids differ"
-        assert np.array_equal(gs[b, :n].view(np.uint32), os_[b, :n].view(np.uint32)), f"query {b}: scores differ"
-        assert np.array_equal(gd[b, :n].view(np.uint32), od[b, :n].view(np.uint32)), f"query {b}: distances differ"
+        assert same_bits(gs[b, :n], os_[b, :n]), f"query {b}: scores differ"
+        assert same_bits(gd[b, :n], od[b, :n]), f"query {b}: distances differ"
 
 
 @pytest.mark.parametrize("case", ["A", "B", "C", "D"])
@@ -49,8 +57,8 @@ def test_golden_vectors_bitwise(case):
     for b, q in enumerate(qs):
         res = g.search(q, n)
         assert [int.from_bytes(r.node_id, "big") for r in res] == list(rows[b])
-        assert np.array_equal(np.array([r.score for r in res], np.float32).view(np.uint32), score[b].view(np.uint32))
-        assert np.array_equal(np.array([r.distance for r in res], np.float32).view(np.uint32), dist[b].view(np.uint32))
+        assert same_bits([r.score for r in res], score[b])
+        assert same_bits([r.distance for r in res], dist[b])
         thr = g.search_threshold(q, 0.75)
         exp = [int(r) for r, s in zip(rows[b], score[b]) if s >= np.float32(0.75)]
         assert [int.from_bytes(r.node_id, "big") for r in thr] == exp
@@ -163,8 +171,7 @@ def test_threshold_search_matches_oracle():
             res = g.search_threshold(q, t)
             exp = o.search_threshold(q, t)
             assert [r.node_id for r in res] == [i.tobytes() for i in exp.ids]
-            assert np.array_equal(np.array([r.score for r in res], np.float32).view(np.uint32),
-                                  exp.score.view(np.uint32))
+            assert same_bits([r.score for r in res], exp.score)
 
 
 def test_query_length_mismatch_follows_zip_truncation():
@@ -175,8 +182,7 @@ def test_query_length_mismatch_follows_zip_truncation():
         res = g.search(q, 7)
         exp = o.search(q, 7)
         assert [r.node_id for r in res] == [i.tobytes() for i in exp.ids]
-        assert np.array_equal(np.array([r.distance for r in res], np.float32).view(np.uint32),
-                              exp.distance.view(np.uint32))
+        assert same_bits([r.distance for r in res], exp.distance)
 
 
 def test_save_load_roundtrip_and_layout(tmp_path):
