@@ -264,13 +264,24 @@ def main():
         torch.cuda.synchronize()
 
     # ---- value: device-resident ---------------------------------------------------
-    for _ in range(max(3, a.warmup)):
-        step_device()
-    barrier()
-    st0 = ix.stats()
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
+    for _ in range(max(3, a.warmup)):
+        step_device()
+    # untimed soak (~1 s) so that clocks settle and nvidia-smi gets samples under load
+    t_soak = time.perf_counter()
+    n_soak = torch.zeros(1, device=dev)
+    while True:
+        for _ in range(8):
+            step_device()
+        n_soak.fill_(1.0 if time.perf_counter() - t_soak < 1.0 else 0.0)
+        if world > 1:
+            dist.broadcast(n_soak, src=0)
+        if n_soak.item() == 0.0:
+            break
+    barrier()
+    st0 = ix.stats()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
@@ -280,7 +291,6 @@ def main():
     barrier()
     ms_total = e0.elapsed_time(e1)
     st1 = ix.stats()
-    clk = clocks.stop() if rank == 0 else None
     t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -301,6 +311,7 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = a.batch * world * a.steps / float(te.item())
+    clk = clocks.stop() if rank == 0 else None
     h2d = a.batch * a.dim * 4
     d2h = a.batch * a.k * (16 + 4 + 4) + a.batch * 4
 

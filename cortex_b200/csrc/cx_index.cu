@@ -210,8 +210,8 @@ static cx_status grow(cx_index* h, uint64_t need) {
   uint8_t* ids = nullptr;
   void* e16 = nullptr;
   CU(cudaMalloc(&E, ncap * h->ld * sizeof(float)));
-  CU(cudaMalloc(&nm, ncap * sizeof(float)));
-  CU(cudaMalloc(&rn, ncap * sizeof(float)));
+  CU(cudaMalloc(&nm, (ncap + 32) * sizeof(float)));  // +32: the scan reads norms in 16 B units
+  CU(cudaMalloc(&rn, (ncap + 32) * sizeof(float)));
   CU(cudaMalloc(&me, ncap * sizeof(uint32_t)));
   CU(cudaMalloc(&ag, ncap * sizeof(uint32_t)));
   CU(cudaMalloc(&ids, ncap * 16));
@@ -430,8 +430,8 @@ extern "C" cx_status cx_rebuild(cx_index* h) {
   uint8_t* ids = nullptr;
   void* e16 = nullptr;
   CU(cudaMalloc(&E, ncap * h->ld * sizeof(float)));
-  CU(cudaMalloc(&nm, ncap * 4));
-  CU(cudaMalloc(&rn, ncap * 4));
+  CU(cudaMalloc(&nm, (ncap + 32) * 4));
+  CU(cudaMalloc(&rn, (ncap + 32) * 4));
   CU(cudaMalloc(&me, ncap * 4));
   CU(cudaMalloc(&ag, ncap * 4));
   CU(cudaMalloc(&ids, ncap * 16));
@@ -531,6 +531,7 @@ struct SearchBufs {
   uint32_t* excl;
   uint64_t* cand_keys;
   uint64_t* cand_bound;
+  uint64_t* gtau;
   uint32_t *rows, *n, *ok;
   float *score, *dist;
   uint8_t* ids;
@@ -586,6 +587,8 @@ static cx_status run_search(cx_index* h, Workspace* ws, const FilterHost& fh, co
     CandView cv;
     cv.keys = sb.cand_keys;
     cv.bound = sb.cand_bound;
+    cv.gtau = sb.gtau;
+    CU(cudaMemsetAsync(sb.gtau, 0, B * 8, s));
     cv.G = G;
     cv.KP = KP;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -661,6 +664,7 @@ static size_t carve_bufs(void* base, const cx_index* h, uint64_t B, uint32_t ldq
   sb->excl = c.take<uint32_t>(n_excl + 1);
   sb->cand_keys = c.take<uint64_t>((size_t)B * G * KP);
   sb->cand_bound = c.take<uint64_t>((size_t)B * G);
+  sb->gtau = c.take<uint64_t>(B);
   sb->n = c.take<uint32_t>(B);
   sb->ok = c.take<uint32_t>(B);
   sb->n_total = c.take<uint32_t>(4);

@@ -31,6 +31,7 @@ struct QueryView {
 struct CandView {
   uint64_t* keys;   // [nq][G][KP] descending, 0 padded
   uint64_t* bound;  // [nq][G] upper bound (key) of anything the group dropped; 0 = nothing dropped
+  uint64_t* gtau;   // [nq] cross-group running cut-off (max of the groups' KP-th best keys); zeroed per call
   uint32_t G, KP;
 };
 

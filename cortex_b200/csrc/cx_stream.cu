@@ -1,15 +1,19 @@
 // cx_stream.cu -- K1: small-batch streaming fp32 scan (HBM-bound).
 //
 // One persistent CTA per SM.  A producer thread streams 32-row tiles of the
-// row-major embedding matrix into a shared-memory ring with 1-D bulk async
-// copies (cp.async.bulk -> UBLKCP, completion on mbarriers); eight consumer
-// warps take four rows each, lanes split the dimension (conflict-free LDS.128),
-// accumulate NQ query dot products per row with FFMA, and finish with a
-// transposing warp reduction so every lane ends up owning one (row, query)
-// score.  Scores only nominate candidates: each CTA keeps a per-query list in
-// shared memory with a running cut-off (the KP-th best key seen so far), and the
-// lists are merged, rescored with reference arithmetic and verified by
-// cx_select.cu.  The matrix is read exactly once per pass:
+// row-major embedding matrix (plus the 32 reciprocal norms that go with them)
+// into a shared-memory ring with 1-D bulk async copies (cp.async.bulk -> UBLKCP,
+// completion on mbarriers).  Sixteen consumer warps work as two groups that take
+// alternate tiles; inside a group every warp owns four rows, lanes split the
+// dimension (conflict-free LDS.128), NQ query dot products per row accumulate
+// with FFMA, and a transposing warp reduction leaves every lane with one
+// (row, query) score.
+//
+// Scores only nominate candidates.  Each CTA keeps a per-query candidate list in
+// shared memory with a running cut-off tau (the KP-th best key seen so far, shared
+// across CTAs through one global word per query), so after the first few tiles a
+// score costs one compare.  Lists are merged, rescored with reference arithmetic
+// and verified by cx_select.cu.  The matrix is read exactly once per pass:
 //   algorithmic bytes per pass = n_rows * ld * 4   
 //
 // Call shapes served (reference): search() at B=1 (api.rs:117-125,
@@ -19,12 +23,15 @@
 
 namespace cx {
 
-constexpr int SC_W = 8;                       // consumer warps
-constexpr int SC_THREADS = 32 * (SC_W + 1);   // + 1 producer warp
-constexpr int SC_R = 4;                       // rows per warp per tile
-constexpr int SC_TILE_ROWS = SC_W * SC_R;     // 32
-constexpr int SC_CHECK = 4;                   // tiles between list checks
-constexpr int SC_KSLICE = 384;                // floats of a row per stage (<= 48 KB stages)
+constexpr int SC_GW = 8;                         // warps per consumer group
+constexpr int SC_GROUPS = 2;                     // groups take alternate tiles
+constexpr int SC_CW = SC_GW * SC_GROUPS;         // consumer warps
+constexpr int SC_CT = SC_CW * 32;                // consumer threads
+constexpr int SC_THREADS = SC_CT + 32;           // + 1 producer warp
+constexpr int SC_R = 4;                          // rows per warp per tile
+constexpr int SC_TILE_ROWS = SC_GW * SC_R;       // 32
+constexpr int SC_QUAD = 4;                       // tiles between list checks
+constexpr int SC_KSLICE = 384;                   // floats of a row per stage (<= 48 KB stages)
 constexpr int SC_MAX_STAGES = 4;
 constexpr size_t SC_SMEM_LIMIT = 227 * 1024;
 
@@ -36,6 +43,7 @@ struct StreamParams {
   DevFilter flt;
   uint64_t* keys;    // &cand.keys[q0][0][0]
   uint64_t* bound;   // &cand.bound[q0][0]
+  uint64_t* gtau;    // &cand.gtau[q0]   (zeroed before the pass)
   uint32_t G, KP, C, n_tiles, stages, kslice, n_slices;
 };
 
@@ -73,37 +81,48 @@ __device__ __forceinline__ uint32_t transpose_index(uint32_t lane) {
   return idx;
 }
 
-__host__ __device__ inline size_t stream_layout(uint32_t ld, uint32_t nq, uint32_t C, uint32_t stages,
-                                                uint32_t kslice, size_t* off_q, size_t* off_list,
-                                                size_t* off_tau, size_t* off_cnt, size_t* off_bars) {
-  size_t o = (size_t)stages * SC_TILE_ROWS * kslice * 4;
-  *off_q = o;
+struct StreamLayout {
+  size_t tiles, rn, q, list, tau, cnt, bars, total;
+};
+
+__host__ __device__ inline StreamLayout stream_layout(uint32_t ld, uint32_t nq, uint32_t C, uint32_t stages,
+                                                      uint32_t kslice) {
+  StreamLayout L;
+  size_t o = 0;
+  L.tiles = o;
+  o += (size_t)stages * SC_TILE_ROWS * kslice * 4;
+  L.rn = o;
+  o += (size_t)SC_MAX_STAGES * SC_TILE_ROWS * 4;
+  L.q = o;
   o += (size_t)nq * ld * 4;
   o = (o + 15) & ~(size_t)15;
-  *off_list = o;
-  o += (size_t)nq * C * 8;
-  *off_tau = o;
+  L.list = o;
+  o += (size_t)nq * 2 * C * 8;  // double buffered
+  L.tau = o;
   o += (size_t)nq * 8;
-  *off_cnt = o;
-  o += (size_t)(nq + 4) * 4;  // cnt[nq] + flag
+  L.cnt = o;
+  o += (size_t)(2 * nq + 4) * 4;  // cnt[nq], cur[nq], flag
   o = (o + 7) & ~(size_t)7;
-  *off_bars = o;
+  L.bars = o;
   o += (size_t)2 * SC_MAX_STAGES * 8;
-  return o;
+  L.total = o;
+  return L;
 }
 
-template <int NQ>
+// KC > 0: the slice is exactly KC chunks of 128 floats (fully unrolled inner loop)
+template <int NQ, int KC>
 __global__ void __launch_bounds__(SC_THREADS, 1) stream_scan_kernel(const StreamParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  size_t off_q, off_list, off_tau, off_cnt, off_bars;
-  stream_layout(p.st.ld, NQ, p.C, p.stages, p.kslice, &off_q, &off_list, &off_tau, &off_cnt, &off_bars);
-  float* tiles = reinterpret_cast<float*>(smem_raw);
-  float* q_s = reinterpret_cast<float*>(smem_raw + off_q);
-  uint64_t* list_s = reinterpret_cast<uint64_t*>(smem_raw + off_list);
-  uint64_t* tau_s = reinterpret_cast<uint64_t*>(smem_raw + off_tau);
-  uint32_t* cnt_s = reinterpret_cast<uint32_t*>(smem_raw + off_cnt);
-  uint32_t* flag_s = cnt_s + NQ;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + off_bars);
+  const StreamLayout L = stream_layout(p.st.ld, NQ, p.C, p.stages, p.kslice);
+  float* tiles = reinterpret_cast<float*>(smem_raw + L.tiles);
+  float* rn_s = reinterpret_cast<float*>(smem_raw + L.rn);
+  float* q_s = reinterpret_cast<float*>(smem_raw + L.q);
+  uint64_t* list_s = reinterpret_cast<uint64_t*>(smem_raw + L.list);
+  uint64_t* tau_s = reinterpret_cast<uint64_t*>(smem_raw + L.tau);
+  uint32_t* cnt_s = reinterpret_cast<uint32_t*>(smem_raw + L.cnt);
+  uint32_t* cur_s = cnt_s + NQ;
+  uint32_t* flag_s = cnt_s + 2 * NQ;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L.bars);
 
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t ld = p.st.ld, ld4 = ld >> 2, S = p.stages;
@@ -113,11 +132,10 @@ __global__ void __launch_bounds__(SC_THREADS, 1) stream_scan_kernel(const Stream
   if (tid == 0) {
     for (uint32_t s = 0; s < S; ++s) {
       mbar_init(full0 + 8 * s, 1);
-      mbar_init(empty0 + 8 * s, SC_W);
+      mbar_init(empty0 + 8 * s, SC_GW);
     }
     fence_mbar_init();
   }
-  // queries -> smem (stride ld), lists cleared
   for (uint32_t i = tid; i < NQ * ld; i += SC_THREADS) {
     uint32_t b = i / ld, d = i % ld;
     q_s[i] = (b < p.nq_valid) ? p.Q[(size_t)b * p.ldq + d] : 0.0f;
@@ -125,12 +143,13 @@ __global__ void __launch_bounds__(SC_THREADS, 1) stream_scan_kernel(const Stream
   for (uint32_t i = tid; i < NQ; i += SC_THREADS) {
     tau_s[i] = 0;
     cnt_s[i] = 0;
+    cur_s[i] = 0;
   }
   __syncthreads();
 
   const uint32_t my_tiles = (p.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
 
-  if (warp == SC_W) {
+  if (warp == SC_CW) {
     // ---------------- producer ----------------
     if (lane == 0) {
       uint32_t it = 0;
@@ -145,15 +164,18 @@ __global__ void __launch_bounds__(SC_THREADS, 1) stream_scan_kernel(const Stream
           const uint32_t k0 = sl * p.kslice;
           const uint32_t klen = min(p.kslice, ld - k0);
           const uint32_t bar = full0 + 8 * stage;
+          const bool last = sl + 1 == p.n_slices;
+          const uint32_t rn_bytes = last ? ((rows_here + 3) & ~3u) * 4 : 0;
           if (p.n_slices == 1) {
             const uint32_t bytes = rows_here * ld * 4;
-            mbar_arrive_expect_tx(bar, bytes);
+            mbar_arrive_expect_tx(bar, bytes + rn_bytes);
             bulk_g2s(dst, p.st.E + (size_t)r0 * ld, bytes, bar);
           } else {
-            mbar_arrive_expect_tx(bar, rows_here * klen * 4);
+            mbar_arrive_expect_tx(bar, rows_here * klen * 4 + rn_bytes);
             for (uint32_t r = 0; r < rows_here; ++r)
               bulk_g2s(dst + r * p.kslice * 4, p.st.E + (size_t)(r0 + r) * ld + k0, klen * 4, bar);
           }
+          if (last) bulk_g2s(smem_u32(rn_s + stage * SC_TILE_ROWS), p.st.rnorm + r0, rn_bytes, bar);
         }
       }
     }
@@ -161,7 +183,9 @@ __global__ void __launch_bounds__(SC_THREADS, 1) stream_scan_kernel(const Stream
   }
 
   // ---------------- consumers ----------------
-  const uint32_t ctid = tid;  // 0..255
+  const uint32_t ctid = tid;             // 0..SC_CT-1
+  const uint32_t grp = warp / SC_GW;     // which alternate tiles
+  const uint32_t gwarp = warp % SC_GW;   // row block inside the tile
   constexpr int NV = SC_R * NQ;
   const uint32_t idx = transpose_index<NV>(lane);
   const bool leader = (lane & ((32u / NV) - 1u)) == 0;  // NV <= 32
@@ -169,30 +193,41 @@ __global__ void __launch_bounds__(SC_THREADS, 1) stream_scan_kernel(const Stream
   const float my_rqn = (my_b < p.nq_valid) ? __ldg(p.rqn + my_b) : 0.0f;
   const float4* q4 = reinterpret_cast<const float4*>(q_s);
   const uint32_t kslice4 = p.kslice >> 2;
+  const uint32_t C = p.C, KP = p.KP;
 
-  auto csync = [] { named_bar_sync(1, SC_W * 32); };
+  auto csync = [] { named_bar_sync(1, SC_CT); };
 
-  auto compact = [&](uint32_t b, bool final_pass) {
-    // all consumer threads; list[b] sorted descending, truncated to KP
-    uint64_t* L = list_s + (size_t)b * p.C;
-    uint32_t n = min(cnt_s[b], p.C);
+  // Keep the KP best of list[b] (rank by counting; keys are distinct), sorted, in the
+  // other half of the double buffer; publish / adopt the global cut-off.
+  auto compact = [&](uint32_t b) {
+    const uint32_t n = min(cnt_s[b], C);
+    const uint32_t cur = cur_s[b];
+    const uint64_t* src = list_s + ((size_t)b * 2 + cur) * C;
+    uint64_t* dst = list_s + ((size_t)b * 2 + (cur ^ 1)) * C;
     csync();
-    for (uint32_t i = ctid; i < p.C; i += SC_W * 32)
-      if (i >= n) L[i] = 0;
+    for (uint32_t i = ctid; i < n; i += SC_CT) {
+      const uint64_t key = src[i];
+      uint32_t rank = 0;
+      for (uint32_t j = 0; j < n; ++j) rank += src[j] > key;
+      if (rank < KP) dst[rank] = key;
+    }
     csync();
-    bitonic_sort_desc(L, p.C, ctid, SC_W * 32, csync);
     if (ctid == 0) {
-      if (n > p.KP) {
-        tau_s[b] = L[p.KP - 1];
-        cnt_s[b] = p.KP;
+      cnt_s[b] = min(n, KP);
+      cur_s[b] = cur ^ 1;
+      if (n >= KP) {
+        uint64_t t = dst[KP - 1];
+        const uint64_t g = atomicMax(reinterpret_cast<unsigned long long*>(p.gtau + b), (unsigned long long)t);
+        if (g > t) t = g;
+        if (t > tau_s[b]) tau_s[b] = t;
       }
     }
-    (void)final_pass;
     csync();
   };
 
-  uint32_t it = 0;
-  for (uint32_t i = 0; i < my_tiles; ++i) {
+  const uint32_t n_quads = my_tiles / SC_QUAD;  // full quads: both groups see the same count
+
+  for (uint32_t i = grp; i < my_tiles; i += SC_GROUPS) {
     const uint32_t t = blockIdx.x + i * gridDim.x;
     float acc[SC_R][NQ];
 #pragma unroll
@@ -200,28 +235,52 @@ __global__ void __launch_bounds__(SC_THREADS, 1) stream_scan_kernel(const Stream
 #pragma unroll
       for (int b = 0; b < NQ; ++b) acc[r][b] = 0.0f;
 
-    for (uint32_t sl = 0; sl < p.n_slices; ++sl, ++it) {
+    float my_rn = 0.0f;
+    for (uint32_t sl = 0; sl < p.n_slices; ++sl) {
+      const uint32_t it = i * p.n_slices + sl;
       const uint32_t stage = it % S;
       mbar_wait(full0 + 8 * stage, (it / S) & 1);
-      const float4* tile4 = reinterpret_cast<const float4*>(tiles + (size_t)stage * tile_floats);
+      const float4* tile4 = reinterpret_cast<const float4*>(tiles + (size_t)stage * tile_floats) +
+                            (size_t)(gwarp * SC_R) * kslice4;
       const uint32_t k0_4 = (sl * p.kslice) >> 2;
-      const uint32_t klen4 = min(kslice4, ld4 - k0_4);
-      for (uint32_t c = lane; c < klen4; c += 32) {
-        float4 e[SC_R];
+      if (KC > 0) {
 #pragma unroll
-        for (int r = 0; r < SC_R; ++r) e[r] = tile4[(warp * SC_R + r) * kslice4 + c];
+        for (int c = 0; c < (KC > 0 ? KC : 1); ++c) {
+          float4 e[SC_R];
 #pragma unroll
-        for (int b = 0; b < NQ; ++b) {
-          const float4 qv = q4[b * ld4 + k0_4 + c];
+          for (int r = 0; r < SC_R; ++r) e[r] = tile4[r * kslice4 + c * 32 + lane];
 #pragma unroll
-          for (int r = 0; r < SC_R; ++r) {
-            acc[r][b] = fmaf(e[r].x, qv.x, acc[r][b]);
-            acc[r][b] = fmaf(e[r].y, qv.y, acc[r][b]);
-            acc[r][b] = fmaf(e[r].z, qv.z, acc[r][b]);
-            acc[r][b] = fmaf(e[r].w, qv.w, acc[r][b]);
+          for (int b = 0; b < NQ; ++b) {
+            const float4 qv = q4[b * ld4 + k0_4 + c * 32 + lane];
+#pragma unroll
+            for (int r = 0; r < SC_R; ++r) {
+              acc[r][b] = fmaf(e[r].x, qv.x, acc[r][b]);
+              acc[r][b] = fmaf(e[r].y, qv.y, acc[r][b]);
+              acc[r][b] = fmaf(e[r].z, qv.z, acc[r][b]);
+              acc[r][b] = fmaf(e[r].w, qv.w, acc[r][b]);
+            }
+          }
+        }
+      } else {
+        const uint32_t klen4 = min(kslice4, ld4 - k0_4);
+        for (uint32_t c = lane; c < klen4; c += 32) {
+          float4 e[SC_R];
+#pragma unroll
+          for (int r = 0; r < SC_R; ++r) e[r] = tile4[r * kslice4 + c];
+#pragma unroll
+          for (int b = 0; b < NQ; ++b) {
+            const float4 qv = q4[b * ld4 + k0_4 + c];
+#pragma unroll
+            for (int r = 0; r < SC_R; ++r) {
+              acc[r][b] = fmaf(e[r].x, qv.x, acc[r][b]);
+              acc[r][b] = fmaf(e[r].y, qv.y, acc[r][b]);
+              acc[r][b] = fmaf(e[r].z, qv.z, acc[r][b]);
+              acc[r][b] = fmaf(e[r].w, qv.w, acc[r][b]);
+            }
           }
         }
       }
+      if (sl + 1 == p.n_slices) my_rn = rn_s[stage * SC_TILE_ROWS + gwarp * SC_R + my_r];
       __syncwarp();
       if (lane == 0) mbar_arrive(empty0 + 8 * stage);
     }
@@ -233,46 +292,50 @@ __global__ void __launch_bounds__(SC_THREADS, 1) stream_scan_kernel(const Stream
       for (int b = 0; b < NQ; ++b) v[r * NQ + b] = acc[r][b];
     const float total = warp_transpose_reduce<NV>(v, lane);
 
-    const uint32_t row = t * SC_TILE_ROWS + warp * SC_R + my_r;
+    const uint32_t row = t * SC_TILE_ROWS + gwarp * SC_R + my_r;
     if (leader && row < p.st.n_rows && my_b < p.nq_valid) {
-      const float approx = total * __ldg(p.st.rnorm + row) * my_rqn;
+      const float approx = total * my_rn * my_rqn;
       if (approx == approx) {
         const uint64_t key = make_key(ord_from_float(approx), row);
         if (key > *((volatile uint64_t*)(tau_s + my_b))) {
           if (row_passes(p.flt, p.st.meta, p.st.agent, row)) {
-            uint32_t pos = atomicAdd(cnt_s + my_b, 1u);
-            if (pos < p.C) list_s[(size_t)my_b * p.C + pos] = key;
+            const uint32_t pos = atomicAdd(cnt_s + my_b, 1u);
+            const uint32_t cur = *((volatile uint32_t*)(cur_s + my_b));
+            if (pos < C) list_s[((size_t)my_b * 2 + cur) * C + pos] = key;
           }
         }
       }
     }
 
-    if ((i + 1) % SC_CHECK == 0 && i + 1 < my_tiles) {
+    // checkpoint after the last tile of every full quad (tile i%4 == 2 for group 0, 3 for group 1)
+    if ((i % SC_QUAD) == (SC_QUAD - SC_GROUPS + grp) && (i / SC_QUAD) < n_quads) {
       csync();
+      if (ctid < NQ) {
+        const uint64_t g = *((volatile uint64_t*)(p.gtau + ctid));
+        if (g > tau_s[ctid]) tau_s[ctid] = g;
+      }
       if (ctid == 0) {
         uint32_t m = 0;
         for (uint32_t b = 0; b < NQ; ++b)
-          if (cnt_s[b] + SC_CHECK * SC_TILE_ROWS > p.C) m |= 1u << b;
+          if (cnt_s[b] >= 2 * KP || cnt_s[b] + SC_QUAD * SC_TILE_ROWS > C) m |= 1u << b;
         *flag_s = m;
       }
       csync();
       const uint32_t m = *flag_s;
       for (uint32_t b = 0; b < NQ; ++b)
-        if (m & (1u << b)) compact(b, false);
+        if (m & (1u << b)) compact(b);
     }
   }
 
-  // final: sort every list, emit the head
+  // final: rank every list, emit the head and the drop bound
   csync();
   for (uint32_t b = 0; b < p.nq_valid; ++b) {
-    const uint32_t n_before = min(cnt_s[b], p.C);
-    const uint64_t tau_before = tau_s[b];
-    compact(b, true);
-    const uint64_t* L = list_s + (size_t)b * p.C;
-    uint64_t* out = p.keys + ((size_t)b * p.G + blockIdx.x) * p.KP;
-    const uint32_t n_keep = min(n_before, p.KP);
-    for (uint32_t j = ctid; j < p.KP; j += SC_W * 32) out[j] = j < n_keep ? L[j] : 0;
-    if (ctid == 0) p.bound[(size_t)b * p.G + blockIdx.x] = (n_before > p.KP) ? L[p.KP - 1] : tau_before;
+    compact(b);
+    const uint64_t* Lb = list_s + ((size_t)b * 2 + cur_s[b]) * C;
+    const uint32_t n_keep = cnt_s[b];
+    uint64_t* out = p.keys + ((size_t)b * p.G + blockIdx.x) * KP;
+    for (uint32_t j = ctid; j < KP; j += SC_CT) out[j] = j < n_keep ? Lb[j] : 0;
+    if (ctid == 0) p.bound[(size_t)b * p.G + blockIdx.x] = tau_s[b];
     csync();
   }
 }
@@ -288,16 +351,24 @@ static uint32_t pow2_at_least(uint32_t x) {
   return p;
 }
 
-static uint32_t stream_list_cap(uint32_t KP) { return pow2_at_least(KP + 2 * SC_CHECK * SC_TILE_ROWS); }
+// floats of a row per stage: the whole row if it fits 48 KB stages, else the largest
+// multiple of 128 that divides the row (unrolled kernel variant), else 384
+static uint32_t stream_pick_kslice(uint32_t ld) {
+  if (ld <= (uint32_t)SC_KSLICE) return ld;
+  for (uint32_t ks = SC_KSLICE; ks >= 128; ks -= 128)
+    if (ld % ks == 0) return ks;
+  return SC_KSLICE;
+}
+
+static uint32_t stream_list_cap(uint32_t KP) { return pow2_at_least(2 * KP + SC_QUAD * SC_TILE_ROWS); }
 
 static uint32_t stream_pick_stages(uint32_t ld, uint32_t nq, uint32_t KP, size_t* total) {
-  uint32_t kslice = ld < (uint32_t)SC_KSLICE ? ld : SC_KSLICE;
+  uint32_t kslice = stream_pick_kslice(ld);
   uint32_t C = stream_list_cap(KP);
   for (uint32_t s = SC_MAX_STAGES; s >= 2; --s) {
-    size_t a, b, c, d, e;
-    size_t bytes = stream_layout(ld, nq, C, s, kslice, &a, &b, &c, &d, &e);
-    if (bytes <= SC_SMEM_LIMIT) {
-      *total = bytes;
+    StreamLayout L = stream_layout(ld, nq, C, s, kslice);
+    if (L.total <= SC_SMEM_LIMIT) {
+      *total = L.total;
       return s;
     }
   }
@@ -311,20 +382,33 @@ size_t stream_scan_smem(uint32_t ld, uint32_t nq_pass, uint32_t KP) {
   return s ? total : 0;
 }
 
-template <int NQ>
-static cudaError_t launch_nq(const StreamParams& p, size_t smem, cudaStream_t s) {
-  cudaError_t e = cudaFuncSetAttribute(stream_scan_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+template <int NQ, int KC>
+static cudaError_t launch_one(const StreamParams& p, size_t smem, cudaStream_t s) {
+  cudaError_t e = cudaFuncSetAttribute(stream_scan_kernel<NQ, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem);
   if (e != cudaSuccess) return e;
-  stream_scan_kernel<NQ><<<p.G, SC_THREADS, smem, s>>>(p);
+  stream_scan_kernel<NQ, KC><<<p.G, SC_THREADS, smem, s>>>(p);
   return cudaGetLastError();
+}
+
+template <int NQ>
+static cudaError_t launch_nq(const StreamParams& p, size_t smem, cudaStream_t s) {
+  // unrolled variants for slices that are exactly 1, 2 or 3 chunks of 128 floats
+  const bool even = (p.st.ld % p.kslice) == 0 && (p.kslice % 128) == 0;
+  const uint32_t kc = even ? p.kslice / 128 : 0;
+  switch (kc) {
+    case 1: return launch_one<NQ, 1>(p, smem, s);
+    case 2: return launch_one<NQ, 2>(p, smem, s);
+    case 3: return launch_one<NQ, 3>(p, smem, s);
+    default: return launch_one<NQ, 0>(p, smem, s);
+  }
 }
 
 cudaError_t launch_stream_scan(const StoreView& st, const QueryView& qv, uint32_t q0, uint32_t nq_pass,
                                const DevFilter& flt, const CandView& cv, int sm_count, cudaStream_t s) {
   if (!st.n_rows || !nq_pass) return cudaSuccess;
-  uint32_t nq_t = nq_pass <= 1 ? 1 : nq_pass <= 2 ? 2 : nq_pass <= 4 ? 4 : 8;
   if (nq_pass > 8) return cudaErrorInvalidValue;
+  const uint32_t nq_t = nq_pass <= 1 ? 1 : nq_pass <= 2 ? 2 : nq_pass <= 4 ? 4 : 8;
   StreamParams p;
   p.st = st;
   p.Q = qv.Q + (size_t)q0 * qv.ldq;
@@ -336,9 +420,10 @@ cudaError_t launch_stream_scan(const StoreView& st, const QueryView& qv, uint32_
   p.KP = cv.KP;
   p.keys = cv.keys + (size_t)q0 * cv.G * cv.KP;
   p.bound = cv.bound + (size_t)q0 * cv.G;
+  p.gtau = cv.gtau + q0;
   p.C = stream_list_cap(cv.KP);
   p.n_tiles = (st.n_rows + SC_TILE_ROWS - 1) / SC_TILE_ROWS;
-  p.kslice = st.ld < (uint32_t)SC_KSLICE ? st.ld : SC_KSLICE;
+  p.kslice = stream_pick_kslice(st.ld);
   p.n_slices = (st.ld + p.kslice - 1) / p.kslice;
   size_t smem;
   p.stages = stream_pick_stages(st.ld, nq_t, cv.KP, &smem);

@@ -70,9 +70,9 @@ class ShardedSearch:
 
     def search(self, queries: torch.Tensor, k: int):
         rows, score, d, n = self.local_search(queries, k)
+        if self.world == 1:  # nothing to exchange: the local list is already the answer
+            return rows.to(torch.int64) + self.row_offset, score, d, n
         key = pack_keys(rows, score, n, self.row_offset)
-        if self.world == 1:
-            return merge_gathered(key[None], d[None], k)
         payload = torch.stack([key, d.contiguous().view(torch.int32).to(torch.int64)], dim=0)  # [2,B,k]
         flat = torch.empty((self.world * 2,) + tuple(payload.shape[1:]), dtype=payload.dtype,
                            device=payload.device)
