@@ -27,12 +27,15 @@ struct QueryView {
   uint32_t nq, qlen, ldq;
 };
 
-// Per-(query, producer group) candidate lists written by a fast pass.
+// Candidates nominated by a fast pass: one merged, unordered key list per query.
+// cnt and gtau must be zero when a pass starts; the select kernel re-zeroes them.
 struct CandView {
-  uint64_t* keys;   // [nq][G][KP] descending, 0 padded
-  uint64_t* bound;  // [nq][G] upper bound (key) of anything the group dropped; 0 = nothing dropped
-  uint64_t* gtau;   // [nq] cross-group running cut-off (max of the groups' KP-th best keys); zeroed per call
-  uint32_t G, KP;
+  uint64_t* keys;   // [nq][cap]
+  uint32_t* cnt;    // [nq] entries appended (may exceed cap: the excess was dropped)
+  uint64_t* gtau;   // [nq] running cut-off shared by all producer groups; at the end of the
+                    //      pass it bounds (as a key) every row that is NOT in the list
+  uint32_t cap;     // list capacity per query
+  uint32_t G, KP;   // producer groups, keys kept per group
 };
 
 struct ResultView {
@@ -61,9 +64,12 @@ cudaError_t launch_stream_scan(const StoreView& st, const QueryView& qv, uint32_
 
 // K5 + K3: merge candidate lists, exact rescore, verify, emit results.
 // eps_cos: bound on |approx - reference| cosine for the pass that produced the candidates.
-size_t select_smem(uint32_t G, uint32_t KP, uint32_t ld);
+// It also computes the query norms (qv.qnorm / qv.rqnorm are written) and re-zeroes cv.cnt / cv.gtau.
+// scale_by_rqn: the pass's keys are cosine * |q| (streaming pass) instead of cosine.
+size_t select_smem(uint32_t cap, uint32_t ld);
 cudaError_t launch_select_rescore(const StoreView& st, const QueryView& qv, uint32_t q0, uint32_t nq,
-                                  const CandView& cv, const ResultView& rv, float eps_cos, cudaStream_t s);
+                                  const CandView& cv, const ResultView& rv, float eps_cos, int scale_by_rqn,
+                                  cudaStream_t s);
 
 // Exact path: every row scored with reference arithmetic -> keys[n_rows] for one query
 void launch_exact_keys(const StoreView& st, const QueryView& qv, uint32_t q, const DevFilter& flt,

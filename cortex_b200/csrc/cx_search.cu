@@ -1,0 +1,418 @@
+// cx_search.cu -- search entry points of the C ABI: VectorIndex::search /
+// search_threshold / search_batch (vector/index.rs:325-410) and the device-resident
+// batch form.  Path selection per call:
+//
+//   small query groups  -> K1 streaming fp32 pass (cx_stream.cu)   } nominate candidates,
+//   large query groups  -> K2 tcgen05 bf16 pass  (cx_tensor.cu)    } then K5/K3 select +
+//                                                                  } exact rescore + verify
+//   tiny indexes, huge k, threshold scans, mismatched query length, and every query
+//   whose fast result could not be verified -> exact path (cx_exact.cu): reference
+//   arithmetic for every row + radix sort.
+//
+// Whatever the path, emitted scores/distances come from the reference's operation
+// sequence, and ids follow (score desc, NaN last, row asc).
+#include "cx_index.h"
+
+using namespace cx;
+
+namespace {
+
+struct FilterHost {
+  DevFilter dev;
+  std::vector<uint32_t> excl_rows;
+};
+
+void build_filter(const cx_index* h, const cx_filter* f, FilterHost* out) {
+  DevFilter& d = out->dev;
+  memset(&d, 0, sizeof d);
+  d.agent = AGENT_NONE;
+  if (!f) return;
+  if (f->has_kinds) {
+    d.has_kinds = 1;
+    for (uint32_t i = 0; i < f->n_kinds; ++i) {
+      uint32_t id;
+      if (f->kinds && f->kinds[i] && h->kinds.find(f->kinds[i], &id)) d.kind_mask[id >> 6] |= 1ull << (id & 63);
+    }
+  }
+  if (f->has_source_agent) {
+    d.has_agent = 1;
+    uint32_t id;
+    if (f->source_agent && h->agents.find(f->source_agent, &id)) d.agent = id;
+  }
+  if (f->has_exclude && f->exclude_ids) {
+    for (uint32_t i = 0; i < f->n_exclude; ++i) {
+      auto it = h->id2row.find(load_id(f->exclude_ids + 16 * i));
+      if (it != h->id2row.end()) out->excl_rows.push_back(it->second);
+    }
+  }
+}
+
+// keys kept per producer group: k plus a margin for near-ties, bounded so that the
+// merged list of all groups still fits the select kernel's shared memory
+uint32_t keep_count(uint32_t k, uint32_t G) {
+  uint32_t margin = k / 4;
+  if (margin < 16) margin = 16;
+  if (margin > 32) margin = 32;
+  uint32_t KP = k + margin;
+  while (KP > k && (uint64_t)KP * G > 16384) --KP;
+  return KP;
+}
+
+// bound on |approximate - reference| cosine for the fp32 streaming pass
+float eps_stream(uint32_t dim) { return (2.1f * (float)dim + 16.0f) * 5.9604645e-8f; }
+
+// Contiguous result block: one D2H copy brings everything the host needs.
+struct ResultBlock {
+  size_t ok, n, rows, score, dist, ids, total;
+  static ResultBlock make(uint64_t B, uint32_t kd) {
+    ResultBlock r;
+    size_t o = 0;
+    r.ok = o;
+    o += align_up(B * 4, 16);
+    r.n = o;
+    o += align_up(B * 4, 16);
+    r.rows = o;
+    o += align_up(B * kd * 4, 16);
+    r.score = o;
+    o += align_up(B * kd * 4, 16);
+    r.dist = o;
+    o += align_up(B * kd * 4, 16);
+    r.ids = o;
+    o += align_up(B * kd * 16, 16);
+    r.total = o;
+    return r;
+  }
+};
+
+struct Carver {
+  char* base;
+  size_t off = 0;
+  explicit Carver(void* b) : base((char*)b) {}
+  template <typename T>
+  T* take(size_t n) {
+    off = align_up(off, 256);
+    T* p = base ? (T*)(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+struct SearchBufs {
+  float* dQ = nullptr;
+  float* qnorm = nullptr;
+  float* rqnorm = nullptr;
+  uint32_t* excl = nullptr;
+  uint64_t* cand_keys = nullptr;
+  char* res = nullptr;       // ResultBlock (device) when results are workspace-owned
+  uint32_t* ok = nullptr;
+  uint32_t* n = nullptr;
+  uint32_t* rows = nullptr;
+  float* score = nullptr;
+  float* dist = nullptr;
+  uint8_t* ids = nullptr;
+  uint64_t* ekeys_a = nullptr;
+  uint64_t* ekeys_b = nullptr;
+  void* sort_tmp = nullptr;
+  size_t sort_tmp_bytes = 0;
+  uint32_t* n_total = nullptr;
+};
+
+struct Plan {
+  uint64_t B;
+  uint32_t qlen, ldq, kd;
+  uint32_t G, KP, cap;
+  bool fast;
+};
+
+Plan make_plan(const cx_index* h, uint64_t B, uint32_t qlen, uint32_t ldq, uint32_t kd, bool threshold_mode) {
+  Plan p;
+  p.B = B;
+  p.qlen = qlen;
+  p.ldq = ldq;
+  p.kd = kd;
+  const uint32_t n_rows = (uint32_t)h->n_rows;
+  p.G = stream_scan_groups(n_rows, h->sm_count);
+  p.KP = keep_count(kd, p.G);
+  p.cap = p.G * p.KP;
+  p.fast = !threshold_mode && qlen == h->dim && n_rows >= 256 && kd <= 128 && p.KP >= kd &&
+           stream_scan_smem(h->ld, 8, p.KP) != 0 && select_smem(p.cap, h->ld) <= 227 * 1024 &&
+           h->force_path != PATH_EXACT;
+  return p;
+}
+
+size_t carve_bufs(void* base, const cx_index* h, const Plan& pl, uint32_t n_excl, bool own_queries,
+                  bool own_results, SearchBufs* sb) {
+  Carver c(base);
+  const uint32_t n_rows = (uint32_t)h->n_rows;
+  sb->dQ = own_queries ? c.take<float>(pl.B * pl.ldq) : nullptr;
+  sb->qnorm = c.take<float>(pl.B);
+  sb->rqnorm = c.take<float>(pl.B);
+  sb->excl = c.take<uint32_t>(n_excl + 1);
+  sb->cand_keys = pl.fast ? c.take<uint64_t>((size_t)pl.B * pl.cap) : nullptr;
+  sb->n_total = c.take<uint32_t>(4);
+  const ResultBlock rb = ResultBlock::make(pl.B, pl.kd);
+  if (own_results) {
+    sb->res = c.take<char>(rb.total);
+    if (sb->res) {
+      sb->ok = (uint32_t*)(sb->res + rb.ok);
+      sb->n = (uint32_t*)(sb->res + rb.n);
+      sb->rows = (uint32_t*)(sb->res + rb.rows);
+      sb->score = (float*)(sb->res + rb.score);
+      sb->dist = (float*)(sb->res + rb.dist);
+      sb->ids = (uint8_t*)(sb->res + rb.ids);
+    }
+  } else {
+    sb->ok = c.take<uint32_t>(pl.B);
+  }
+  sb->ekeys_a = c.take<uint64_t>(n_rows);
+  sb->ekeys_b = c.take<uint64_t>(n_rows);
+  sb->sort_tmp_bytes = exact_sort_tmp_bytes(n_rows);
+  sb->sort_tmp = c.take<char>(sb->sort_tmp_bytes);
+  return align_up(c.off, 256);
+}
+
+// Core.  Queries are on the device at sb.dQ [B][ldq]; results land in sb.rows/score/
+// dist/ids/n (device).  If h_block != nullptr the whole ResultBlock is also copied to
+// it (pinned host).  h_ok: pinned host scratch of B words.  Returns with the stream idle.
+cx_status run_search(cx_index* h, Workspace* ws, const FilterHost& fh, const SearchBufs& sb, const Plan& pl,
+                     bool threshold_mode, float threshold, char* h_block, uint32_t* h_ok,
+                     uint64_t* h_total /* threshold mode: per-query totals */) {
+  cudaStream_t s = ws->stream;
+  const uint64_t B = pl.B;
+  StoreView st = h->view();
+  QueryView qv;
+  qv.Q = sb.dQ;
+  qv.qnorm = sb.qnorm;
+  qv.rqnorm = sb.rqnorm;
+  qv.nq = (uint32_t)B;
+  qv.qlen = pl.qlen;
+  qv.ldq = pl.ldq;
+  DevFilter flt = fh.dev;
+  flt.excl_rows = sb.excl;
+  flt.n_excl = (uint32_t)fh.excl_rows.size();
+  if (flt.n_excl) CU(cudaMemcpyAsync(sb.excl, fh.excl_rows.data(), flt.n_excl * 4, cudaMemcpyHostToDevice, s));
+
+  ResultView rv;
+  rv.rows = sb.rows;
+  rv.score = sb.score;
+  rv.dist = sb.dist;
+  rv.ids = sb.ids;
+  rv.n = sb.n;
+  rv.ok = sb.ok;
+  rv.k = pl.kd;
+  const ResultBlock rb = ResultBlock::make(B, pl.kd);
+
+  if (h->force_path == PATH_STREAM && !pl.fast && !threshold_mode)
+    return fail(CX_ERR_VALIDATION, "force_path=stream but the call shape is not eligible");
+
+  std::vector<uint32_t> redo;
+  if (pl.fast) {
+    CU(ws->ensure_state(B));
+    ws->state_dirty = true;  // until the select kernel has re-zeroed it and the stream drained cleanly
+    CandView cv;
+    cv.keys = sb.cand_keys;
+    cv.cnt = ws->d_cnt;
+    cv.gtau = ws->d_gtau;
+    cv.cap = pl.cap;
+    cv.G = pl.G;
+    cv.KP = pl.KP;
+    uint32_t n_pass = 0;
+    if (h->profile) CU(cudaEventRecord(ws->ev0, s));
+    for (uint64_t q0 = 0; q0 < B; q0 += 8) {
+      const uint32_t nq = (uint32_t)(B - q0 < 8 ? B - q0 : 8);
+      CU(launch_stream_scan(st, qv, (uint32_t)q0, nq, flt, cv, h->sm_count, s));
+      ++n_pass;
+    }
+    if (h->profile) CU(cudaEventRecord(ws->ev1, s));
+    CU(launch_select_rescore(st, qv, 0, (uint32_t)B, cv, rv, eps_stream(h->dim), /*scale_by_rqn=*/1, s));
+    h->launches += n_pass + 1;
+    if (h_block) {
+      CU(cudaMemcpyAsync(h_block, sb.res, rb.total, cudaMemcpyDeviceToHost, s));
+      h_ok = (uint32_t*)(h_block + rb.ok);
+    } else {
+      CU(cudaMemcpyAsync(h_ok, sb.ok, B * 4, cudaMemcpyDeviceToHost, s));
+    }
+    CU(cudaStreamSynchronize(s));
+    ws->state_dirty = false;
+    if (h->profile) {
+      float ms = 0.f;
+      CU(cudaEventElapsedTime(&ms, ws->ev0, ws->ev1));
+      h->pass_ns += (uint64_t)(ms * 1e6);
+      h->pass_launches += n_pass;
+    }
+    for (uint64_t b = 0; b < B; ++b)
+      if (!h_ok[b]) redo.push_back((uint32_t)b);
+    h->q_stream += B - redo.size();
+    h->fallbacks += redo.size();
+    if (redo.empty()) return CX_OK;
+  } else {
+    launch_prepare_queries(sb.dQ, sb.qnorm, sb.rqnorm, (uint32_t)B, pl.qlen, pl.ldq, s);
+    h->launches += 1;
+    redo.resize(B);
+    for (uint64_t b = 0; b < B; ++b) redo[b] = (uint32_t)b;
+  }
+
+  // exact path
+  uint32_t min_ord = 1;  // every real key, NaN included (they sort last)
+  if (threshold_mode) {
+    if (threshold != threshold) min_ord = 0xFFFFFFFFu;  // score >= NaN is false
+    else min_ord = ord_from_score(threshold > 0.0f ? threshold : 0.0f);
+  }
+  for (uint32_t b : redo) {
+    launch_exact_keys(st, qv, b, flt, sb.ekeys_a, s);
+    CU(exact_sort(sb.ekeys_a, sb.ekeys_b, st.n_rows, sb.sort_tmp, sb.sort_tmp_bytes, s));
+    launch_exact_emit(st, qv, b, sb.ekeys_b, st.n_rows, pl.kd, min_ord, sb.rows + (size_t)b * pl.kd,
+                      sb.score + (size_t)b * pl.kd, sb.dist + (size_t)b * pl.kd,
+                      sb.ids ? sb.ids + (size_t)b * pl.kd * 16 : nullptr, sb.n + b, sb.n_total, s);
+    h->launches += 4;
+    if (h_total) {
+      uint32_t t32 = 0;
+      CU(cudaMemcpyAsync(&t32, sb.n_total, 4, cudaMemcpyDeviceToHost, s));
+      CU(cudaStreamSynchronize(s));
+      h_total[b] = t32;
+    }
+  }
+  h->q_exact += redo.size();
+  CU(cudaGetLastError());
+  if (h_block) CU(cudaMemcpyAsync(h_block, sb.res, rb.total, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return CX_OK;
+}
+
+cx_status search_host(cx_index* h, const float* queries, uint64_t B, uint32_t qlen, uint64_t k,
+                      const cx_filter* filter, bool threshold_mode, float threshold, uint8_t* out_ids,
+                      float* out_score, float* out_dist, uint64_t* out_n, uint64_t* out_total) {
+  if (!h) return fail(CX_ERR_VALIDATION, "null index");
+  if (B && !queries) return fail(CX_ERR_VALIDATION, "null queries");
+  if (!out_n) return fail(CX_ERR_VALIDATION, "null out_n");
+  for (uint64_t b = 0; b < B; ++b) out_n[b] = 0;
+  if (out_total)
+    for (uint64_t b = 0; b < B; ++b) out_total[b] = 0;
+  if (h->n_live == 0 || B == 0) return CX_OK;  // index.rs:331: empty -> Ok(vec![])
+  CU(cudaSetDevice(h->device));
+  const uint64_t kd64 = k < h->n_rows ? k : h->n_rows;
+  if (kd64 == 0) return CX_OK;
+  const uint32_t kd = (uint32_t)kd64;
+  const uint32_t ldq = (uint32_t)align_up(qlen > h->ld ? qlen : h->ld, 4);
+
+  FilterHost fh;
+  build_filter(h, filter, &fh);
+  const Plan pl = make_plan(h, B, qlen, ldq, kd, threshold_mode);
+
+  WsLease lease(h);
+  CU(lease.init());
+  Workspace* ws = lease.ws;
+  SearchBufs sb;
+  const size_t dbytes = carve_bufs(nullptr, h, pl, (uint32_t)fh.excl_rows.size(), true, true, &sb);
+  const ResultBlock rb = ResultBlock::make(B, kd);
+  const size_t hq = align_up(B * ldq * 4, 256);
+  CU(ws->ensure(dbytes, hq + rb.total));
+  carve_bufs(ws->d, h, pl, (uint32_t)fh.excl_rows.size(), true, true, &sb);
+  char* hp = (char*)ws->hp;
+  float* hQ = (float*)hp;
+  char* h_block = hp + hq;
+
+  // stage queries, zero padded to ldq
+  for (uint64_t b = 0; b < B; ++b) {
+    memcpy(hQ + b * ldq, queries + b * qlen, (size_t)qlen * 4);
+    for (uint32_t d = qlen; d < ldq; ++d) hQ[b * ldq + d] = 0.0f;
+  }
+  cudaStream_t s = ws->stream;
+  CU(cudaMemcpyAsync(sb.dQ, hQ, B * ldq * 4, cudaMemcpyHostToDevice, s));
+  h->h2d += B * ldq * 4;
+
+  std::vector<uint64_t> totals;
+  if (threshold_mode) totals.assign(B, 0);
+  cx_status stt = run_search(h, ws, fh, sb, pl, threshold_mode, threshold, h_block, nullptr,
+                             threshold_mode ? totals.data() : nullptr);
+  if (stt != CX_OK) return stt;
+  h->d2h += rb.total;
+
+  const uint32_t* h_n = (const uint32_t*)(h_block + rb.n);
+  const float* h_score = (const float*)(h_block + rb.score);
+  const float* h_dist = (const float*)(h_block + rb.dist);
+  const uint8_t* h_ids = (const uint8_t*)(h_block + rb.ids);
+  for (uint64_t b = 0; b < B; ++b) {
+    const uint32_t n = h_n[b];
+    out_n[b] = n;
+    if (out_total) out_total[b] = threshold_mode ? totals[b] : n;
+    if (out_score) memcpy(out_score + b * k, h_score + b * kd, (size_t)n * 4);
+    if (out_dist) memcpy(out_dist + b * k, h_dist + b * kd, (size_t)n * 4);
+    if (out_ids) memcpy(out_ids + b * k * 16, h_ids + b * kd * 16, (size_t)n * 16);
+  }
+  return CX_OK;
+}
+
+}  // namespace
+
+extern "C" cx_status cx_search(cx_index* h, const float* query, uint32_t qlen, uint64_t k,
+                               const cx_filter* filter, uint8_t* out_ids, float* out_score, float* out_distance,
+                               uint64_t* out_n) {
+  return search_host(h, query, 1, qlen, k, filter, false, 0.0f, out_ids, out_score, out_distance, out_n, nullptr);
+}
+
+extern "C" cx_status cx_search_batch(cx_index* h, const float* queries, uint64_t B, uint32_t qlen, uint64_t k,
+                                     const cx_filter* filter, uint8_t* out_ids, float* out_score,
+                                     float* out_distance, uint64_t* out_n) {
+  return search_host(h, queries, B, qlen, k, filter, false, 0.0f, out_ids, out_score, out_distance, out_n,
+                     nullptr);
+}
+
+extern "C" cx_status cx_search_threshold(cx_index* h, const float* query, uint32_t qlen, float threshold,
+                                         const cx_filter* filter, uint64_t cap, uint8_t* out_ids,
+                                         float* out_score, float* out_distance, uint64_t* out_n,
+                                         uint64_t* out_total) {
+  uint64_t total = 0;
+  cx_status st = search_host(h, query, 1, qlen, cap, filter, true, threshold, out_ids, out_score, out_distance,
+                             out_n, &total);
+  if (out_total) *out_total = total;
+  return st;
+}
+
+extern "C" cx_status cx_search_batch_device(cx_index* h, const float* d_queries, uint64_t B, uint64_t k,
+                                            const cx_filter* filter, uint32_t* d_out_rows, float* d_out_score,
+                                            float* d_out_distance, uint8_t* d_out_ids, uint32_t* d_out_n,
+                                            void* stream) {
+  if (!h) return fail(CX_ERR_VALIDATION, "null index");
+  if (!d_queries || !d_out_rows || !d_out_score || !d_out_distance || !d_out_n)
+    return fail(CX_ERR_VALIDATION, "null device buffer");
+  if (B == 0) return CX_OK;
+  CU(cudaSetDevice(h->device));
+  cudaStream_t user = (cudaStream_t)stream;
+  if (h->n_live == 0 || k == 0) {
+    CU(cudaMemsetAsync(d_out_n, 0, B * 4, user));
+    return CX_OK;
+  }
+  if (k > h->n_rows) return fail(CX_ERR_VALIDATION, "device search needs k <= rows in the shard");
+  const uint32_t kd = (uint32_t)k;
+  const uint32_t ldq = h->ld;
+  FilterHost fh;
+  build_filter(h, filter, &fh);
+  const Plan pl = make_plan(h, B, h->dim, ldq, kd, false);
+  WsLease lease(h);
+  CU(lease.init());
+  Workspace* ws = lease.ws;
+  SearchBufs sb;
+  const bool own_q = h->dim != h->ld;
+  const size_t dbytes = carve_bufs(nullptr, h, pl, (uint32_t)fh.excl_rows.size(), own_q, false, &sb);
+  CU(ws->ensure(dbytes, align_up(B * 4, 256)));
+  carve_bufs(ws->d, h, pl, (uint32_t)fh.excl_rows.size(), own_q, false, &sb);
+  // order after whatever produced the queries on the caller's stream
+  CU(cudaEventRecord(ws->ev_sync, user));
+  CU(cudaStreamWaitEvent(ws->stream, ws->ev_sync, 0));
+  if (own_q) {
+    CU(cudaMemsetAsync(sb.dQ, 0, B * ldq * 4, ws->stream));
+    CU(cudaMemcpy2DAsync(sb.dQ, ldq * 4, d_queries, h->dim * 4, h->dim * 4, B, cudaMemcpyDeviceToDevice,
+                         ws->stream));
+  } else {
+    sb.dQ = const_cast<float*>(d_queries);
+  }
+  sb.rows = d_out_rows;
+  sb.score = d_out_score;
+  sb.dist = d_out_distance;
+  sb.ids = d_out_ids;
+  sb.n = d_out_n;
+  cx_status st = run_search(h, ws, fh, sb, pl, false, 0.0f, nullptr, (uint32_t*)ws->hp, nullptr);
+  // run_search returned with its stream idle: the results are complete and visible
+  return st;
+}

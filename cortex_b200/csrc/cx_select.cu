@@ -1,17 +1,19 @@
-// cx_select.cu -- K5 + K3: merge per-group candidate lists, rescore the head with
-// reference arithmetic, order, verify, emit.
+// cx_select.cu -- K5 + K3: order the nominated candidates, rescore the head with
+// reference arithmetic, verify, emit.
 //
 // One CTA per query.
-//   1. gather the G x KP approximate keys, block-wide bitonic sort (descending)
-//   2. the KS = min(#candidates, KP) best are rescored exactly: rows are staged
-//      into shared memory with coalesced loads, then one thread per row runs the
+//   1. load the query's merged candidate list (approximate keys), block-wide bitonic
+//      sort (descending) of the next power of two; meanwhile one thread computes the
+//      query norm in reference order (index.rs:173)
+//   2. the KS = min(#candidates, KP) best are rescored exactly: rows are staged into
+//      shared memory with coalesced loads, then one thread per row runs the
 //      reference's strict left-to-right fp32 fold (index.rs:172) -- so scores and
 //      distances that leave here are bit-identical to the reference's
-//   3. the rescored rows are ordered by (score desc, NaN last, row asc) -- the
-//      stable descending sort of index.rs:287-292 with row order as the
-//      (reference-unspecified) tie order -- and the first k are emitted
-//   4. verification: U = best approximate cosine among everything NOT rescored
-//      (the next merged key and every group's drop bound).  The result is exact if
+//   3. the rescored rows are ordered by (score desc, NaN last, row asc) -- the stable
+//      descending sort of index.rs:287-292 with row order as the (reference-
+//      unspecified) tie order -- and the first k are emitted
+//   4. verification: U = best approximate cosine among everything NOT rescored (the
+//      next key of the list and the pass's global cut-off).  The result is exact if
 //      sim_k > U + eps, where eps bounds |approximate - reference| for the pass that
 //      nominated the candidates, and score_k > 0 (below that the clamp of
 //      index.rs:255 creates ties the approximate order cannot see).  Otherwise
@@ -27,13 +29,16 @@ constexpr int SEL_MAX_KS = 256;
 struct SelectParams {
   StoreView st;
   const float* Q;
-  const float* qnorm;
+  float* qnorm;    // written here (reference-order norm), read by the exact path
+  float* rqnorm;
   uint32_t ldq, qlen;
-  const uint64_t* keys;   // [nq][G][KP]
-  const uint64_t* bound;  // [nq][G]
-  uint32_t G, KP, NK;     // NK = pow2 >= G*KP
-  ResultView rv;          // pointers already offset to the first query of this launch
+  const uint64_t* keys;  // [nq][cap]
+  uint32_t* cnt;         // [nq]   (re-zeroed on exit)
+  uint64_t* gtau;        // [nq]   (re-zeroed on exit)
+  uint32_t cap, KP, NKmax;
+  ResultView rv;         // pointers already offset to the first query of this launch
   float eps;
+  int scale_by_rqn;      // pass keys are cosine * |q| (streaming pass) rather than cosine
 };
 
 static uint32_t pow2_at_least(uint32_t x) {
@@ -42,66 +47,77 @@ static uint32_t pow2_at_least(uint32_t x) {
   return p;
 }
 
-__host__ __device__ inline size_t select_layout(uint32_t NK, uint32_t ld, size_t* off_q, size_t* off_stage,
-                                                size_t* off_e) {
-  size_t o = (size_t)NK * 8;
-  *off_q = o;
+struct SelectLayout {
+  size_t keys, q, stage, e, total;
+};
+
+__host__ __device__ inline SelectLayout select_layout(uint32_t NKmax, uint32_t ld) {
+  SelectLayout L;
+  size_t o = 0;
+  L.keys = o;
+  o += (size_t)NKmax * 8;
+  L.q = o;
   o += (size_t)ld * 4;
-  *off_stage = o;
+  L.stage = o;
   o += (size_t)SEL_BATCH * (ld + 1) * 4;
   o = (o + 7) & ~(size_t)7;
-  *off_e = o;
+  L.e = o;
   o += (size_t)SEL_MAX_KS * (8 + 4 + 4 + 4);
-  return o;
+  L.total = o;
+  return L;
 }
 
 __global__ void __launch_bounds__(SEL_THREADS, 1) select_rescore_kernel(const SelectParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  size_t off_q, off_stage, off_e;
-  select_layout(p.NK, p.st.ld, &off_q, &off_stage, &off_e);
-  uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw);
-  float* q_s = reinterpret_cast<float*>(smem_raw + off_q);
-  float* stage = reinterpret_cast<float*>(smem_raw + off_stage);
-  uint64_t* ekey = reinterpret_cast<uint64_t*>(smem_raw + off_e);
+  const SelectLayout L = select_layout(p.NKmax, p.st.ld);
+  uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw + L.keys);
+  float* q_s = reinterpret_cast<float*>(smem_raw + L.q);
+  float* stage = reinterpret_cast<float*>(smem_raw + L.stage);
+  uint64_t* ekey = reinterpret_cast<uint64_t*>(smem_raw + L.e);
   float* esim = reinterpret_cast<float*>(ekey + SEL_MAX_KS);
   float* edist = esim + SEL_MAX_KS;
   float* escore = edist + SEL_MAX_KS;
-  __shared__ unsigned long long s_bound;
-  __shared__ uint32_t s_M;
-  __shared__ float s_simk, s_scorek;
+  __shared__ float s_na, s_simk, s_scorek;
 
   const uint32_t q = blockIdx.x, tid = threadIdx.x;
   const uint32_t ld = p.st.ld, dim = p.st.dim;
-  const uint32_t total = p.G * p.KP;
-  const uint64_t* src = p.keys + (size_t)q * total;
+  const uint32_t n_app = p.cnt[q];
+  const bool overflow = n_app > p.cap || n_app > p.NKmax;
+  const uint32_t M = min(min(n_app, p.cap), p.NKmax);
+  const uint64_t* src = p.keys + (size_t)q * p.cap;
+  uint32_t NK = 32;
+  while (NK < M) NK <<= 1;
 
+  for (uint32_t i = tid; i < NK; i += SEL_THREADS) keys[i] = i < M ? src[i] : 0ull;
+  for (uint32_t d = tid; d < ld; d += SEL_THREADS) q_s[d] = d < p.qlen ? p.Q[(size_t)q * p.ldq + d] : 0.0f;
   if (tid == 0) {
-    s_bound = 0ull;
-    s_M = 0;
     s_simk = 0.0f;
     s_scorek = 0.0f;
   }
-  for (uint32_t i = tid; i < p.NK; i += SEL_THREADS) keys[i] = i < total ? src[i] : 0ull;
-  for (uint32_t d = tid; d < ld; d += SEL_THREADS) q_s[d] = d < p.qlen ? p.Q[(size_t)q * p.ldq + d] : 0.0f;
   __syncthreads();
-  {
-    unsigned long long b = 0;
-    for (uint32_t g = tid; g < p.G; g += SEL_THREADS) {
-      unsigned long long v = p.bound[(size_t)q * p.G + g];
-      b = v > b ? v : b;
+  if (tid == SEL_THREADS - 1) {  // query norm, reference order
+    float acc = 0.0f;
+    const uint32_t n = p.qlen < ld ? p.qlen : ld;
+    uint32_t d = 0;
+    for (; d + 8 <= n; d += 8) {
+      float x[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = q_s[d + j];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc = ref_fold(acc, x[j], x[j]);
     }
-    if (b) atomicMax(&s_bound, b);
+    for (; d < n; ++d) acc = ref_fold(acc, q_s[d], q_s[d]);
+    const float na = __fsqrt_rn(acc);
+    s_na = na;
+    p.qnorm[q] = na;
+    p.rqnorm[q] = __frcp_rn(na);
   }
-  bitonic_sort_desc(keys, p.NK, tid, SEL_THREADS, [] { __syncthreads(); });
-  // number of real candidates (keys are > 0, sorted descending)
-  for (uint32_t i = tid; i < p.NK; i += SEL_THREADS)
-    if (keys[i] != 0ull && (i + 1 == p.NK || keys[i + 1] == 0ull)) s_M = i + 1;
+  bitonic_sort_desc(keys, NK, tid, SEL_THREADS, [] { __syncthreads(); });
   __syncthreads();
-  const uint32_t M = s_M;
+  const float na = s_na;
   const uint32_t KS = min(min(M, p.KP), (uint32_t)SEL_MAX_KS);
-  unsigned long long U = s_bound;
+  unsigned long long U = p.gtau[q];
   if (M > KS && keys[KS] > U) U = keys[KS];
-  const float na = p.qnorm[q];
 
   // exact rescore, SEL_BATCH rows per round
   const uint32_t warp = tid >> 5, lane = tid & 31, nwarps = SEL_THREADS / 32;
@@ -119,7 +135,18 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) select_rescore_kernel(const Se
       const float* r = stage + tid * sstride;
       const uint32_t n = p.qlen < dim ? p.qlen : dim;
       float dot = 0.0f;
-      for (uint32_t d = 0; d < n; ++d) dot = ref_fold(dot, q_s[d], r[d]);
+      uint32_t d = 0;
+      for (; d + 8 <= n; d += 8) {
+        float a[8], b[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          a[j] = q_s[d + j];
+          b[j] = r[d + j];
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dot = ref_fold(dot, a[j], b[j]);
+      }
+      for (; d < n; ++d) dot = ref_fold(dot, q_s[d], r[d]);
       const float nbm = __ldg(p.st.norm + row);
       const float sim = __fdiv_rn(dot, __fmul_rn(na, nbm));
       const float dist = __fsub_rn(1.0f, sim);
@@ -157,38 +184,46 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) select_rescore_kernel(const Se
   __syncthreads();
   if (tid == 0) {
     p.rv.n[q] = n_out;
-    bool ok = KS >= k;
+    bool ok = KS >= k && !overflow;
     if (ok) {
       const float sk = s_scorek, simk = s_simk;
       if (sk != sk) ok = false;
       else if (U != 0ull) {
-        const float u = float_from_ord(key_ord(U));
+        float u = float_from_ord(key_ord(U));
+        if (p.scale_by_rqn) u = u * __frcp_rn(na);
         ok = (sk > 0.0f) && (simk > u + p.eps);
       }
     }
     p.rv.ok[q] = ok ? 1u : 0u;
+    p.cnt[q] = 0;   // leave the workspace ready for the next pass
+    p.gtau[q] = 0ull;
   }
 }
 
-size_t select_smem(uint32_t G, uint32_t KP, uint32_t ld) {
-  size_t a, b, c;
-  return select_layout(pow2_at_least(G * KP), ld, &a, &b, &c);
+size_t select_smem(uint32_t cap, uint32_t ld) {
+  uint32_t nk = pow2_at_least(cap < 32 ? 32 : cap);
+  if (nk > 16384) nk = 16384;
+  return select_layout(nk, ld).total;
 }
 
 cudaError_t launch_select_rescore(const StoreView& st, const QueryView& qv, uint32_t q0, uint32_t nq,
-                                  const CandView& cv, const ResultView& rv, float eps_cos, cudaStream_t s) {
+                                  const CandView& cv, const ResultView& rv, float eps_cos, int scale_by_rqn,
+                                  cudaStream_t s) {
   if (!nq) return cudaSuccess;
   SelectParams p;
   p.st = st;
   p.Q = qv.Q + (size_t)q0 * qv.ldq;
-  p.qnorm = qv.qnorm + q0;
+  p.qnorm = const_cast<float*>(qv.qnorm) + q0;
+  p.rqnorm = const_cast<float*>(qv.rqnorm) + q0;
   p.ldq = qv.ldq;
   p.qlen = qv.qlen;
-  p.keys = cv.keys + (size_t)q0 * cv.G * cv.KP;
-  p.bound = cv.bound + (size_t)q0 * cv.G;
-  p.G = cv.G;
+  p.keys = cv.keys + (size_t)q0 * cv.cap;
+  p.cnt = cv.cnt + q0;
+  p.gtau = cv.gtau + q0;
+  p.cap = cv.cap;
   p.KP = cv.KP;
-  p.NK = pow2_at_least(cv.G * cv.KP);
+  p.NKmax = pow2_at_least(cv.cap < 32 ? 32 : cv.cap);
+  if (p.NKmax > 16384) p.NKmax = 16384;
   p.rv = rv;
   p.rv.rows += (size_t)q0 * rv.k;
   p.rv.score += (size_t)q0 * rv.k;
@@ -197,7 +232,8 @@ cudaError_t launch_select_rescore(const StoreView& st, const QueryView& qv, uint
   p.rv.n += q0;
   p.rv.ok += q0;
   p.eps = eps_cos;
-  size_t smem = select_smem(cv.G, cv.KP, st.ld);
+  p.scale_by_rqn = scale_by_rqn;
+  const size_t smem = select_layout(p.NKmax, st.ld).total;
   if (smem > 227 * 1024 || cv.KP > SEL_MAX_KS) return cudaErrorInvalidConfiguration;
   cudaError_t e =
       cudaFuncSetAttribute(select_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

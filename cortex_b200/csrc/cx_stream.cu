@@ -38,12 +38,12 @@ constexpr size_t SC_SMEM_LIMIT = 227 * 1024;
 struct StreamParams {
   StoreView st;
   const float* Q;    // first query of this pass
-  const float* rqn;  // its reciprocal norm
   uint32_t ldq, nq_valid;
   DevFilter flt;
-  uint64_t* keys;    // &cand.keys[q0][0][0]
-  uint64_t* bound;   // &cand.bound[q0][0]
-  uint64_t* gtau;    // &cand.gtau[q0]   (zeroed before the pass)
+  uint64_t* keys;    // &cand.keys[q0][0]   merged candidate list per query, capacity cap
+  uint32_t* cnt;     // &cand.cnt[q0]       its fill count        (zero before the pass)
+  uint64_t* gtau;    // &cand.gtau[q0]      cross-CTA cut-off     (zero before the pass)
+  uint32_t cap;
   uint32_t G, KP, C, n_tiles, stages, kslice, n_slices;
 };
 
@@ -190,7 +190,6 @@ __global__ void __launch_bounds__(SC_THREADS, 1) stream_scan_kernel(const Stream
   const uint32_t idx = transpose_index<NV>(lane);
   const bool leader = (lane & ((32u / NV) - 1u)) == 0;  // NV <= 32
   const uint32_t my_r = idx / NQ, my_b = idx % NQ;
-  const float my_rqn = (my_b < p.nq_valid) ? __ldg(p.rqn + my_b) : 0.0f;
   const float4* q4 = reinterpret_cast<const float4*>(q_s);
   const uint32_t kslice4 = p.kslice >> 2;
   const uint32_t C = p.C, KP = p.KP;
@@ -294,7 +293,9 @@ __global__ void __launch_bounds__(SC_THREADS, 1) stream_scan_kernel(const Stream
 
     const uint32_t row = t * SC_TILE_ROWS + gwarp * SC_R + my_r;
     if (leader && row < p.st.n_rows && my_b < p.nq_valid) {
-      const float approx = total * my_rn * my_rqn;
+      // cosine up to the query's own (positive) norm, which cannot change the order
+      // within a query; cx_select.cu applies it when it compares against eps
+      const float approx = total * my_rn;
       if (approx == approx) {
         const uint64_t key = make_key(ord_from_float(approx), row);
         if (key > *((volatile uint64_t*)(tau_s + my_b))) {
@@ -327,15 +328,25 @@ __global__ void __launch_bounds__(SC_THREADS, 1) stream_scan_kernel(const Stream
     }
   }
 
-  // final: rank every list, emit the head and the drop bound
+  // final: rank every list and append the part that can still matter -- keys at or
+  // above the global cut-off -- to the query's merged list.  gtau ends up as the
+  // maximum of every group's cut-off, i.e. an upper bound of everything dropped.
   csync();
   for (uint32_t b = 0; b < p.nq_valid; ++b) {
     compact(b);
     const uint64_t* Lb = list_s + ((size_t)b * 2 + cur_s[b]) * C;
     const uint32_t n_keep = cnt_s[b];
-    uint64_t* out = p.keys + ((size_t)b * p.G + blockIdx.x) * KP;
-    for (uint32_t j = ctid; j < KP; j += SC_CT) out[j] = j < n_keep ? Lb[j] : 0;
-    if (ctid == 0) p.bound[(size_t)b * p.G + blockIdx.x] = tau_s[b];
+    if (ctid == 0) {
+      const uint64_t g = *((volatile uint64_t*)(p.gtau + b));
+      uint32_t m = 0;
+      while (m < n_keep && Lb[m] >= g) ++m;  // sorted descending: a prefix survives
+      flag_s[1] = m;
+      flag_s[2] = m ? atomicAdd(p.cnt + b, m) : 0;
+    }
+    csync();
+    const uint32_t m = flag_s[1], base = flag_s[2];
+    uint64_t* out = p.keys + (size_t)b * p.cap + base;
+    for (uint32_t j = ctid; j < m; j += SC_CT) out[j] = Lb[j];
     csync();
   }
 }
@@ -412,14 +423,14 @@ cudaError_t launch_stream_scan(const StoreView& st, const QueryView& qv, uint32_
   StreamParams p;
   p.st = st;
   p.Q = qv.Q + (size_t)q0 * qv.ldq;
-  p.rqn = qv.rqnorm + q0;
   p.ldq = qv.ldq;
   p.nq_valid = nq_pass;
   p.flt = flt;
   p.G = cv.G;
   p.KP = cv.KP;
-  p.keys = cv.keys + (size_t)q0 * cv.G * cv.KP;
-  p.bound = cv.bound + (size_t)q0 * cv.G;
+  p.cap = cv.cap;
+  p.keys = cv.keys + (size_t)q0 * cv.cap;
+  p.cnt = cv.cnt + q0;
   p.gtau = cv.gtau + q0;
   p.C = stream_list_cap(cv.KP);
   p.n_tiles = (st.n_rows + SC_TILE_ROWS - 1) / SC_TILE_ROWS;
