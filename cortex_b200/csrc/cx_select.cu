@@ -81,19 +81,33 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) select_rescore_kernel(const Se
 
   const uint32_t q = blockIdx.x, tid = threadIdx.x;
   const uint32_t ld = p.st.ld, dim = p.st.dim;
+  __shared__ uint32_t s_m;
   const uint32_t n_app = p.cnt[q];
-  const bool overflow = n_app > p.cap || n_app > p.NKmax;
-  const uint32_t M = min(min(n_app, p.cap), p.NKmax);
+  const unsigned long long gt = p.gtau[q];  // final cut-off: nothing below it can reach the top KP
+  const bool overflow = n_app > p.cap;
+  const uint32_t n_src = min(n_app, p.cap);
   const uint64_t* src = p.keys + (size_t)q * p.cap;
-  uint32_t NK = 32;
-  while (NK < M) NK <<= 1;
-
-  for (uint32_t i = tid; i < NK; i += SEL_THREADS) keys[i] = i < M ? src[i] : 0ull;
-  for (uint32_t d = tid; d < ld; d += SEL_THREADS) q_s[d] = d < p.qlen ? p.Q[(size_t)q * p.ldq + d] : 0.0f;
   if (tid == 0) {
     s_simk = 0.0f;
     s_scorek = 0.0f;
+    s_m = 0;
   }
+  for (uint32_t d = tid; d < ld; d += SEL_THREADS) q_s[d] = d < p.qlen ? p.Q[(size_t)q * p.ldq + d] : 0.0f;
+  __syncthreads();
+  // keep only keys at or above the final cut-off (groups appended against older, lower ones)
+  for (uint32_t i = tid; i < n_src; i += SEL_THREADS) {
+    const uint64_t key = src[i];
+    if (key >= gt) {
+      const uint32_t pos = atomicAdd(&s_m, 1u);
+      if (pos < p.NKmax) keys[pos] = key;
+    }
+  }
+  __syncthreads();
+  const uint32_t M = min(s_m, p.NKmax);
+  const bool truncated = s_m > p.NKmax;
+  uint32_t NK = 32;
+  while (NK < M) NK <<= 1;
+  for (uint32_t i = M + tid; i < NK; i += SEL_THREADS) keys[i] = 0ull;
   __syncthreads();
   if (tid == SEL_THREADS - 1) {  // query norm, reference order
     float acc = 0.0f;
@@ -116,7 +130,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) select_rescore_kernel(const Se
   __syncthreads();
   const float na = s_na;
   const uint32_t KS = min(min(M, p.KP), (uint32_t)SEL_MAX_KS);
-  unsigned long long U = p.gtau[q];
+  unsigned long long U = gt;
   if (M > KS && keys[KS] > U) U = keys[KS];
 
   // exact rescore, SEL_BATCH rows per round
@@ -127,7 +141,15 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) select_rescore_kernel(const Se
     for (uint32_t j = warp; j < nb; j += nwarps) {
       const uint32_t row = key_row(keys[base + j]);
       const float* g = p.st.E + (size_t)row * ld;
-      for (uint32_t d = lane; d < ld; d += 32) stage[j * sstride + d] = __ldg(g + d);
+      uint32_t d = lane;
+      for (; d + 7 * 32 < ld; d += 8 * 32) {  // eight loads in flight per lane
+        float x[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) x[u] = __ldg(g + d + u * 32);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) stage[j * sstride + d + u * 32] = x[u];
+      }
+      for (; d < ld; d += 32) stage[j * sstride + d] = __ldg(g + d);
     }
     __syncthreads();
     if (tid < nb) {
@@ -184,7 +206,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) select_rescore_kernel(const Se
   __syncthreads();
   if (tid == 0) {
     p.rv.n[q] = n_out;
-    bool ok = KS >= k && !overflow;
+    bool ok = KS >= k && !overflow && !truncated;
     if (ok) {
       const float sk = s_scorek, simk = s_simk;
       if (sk != sk) ok = false;
