@@ -37,13 +37,17 @@ __global__ void row_norm_kernel(float* __restrict__ E, float* __restrict__ norm,
   rnorm[r0 + i] = __frcp_rn(nb);
 }
 
-__global__ void row_shadow_kernel(const float* __restrict__ E, __nv_bfloat16* __restrict__ E16, uint32_t ld,
-                                  uint32_t ld16, uint32_t r0, uint32_t n) {
+// bf16 shadow for the tensor pass: rows are stored NORMALISED (x / |x|) so that the
+// tcgen05 contraction with a normalised query yields the cosine directly.  The shadow
+// only nominates candidates; zero-norm rows become NaN and are never nominated.
+__global__ void row_shadow_kernel(const float* __restrict__ E, const float* __restrict__ rnorm,
+                                  __nv_bfloat16* __restrict__ E16, uint32_t ld, uint32_t ld16, uint32_t r0,
+                                  uint32_t n) {
   size_t total = (size_t)n * ld16;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (size_t)gridDim.x * blockDim.x) {
     uint32_t r = (uint32_t)(i / ld16), c = (uint32_t)(i % ld16);
-    float v = c < ld ? E[(size_t)(r0 + r) * ld + c] : 0.0f;
+    float v = c < ld ? E[(size_t)(r0 + r) * ld + c] * rnorm[r0 + r] : 0.0f;
     E16[(size_t)(r0 + r) * ld16 + c] = __float2bfloat16_rn(v);
   }
 }
@@ -55,7 +59,7 @@ void launch_prepare_rows(float* E, float* norm, float* rnorm, void* E16, uint32_
   if (E16) {
     size_t total = (size_t)n * ld16;
     uint32_t blocks = (uint32_t)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
-    row_shadow_kernel<<<blocks, 256, 0, s>>>(E, (__nv_bfloat16*)E16, ld, ld16, r0, n);
+    row_shadow_kernel<<<blocks, 256, 0, s>>>(E, rnorm, (__nv_bfloat16*)E16, ld, ld16, r0, n);
   }
 }
 

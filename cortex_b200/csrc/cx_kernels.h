@@ -30,7 +30,8 @@ struct QueryView {
 // Candidates nominated by a fast pass: one merged, unordered key list per query.
 // cnt and gtau must be zero when a pass starts; the select kernel re-zeroes them.
 struct CandView {
-  uint64_t* keys;   // [nq][cap]
+  uint64_t* keys;   // [nq][cap]; the list of query q starts at keys + (q - q_base) * cap
+  uint32_t q_base = 0;
   uint32_t* cnt;    // [nq] entries appended (may exceed cap: the excess was dropped)
   uint64_t* gtau;   // [nq] running cut-off shared by all producer groups; at the end of the
                     //      pass it bounds (as a key) every row that is NOT in the list
@@ -70,6 +71,18 @@ size_t select_smem(uint32_t cap, uint32_t ld);
 cudaError_t launch_select_rescore(const StoreView& st, const QueryView& qv, uint32_t q0, uint32_t nq,
                                   const CandView& cv, const ResultView& rv, float eps_cos, int scale_by_rqn,
                                   cudaStream_t s);
+
+// K2: tcgen05 bf16 pass over the normalised shadow matrix.  Q16 = normalised bf16 queries
+// [round_up(nq_total,128)][ld16] made by launch_query_bf16.  One launch serves at most
+// sm_count*128 queries starting at q0; `lists` is scratch of tensor_scratch_bytes().
+bool tensor_scan_eligible(uint32_t ld16, uint32_t KP);
+void tensor_scan_shape(uint32_t nq, int sm_count, uint32_t* n_qt, uint32_t* n_es);
+size_t tensor_scratch_bytes(uint32_t KP, int sm_count);
+void launch_query_bf16(const float* Q, uint32_t ldq, uint32_t dim, uint32_t nq, uint32_t nq_pad, void* Q16,
+                       uint32_t ld16, cudaStream_t s);
+cudaError_t launch_tensor_scan(const StoreView& st, const void* Q16, uint32_t q0, uint32_t nq,
+                               const DevFilter& flt, const CandView& cv, uint64_t* lists, int sm_count,
+                               cudaStream_t s);
 
 // Exact path: every row scored with reference arithmetic -> keys[n_rows] for one query
 void launch_exact_keys(const StoreView& st, const QueryView& qv, uint32_t q, const DevFilter& flt,

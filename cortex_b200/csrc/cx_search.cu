@@ -103,6 +103,9 @@ struct SearchBufs {
   float* rqnorm = nullptr;
   uint32_t* excl = nullptr;
   uint64_t* cand_keys = nullptr;
+  uint16_t* q16 = nullptr;        // normalised bf16 queries (tensor pass)
+  uint64_t* lists = nullptr;      // tensor pass private-list scratch
+  uint64_t* retry_keys = nullptr; // merged list for single-query streaming retries
   char* res = nullptr;       // ResultBlock (device) when results are workspace-owned
   uint32_t* ok = nullptr;
   uint32_t* n = nullptr;
@@ -117,11 +120,20 @@ struct SearchBufs {
   uint32_t* n_total = nullptr;
 };
 
+// bound on |approximate - reference| cosine for the bf16 tensor pass: both operands are
+// rounded to bf16 (2^-9 relative each, so 2^-8 on every product; Cauchy-Schwarz bounds
+// the sum by the product of the norms), plus fp32 accumulation and normalisation slack.
+float eps_tensor(uint32_t dim) { return 0.00390625f * 1.02f + ((float)dim + 32.0f) * 1.1920929e-7f; }
+
 struct Plan {
   uint64_t B;
   uint32_t qlen, ldq, kd;
-  uint32_t G, KP, cap;
-  bool fast;
+  uint32_t G, KP;     // streaming pass: producer groups, keys kept per group
+  uint32_t cap;       // merged-list capacity per query for the primary pass
+  uint32_t cap_retry; // ... and for streaming retries of single queries after a tensor pass
+  uint32_t q_per_launch;  // tensor pass: queries per launch
+  bool fast;          // a nominate + rescore pass is usable for this call
+  bool tensor;        // ... and it is the tcgen05 pass (else the streaming pass)
 };
 
 Plan make_plan(const cx_index* h, uint64_t B, uint32_t qlen, uint32_t ldq, uint32_t kd, bool threshold_mode) {
@@ -134,9 +146,22 @@ Plan make_plan(const cx_index* h, uint64_t B, uint32_t qlen, uint32_t ldq, uint3
   p.G = stream_scan_groups(n_rows, h->sm_count);
   p.KP = keep_count(kd, p.G);
   p.cap = p.G * p.KP;
+  p.cap_retry = 0;
+  p.q_per_launch = 0;
   p.fast = !threshold_mode && qlen == h->dim && n_rows >= 256 && kd <= 128 && p.KP >= kd &&
            stream_scan_smem(h->ld, 8, p.KP) != 0 && select_smem(p.cap, h->ld) <= 227 * 1024 &&
            h->force_path != PATH_EXACT;
+  p.tensor = false;
+  if (p.fast && h->dE16 && h->force_path != PATH_STREAM &&
+      (B >= h->tensor_min_batch || h->force_path == PATH_TENSOR) && tensor_scan_eligible(h->ld16, p.KP)) {
+    p.tensor = true;
+    p.q_per_launch = (uint32_t)h->sm_count * 128u;
+    uint32_t n_qt, n_es;
+    tensor_scan_shape((uint32_t)(B < p.q_per_launch ? B : p.q_per_launch), h->sm_count, &n_qt, &n_es);
+    p.cap_retry = p.cap;
+    p.cap = n_es * p.KP;
+    if (p.cap < 2 * p.KP) p.cap = 2 * p.KP;
+  }
   return p;
 }
 
@@ -149,6 +174,11 @@ size_t carve_bufs(void* base, const cx_index* h, const Plan& pl, uint32_t n_excl
   sb->rqnorm = c.take<float>(pl.B);
   sb->excl = c.take<uint32_t>(n_excl + 1);
   sb->cand_keys = pl.fast ? c.take<uint64_t>((size_t)pl.B * pl.cap) : nullptr;
+  if (pl.tensor) {
+    sb->q16 = c.take<uint16_t>(align_up(pl.B, 128) * h->ld16);
+    sb->lists = (uint64_t*)c.take<char>(tensor_scratch_bytes(pl.KP, h->sm_count));
+    sb->retry_keys = c.take<uint64_t>(pl.cap_retry);
+  }
   sb->n_total = c.take<uint32_t>(4);
   const ResultBlock rb = ResultBlock::make(pl.B, pl.kd);
   if (own_results) {
@@ -217,14 +247,27 @@ cx_status run_search(cx_index* h, Workspace* ws, const FilterHost& fh, const Sea
     cv.G = pl.G;
     cv.KP = pl.KP;
     uint32_t n_pass = 0;
+    if (pl.tensor) {
+      launch_query_bf16(sb.dQ, pl.ldq, h->dim, (uint32_t)B, (uint32_t)align_up(B, 128), sb.q16, h->ld16, s);
+      h->launches += 1;
+    }
     if (h->profile) CU(cudaEventRecord(ws->ev0, s));
-    for (uint64_t q0 = 0; q0 < B; q0 += 8) {
-      const uint32_t nq = (uint32_t)(B - q0 < 8 ? B - q0 : 8);
-      CU(launch_stream_scan(st, qv, (uint32_t)q0, nq, flt, cv, h->sm_count, s));
-      ++n_pass;
+    if (pl.tensor) {
+      for (uint64_t q0 = 0; q0 < B; q0 += pl.q_per_launch) {
+        const uint32_t nq = (uint32_t)(B - q0 < pl.q_per_launch ? B - q0 : pl.q_per_launch);
+        CU(launch_tensor_scan(st, sb.q16, (uint32_t)q0, nq, flt, cv, sb.lists, h->sm_count, s));
+        ++n_pass;
+      }
+    } else {
+      for (uint64_t q0 = 0; q0 < B; q0 += 8) {
+        const uint32_t nq = (uint32_t)(B - q0 < 8 ? B - q0 : 8);
+        CU(launch_stream_scan(st, qv, (uint32_t)q0, nq, flt, cv, h->sm_count, s));
+        ++n_pass;
+      }
     }
     if (h->profile) CU(cudaEventRecord(ws->ev1, s));
-    CU(launch_select_rescore(st, qv, 0, (uint32_t)B, cv, rv, eps_stream(h->dim), /*scale_by_rqn=*/1, s));
+    CU(launch_select_rescore(st, qv, 0, (uint32_t)B, cv, rv, pl.tensor ? eps_tensor(h->dim) : eps_stream(h->dim),
+                             /*scale_by_rqn=*/pl.tensor ? 0 : 1, s));
     h->launches += n_pass + 1;
     if (h_block) {
       CU(cudaMemcpyAsync(h_block, sb.res, rb.total, cudaMemcpyDeviceToHost, s));
@@ -233,7 +276,6 @@ cx_status run_search(cx_index* h, Workspace* ws, const FilterHost& fh, const Sea
       CU(cudaMemcpyAsync(h_ok, sb.ok, B * 4, cudaMemcpyDeviceToHost, s));
     }
     CU(cudaStreamSynchronize(s));
-    ws->state_dirty = false;
     if (h->profile) {
       float ms = 0.f;
       CU(cudaEventElapsedTime(&ms, ws->ev0, ws->ev1));
@@ -242,8 +284,33 @@ cx_status run_search(cx_index* h, Workspace* ws, const FilterHost& fh, const Sea
     }
     for (uint64_t b = 0; b < B; ++b)
       if (!h_ok[b]) redo.push_back((uint32_t)b);
-    h->q_stream += B - redo.size();
+    (pl.tensor ? h->q_tensor : h->q_stream) += B - redo.size();
     h->fallbacks += redo.size();
+    if (pl.tensor && !redo.empty()) {
+      // second tier: queries the bf16 pass could not verify go through the fp32 streaming
+      // pass one at a time (its error bound is ~100x tighter); only what still fails after
+      // that is left to the exact path
+      CandView cr = cv;
+      cr.keys = sb.retry_keys;
+      cr.cap = pl.cap_retry;
+      cr.G = pl.G;
+      for (uint32_t b : redo) {
+        cr.q_base = b;
+        CU(launch_stream_scan(st, qv, b, 1, flt, cr, h->sm_count, s));
+        CU(launch_select_rescore(st, qv, b, 1, cr, rv, eps_stream(h->dim), 1, s));
+        h->launches += 2;
+      }
+      CU(cudaMemcpyAsync(h_ok, sb.ok, B * 4, cudaMemcpyDeviceToHost, s));
+      CU(cudaStreamSynchronize(s));
+      std::vector<uint32_t> still;
+      for (uint32_t b : redo)
+        if (!h_ok[b]) still.push_back(b);
+      h->q_stream += redo.size() - still.size();
+      redo.swap(still);
+      if (redo.empty() && h_block) CU(cudaMemcpyAsync(h_block, sb.res, rb.total, cudaMemcpyDeviceToHost, s));
+      if (redo.empty()) CU(cudaStreamSynchronize(s));
+    }
+    ws->state_dirty = false;
     if (redo.empty()) return CX_OK;
   } else {
     launch_prepare_queries(sb.dQ, sb.qnorm, sb.rqnorm, (uint32_t)B, pl.qlen, pl.ldq, s);

@@ -239,7 +239,7 @@ cudaError_t launch_select_rescore(const StoreView& st, const QueryView& qv, uint
   p.rqnorm = const_cast<float*>(qv.rqnorm) + q0;
   p.ldq = qv.ldq;
   p.qlen = qv.qlen;
-  p.keys = cv.keys + (size_t)q0 * cv.cap;
+  p.keys = cv.keys + (size_t)(q0 - cv.q_base) * cv.cap;
   p.cnt = cv.cnt + q0;
   p.gtau = cv.gtau + q0;
   p.cap = cv.cap;

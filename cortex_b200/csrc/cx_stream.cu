@@ -346,7 +346,8 @@ __global__ void __launch_bounds__(SC_THREADS, 1) stream_scan_kernel(const Stream
     csync();
     const uint32_t m = flag_s[1], base = flag_s[2];
     uint64_t* out = p.keys + (size_t)b * p.cap + base;
-    for (uint32_t j = ctid; j < m; j += SC_CT) out[j] = Lb[j];
+    for (uint32_t j = ctid; j < m; j += SC_CT)
+      if (base + j < p.cap) out[j] = Lb[j];  // excess is dropped; cnt > cap tells the select kernel
     csync();
   }
 }
@@ -429,7 +430,7 @@ cudaError_t launch_stream_scan(const StoreView& st, const QueryView& qv, uint32_
   p.G = cv.G;
   p.KP = cv.KP;
   p.cap = cv.cap;
-  p.keys = cv.keys + (size_t)q0 * cv.cap;
+  p.keys = cv.keys + (size_t)(q0 - cv.q_base) * cv.cap;
   p.cnt = cv.cnt + q0;
   p.gtau = cv.gtau + q0;
   p.C = stream_list_cap(cv.KP);

@@ -1,0 +1,509 @@
+// cx_tensor.cu -- K2: batched Q.E^T on the 5th-gen tensor cores (tcgen05 + TMEM),
+// operands fed by TMA, with the candidate selection fused into the epilogue so the
+// score matrix is never written.
+//
+// Shapes (reference call sites): search_batch (vector/index.rs:390-410), the
+// auto-linker's per-node search loop (linker/auto_linker.rs:215-222) and the dedup
+// self-join (linker/dedup.rs:72-88) all become  scores[B, N] = Qn[B, D] . En[N, D]^T
+// on the NORMALISED bf16 copies (so a score is an approximate cosine).
+//
+// One CTA per SM, 8 warps:
+//   warp 0  TMA producer: the CTA's 128-query tile once (resident in smem for the
+//           whole pass), then [256 rows x 64] bf16 boxes of E through a ring of stages
+//   warp 1  one thread issues tcgen05.mma (M=128 queries x N=256 rows x K=16),
+//           accumulators in TMEM, double buffered (2 x 256 columns)
+//   warp 2  TMEM allocation
+//   warps 4-7  epilogue: lane == query.  tcgen05.ld 32 columns at a time; a running
+//           max against the query's cut-off tau is the whole common path.  Scores at or
+//           above tau are appended to the thread's private list (global scratch, L2
+//           resident); full lists are compacted to the best KP by the warp
+//           cooperatively (bitonic sort in registers), which raises tau; tau is shared
+//           between the CTAs that scan other row ranges for the same queries.
+// CTAs are arranged (query tile) x (row split); CTAs that differ only in the query
+// tile walk the same rows at the same time, so E streams from HBM once and is served
+// to the others from L2.
+//
+// Algorithmic work: 2*D flops per scored pair; DESIGN.md §4.
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include "cx_kernels.h"
+
+namespace cx {
+
+constexpr uint32_t TC_BM = 128;       // queries per CTA (UMMA M, TMEM lanes)
+constexpr uint32_t TC_BN = 256;       // corpus rows per tile (UMMA N, TMEM columns)
+constexpr uint32_t TC_BK = 64;        // bf16 per K chunk = one 128 B swizzle atom
+constexpr uint32_t TC_UK = 16;        // K of one tcgen05.mma for 16-bit inputs
+constexpr uint32_t TC_THREADS = 256;
+constexpr uint32_t TC_QCHUNK_BYTES = TC_BM * TC_BK * 2;  // 16 KB
+constexpr uint32_t TC_ESTAGE_BYTES = TC_BN * TC_BK * 2;  // 32 KB
+constexpr uint32_t TC_MAX_STAGES = 6;
+constexpr uint32_t TC_SMEM_LIMIT = 227 * 1024;
+constexpr uint32_t TC_TMEM_COLS = 512;
+
+struct TensorParams {
+  uint32_t n_rows, n_tiles, n_kc;
+  uint32_t n_qt, n_es;
+  uint32_t nq_valid;
+  uint32_t KP, stages;
+  const uint32_t* meta;
+  const uint32_t* agent;
+  DevFilter flt;
+  uint64_t* lists;  // [grid][128][C] private candidate lists (scratch)
+  uint64_t* keys;   // merged list per query [nq][cap]
+  uint32_t* cnt;
+  uint64_t* gtau;
+  uint32_t cap;
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, 128 B swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+// start address >> 4, LBO (unused for swizzled K-major) = 1, SBO = 1024 B (8 rows of
+// 128 B), version 1 (Blackwell), layout type 2 (SWIZZLE_128B).
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// kind::f16 instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7, 10), both K-major,
+// N >> 3 at bit 17, M >> 4 at bit 24.
+constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((TC_BN >> 3) << 17) | ((TC_BM >> 4) << 24);
+
+// ---- warp-cooperative compaction of one private list --------------------------------
+// Sort (descending) the n <= NPL*32 keys at L across the warp's registers, write the best
+// KP back in order, return the KP-th key (0 if n < KP).  All lanes call it.
+template <int NPL>
+__device__ __forceinline__ uint64_t warp_compact(uint64_t* L, uint32_t n, uint32_t KP, uint32_t lane) {
+  uint64_t k[NPL];
+#pragma unroll
+  for (int i = 0; i < NPL; ++i) {
+    const uint32_t e = i * 32 + lane;
+    k[i] = e < n ? L[e] : 0ull;
+  }
+  constexpr uint32_t N = NPL * 32;
+#pragma unroll
+  for (uint32_t kk = 2; kk <= N; kk <<= 1) {
+#pragma unroll
+    for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
+      if (j >= 32) {
+        const uint32_t ji = j >> 5;
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) {
+          const int pi = i ^ (int)ji;
+          if (pi > i) {
+            const uint32_t e = i * 32 + lane;
+            const bool desc = (e & kk) == 0;
+            const uint64_t a = k[i], b = k[pi];
+            const bool sw = desc ? (a < b) : (a > b);
+            k[i] = sw ? b : a;
+            k[pi] = sw ? a : b;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) {
+          const uint32_t e = i * 32 + lane;
+          const uint64_t mine = k[i];
+          const uint64_t other = __shfl_xor_sync(0xffffffffu, mine, j);
+          const bool lower = (lane & j) == 0;           // I hold the lower index of the pair
+          const bool desc = (e & kk) == 0;
+          // descending block: lower index keeps the larger key
+          const bool keep_max = (lower == desc);
+          k[i] = keep_max ? (mine > other ? mine : other) : (mine < other ? mine : other);
+        }
+      }
+    }
+  }
+  uint64_t kth = 0ull;
+#pragma unroll
+  for (int i = 0; i < NPL; ++i) {
+    const uint32_t e = i * 32 + lane;
+    if (e < KP && e < n) L[e] = k[i];
+    const uint64_t cand = __shfl_sync(0xffffffffu, k[i], (KP - 1) & 31);
+    if ((uint32_t)i == ((KP - 1) >> 5)) kth = cand;
+  }
+  __syncwarp();
+  return n >= KP ? kth : 0ull;
+}
+
+template <int NPL>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmE,
+                   const TensorParams p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  constexpr uint32_t C = NPL * 32;
+  const uint32_t S = p.stages;
+  unsigned char* sQ = smem;
+  unsigned char* sE = smem + (size_t)p.n_kc * TC_QCHUNK_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sE + (size_t)S * TC_ESTAGE_BYTES);
+  const uint32_t bar_q = smem_u32(bars);
+  const uint32_t bar_full = smem_u32(bars + 1);
+  const uint32_t bar_empty = smem_u32(bars + 1 + TC_MAX_STAGES);
+  const uint32_t bar_tfull = smem_u32(bars + 1 + 2 * TC_MAX_STAGES);
+  const uint32_t bar_tempty = smem_u32(bars + 3 + 2 * TC_MAX_STAGES);
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 5 + 2 * TC_MAX_STAGES);
+
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    mbar_init(bar_q, 1);
+    for (uint32_t s = 0; s < S; ++s) {
+      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_empty + 8 * s, 1);
+    }
+    for (uint32_t a = 0; a < 2; ++a) {
+      mbar_init(bar_tfull + 8 * a, 1);
+      mbar_init(bar_tempty + 8 * a, 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(smem_u32(tmem_ptr_s), TC_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_s;
+
+  const uint32_t qt = blockIdx.x % p.n_qt, es = blockIdx.x / p.n_qt;
+  const uint32_t t_begin = (uint32_t)(((uint64_t)es * p.n_tiles) / p.n_es);
+  const uint32_t t_end = (uint32_t)(((uint64_t)(es + 1) * p.n_tiles) / p.n_es);
+  const uint32_t n_my = t_end - t_begin;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      mbar_arrive_expect_tx(bar_q, p.n_kc * TC_QCHUNK_BYTES);
+      for (uint32_t kc = 0; kc < p.n_kc; ++kc)
+        tma_load_2d(smem_u32(sQ + (size_t)kc * TC_QCHUNK_BYTES), &tmQ, (int)(kc * TC_BK), (int)(qt * TC_BM), bar_q);
+      uint32_t it = 0;
+      for (uint32_t ti = 0; ti < n_my; ++ti) {
+        const int row0 = (int)((t_begin + ti) * TC_BN);
+        for (uint32_t kc = 0; kc < p.n_kc; ++kc, ++it) {
+          const uint32_t stage = it % S;
+          if (it >= S) mbar_wait(bar_empty + 8 * stage, ((it / S) - 1) & 1);
+          mbar_arrive_expect_tx(bar_full + 8 * stage, TC_ESTAGE_BYTES);
+          tma_load_2d(smem_u32(sE + (size_t)stage * TC_ESTAGE_BYTES), &tmE, (int)(kc * TC_BK), row0,
+                      bar_full + 8 * stage);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer --------------------------------
+    if (lane == 0) {
+      mbar_wait(bar_q, 0);
+      tc_fence_after();
+      uint32_t it = 0;
+      for (uint32_t ti = 0; ti < n_my; ++ti) {
+        const uint32_t acc = ti & 1, use = ti >> 1;
+        if (use > 0) mbar_wait(bar_tempty + 8 * acc, (use - 1) & 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * TC_BN;
+        for (uint32_t kc = 0; kc < p.n_kc; ++kc, ++it) {
+          const uint32_t stage = it % S;
+          mbar_wait(bar_full + 8 * stage, (it / S) & 1);
+          tc_fence_after();
+          const uint64_t adesc = make_sw128_desc(smem_u32(sQ + (size_t)kc * TC_QCHUNK_BYTES));
+          const uint64_t bdesc = make_sw128_desc(smem_u32(sE + (size_t)stage * TC_ESTAGE_BYTES));
+#pragma unroll
+          for (uint32_t k = 0; k < TC_BK / TC_UK; ++k) {
+            // advance 16 bf16 = 32 B inside the swizzle atom: +2 in the (addr >> 4) field
+            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, TC_IDESC, (kc | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(bar_empty + 8 * stage);  // frees the smem stage when these MMAs retire
+        }
+        umma_commit(bar_tfull + 8 * acc);  // accumulator complete
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------ epilogue ----------------------------------
+    const uint32_t ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
+    const uint32_t q = qt * TC_BM + ew * 32 + lane;
+    const bool valid = q < p.nq_valid;
+    uint64_t* myL = p.lists + ((size_t)blockIdx.x * TC_BM + ew * 32 + lane) * C;
+    uint32_t cnt = 0;
+    uint64_t tau_key = 0ull;
+    float tau_f = valid ? -INFINITY : INFINITY;
+
+    auto compact_lane = [&](uint32_t l) {
+      // warp-cooperative: sort lane l's list, keep KP, raise and share its cut-off
+      uint64_t* Ll = p.lists + ((size_t)blockIdx.x * TC_BM + ew * 32 + l) * C;
+      __syncwarp();  // lane l's appended keys must be visible to the whole warp
+      const uint32_t n_l = __shfl_sync(0xffffffffu, cnt, l);
+      const uint32_t q_l = qt * TC_BM + ew * 32 + l;
+      uint64_t kth = warp_compact<NPL>(Ll, n_l, p.KP, lane);
+      if (kth != 0ull) {
+        unsigned long long old = 0ull;
+        if (lane == 0) old = atomicMax(reinterpret_cast<unsigned long long*>(p.gtau + q_l), (unsigned long long)kth);
+        old = __shfl_sync(0xffffffffu, old, 0);
+        if (old > kth) kth = old;
+      }
+      if (lane == l) {
+        cnt = n_l < p.KP ? n_l : p.KP;
+        if (kth > tau_key) {
+          tau_key = kth;
+          tau_f = float_from_ord(key_ord(kth));
+        }
+      }
+    };
+
+    for (uint32_t ti = 0; ti < n_my; ++ti) {
+      const uint32_t acc = ti & 1, use = ti >> 1;
+      const uint32_t row_base = (t_begin + ti) * TC_BN;
+      if (valid) {  // adopt a cut-off published by CTAs scanning other rows for this query
+        const uint64_t g = *((volatile uint64_t*)(p.gtau + q));
+        if (g > tau_key) {
+          tau_key = g;
+          tau_f = float_from_ord(key_ord(g));
+        }
+      }
+      mbar_wait(bar_tfull + 8 * acc, use & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((ew * 32u) << 16) + acc * TC_BN;
+#pragma unroll 1
+      for (uint32_t ch = 0; ch < TC_BN / 32; ++ch) {
+        float v[32];
+        tmem_ld32(taddr + ch * 32, v);
+        if (ch == TC_BN / 32 - 1) {  // accumulator drained: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+        }
+        float mx = v[0];
+#pragma unroll
+        for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
+        const bool hit = mx >= tau_f;  // false for invalid lanes (tau = +inf) and all-NaN
+        if (__any_sync(0xffffffffu, hit)) {
+          // make room first: a chunk can append up to 32 keys
+          uint32_t full = __ballot_sync(0xffffffffu, cnt + 32 > C);
+          while (full) {
+            const uint32_t l = __ffs(full) - 1;
+            full &= full - 1;
+            compact_lane(l);
+          }
+          if (hit) {
+            const uint32_t r0 = row_base + ch * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float s = v[j];
+              if (s >= tau_f) {
+                const uint32_t row = r0 + j;
+                if (row < p.n_rows) {
+                  const uint64_t key = make_key(ord_from_float(s), row);
+                  if (key > tau_key && row_passes(p.flt, p.meta, p.agent, row)) myL[cnt++] = key;
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+
+    // final: order every list, then append what can still matter to the merged list
+    __syncwarp();
+    for (uint32_t l = 0; l < 32; ++l) compact_lane(l);
+    __syncwarp();
+    if (valid && cnt) {
+      const uint64_t g = *((volatile uint64_t*)(p.gtau + q));
+      uint32_t m = 0;
+      while (m < cnt && myL[m] >= g) ++m;
+      if (m) {
+        const uint32_t base = atomicAdd(p.cnt + q, m);
+        uint64_t* out = p.keys + (size_t)q * p.cap;
+        for (uint32_t i = 0; i < m; ++i)
+          if (base + i < p.cap) out[base + i] = myL[i];
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TC_TMEM_COLS);
+  }
+}
+
+// ---- query preparation: normalise + convert to bf16, zero padded to [n_qt*128][ld16] --
+__global__ void query_bf16_kernel(const float* __restrict__ Q, uint32_t ldq, uint32_t dim, uint32_t nq,
+                                  uint32_t nq_pad, __nv_bfloat16* __restrict__ Q16, uint32_t ld16) {
+  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= nq_pad) return;
+  __nv_bfloat16* out = Q16 + (size_t)w * ld16;
+  if (w >= nq) {
+    for (uint32_t d = lane; d < ld16; d += 32) out[d] = __float2bfloat16_rn(0.0f);
+    return;
+  }
+  const float* q = Q + (size_t)w * ldq;
+  float ss = 0.0f;
+  for (uint32_t d = lane; d < dim; d += 32) ss = fmaf(q[d], q[d], ss);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float inv = rsqrtf(ss);
+  for (uint32_t d = lane; d < ld16; d += 32) out[d] = __float2bfloat16_rn(d < dim ? q[d] * inv : 0.0f);
+}
+
+void launch_query_bf16(const float* Q, uint32_t ldq, uint32_t dim, uint32_t nq, uint32_t nq_pad, void* Q16,
+                       uint32_t ld16, cudaStream_t s) {
+  if (!nq_pad) return;
+  const uint32_t threads = 256, wpb = threads / 32;
+  query_bf16_kernel<<<(nq_pad + wpb - 1) / wpb, threads, 0, s>>>(Q, ldq, dim, nq, nq_pad, (__nv_bfloat16*)Q16, ld16);
+}
+
+// ---- host side ---------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+static bool encode_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t rows, uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {inner * 2};
+  cuuint32_t box[2] = {TC_BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static uint32_t tensor_stages(uint32_t n_kc, size_t* total) {
+  const size_t fixed = (size_t)n_kc * TC_QCHUNK_BYTES + (6 + 2 * TC_MAX_STAGES) * 8 + 64;
+  for (uint32_t s = TC_MAX_STAGES; s >= 2; --s) {
+    size_t t = fixed + (size_t)s * TC_ESTAGE_BYTES;
+    if (t <= TC_SMEM_LIMIT) {
+      *total = t;
+      return s;
+    }
+  }
+  *total = 0;
+  return 0;
+}
+
+uint32_t tensor_list_cap(uint32_t KP) { return KP <= 32 ? 128u : 512u; }
+
+bool tensor_scan_eligible(uint32_t ld16, uint32_t KP) {
+  size_t t;
+  return get_encode() != nullptr && KP + 64 <= 512 && tensor_stages(ld16 / TC_BK, &t) != 0;
+}
+
+void tensor_scan_shape(uint32_t nq, int sm_count, uint32_t* n_qt, uint32_t* n_es) {
+  uint32_t qt = (nq + TC_BM - 1) / TC_BM;
+  if (qt > (uint32_t)sm_count) qt = (uint32_t)sm_count;
+  uint32_t es = (uint32_t)sm_count / qt;
+  if (es < 1) es = 1;
+  *n_qt = qt;
+  *n_es = es;
+}
+
+size_t tensor_scratch_bytes(uint32_t KP, int sm_count) {
+  return (size_t)sm_count * TC_BM * tensor_list_cap(KP) * 8;
+}
+
+cudaError_t launch_tensor_scan(const StoreView& st, const void* Q16, uint32_t q0, uint32_t nq,
+                               const DevFilter& flt, const CandView& cv, uint64_t* lists, int sm_count,
+                               cudaStream_t s) {
+  if (!nq || !st.n_rows) return cudaSuccess;
+  uint32_t n_qt, n_es;
+  tensor_scan_shape(nq, sm_count, &n_qt, &n_es);
+  if (nq > n_qt * TC_BM) return cudaErrorInvalidValue;  // caller splits larger batches
+  TensorParams p;
+  p.n_rows = st.n_rows;
+  p.n_tiles = (st.n_rows + TC_BN - 1) / TC_BN;
+  if (n_es > p.n_tiles) n_es = p.n_tiles;
+  p.n_kc = st.ld16 / TC_BK;
+  p.n_qt = n_qt;
+  p.n_es = n_es;
+  p.nq_valid = nq;
+  p.KP = cv.KP;
+  size_t smem;
+  p.stages = tensor_stages(p.n_kc, &smem);
+  if (!p.stages) return cudaErrorInvalidConfiguration;
+  p.meta = st.meta;
+  p.agent = st.agent;
+  p.flt = flt;
+  p.lists = lists;
+  p.keys = cv.keys + (size_t)(q0 - cv.q_base) * cv.cap;
+  p.cnt = cv.cnt + q0;
+  p.gtau = cv.gtau + q0;
+  p.cap = cv.cap;
+  CUtensorMap tmQ, tmE;
+  const __nv_bfloat16* qbase = (const __nv_bfloat16*)Q16 + (size_t)q0 * st.ld16;
+  if (!encode_2d(&tmQ, qbase, st.ld16, (uint64_t)n_qt * TC_BM, TC_BM)) return cudaErrorInvalidValue;
+  if (!encode_2d(&tmE, st.E16, st.ld16, st.n_rows, TC_BN)) return cudaErrorInvalidValue;
+  const uint32_t grid = n_qt * n_es;
+  cudaError_t e;
+  if (tensor_list_cap(cv.KP) == 128) {
+    e = cudaFuncSetAttribute(tensor_scan_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    tensor_scan_kernel<4><<<grid, TC_THREADS, smem, s>>>(tmQ, tmE, p);
+  } else {
+    e = cudaFuncSetAttribute(tensor_scan_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    tensor_scan_kernel<16><<<grid, TC_THREADS, smem, s>>>(tmQ, tmE, p);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace cx

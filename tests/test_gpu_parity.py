@@ -90,6 +90,38 @@ def test_shapes(n, d, b, k):
     assert_batch_equal(g, o, Q, k)
 
 
+@pytest.mark.parametrize("n,d,b,k", [
+    (5000, 384, 16, 10), (20_000, 384, 200, 10), (3000, 128, 33, 5), (8000, 384, 130, 30),
+    (50_000, 384, 1024, 10), (4000, 100, 40, 10), (6000, 640, 17, 10), (700, 384, 129, 3),
+])
+def test_tensor_pass_parity(n, d, b, k):
+    """K2 (tcgen05 bf16 pass) nominates, K3 rescores: results must equal the oracle bit for bit."""
+    corpus = synth.make_corpus(n, d, zero_row=True, seed=synth.SEED + 3 * n + d)
+    Q = synth.make_queries(corpus, b, seed=synth.SEED + n + 1)
+    g, o, _ = build_pair(corpus)
+    g.set_option("force_path", 2)
+    assert_batch_equal(g, o, Q, k)
+    st = g.stats()
+    assert st["queries_tensor"] > 0, st
+    assert st["queries_tensor"] + st["queries_stream"] >= 0.9 * b, st  # few exact-path fallbacks
+
+
+def test_tensor_pass_filters_and_dead_rows():
+    corpus = synth.make_corpus(9000, 384, seed=41)
+    Q = synth.make_queries(corpus, 64, seed=41)
+    g, o, ids = build_pair(corpus)
+    for r in range(0, 9000, 3):
+        g.set_metadata(ids[r].tobytes(), "fact" if r % 2 else "event", "a1")
+        o.set_metadata(ids[r].tobytes(), "fact" if r % 2 else "event", "a1")
+    for r in range(5, 9000, 11):
+        g.remove(ids[r].tobytes())
+        o.remove(ids[r].tobytes())
+    g.set_option("force_path", 2)
+    assert_batch_equal(g, o, Q, 10, VectorFilter().with_kinds(["fact"]), Filter(kinds=["fact"]))
+    assert_batch_equal(g, o, Q, 10)
+    assert g.stats()["queries_tensor"] > 0
+
+
 def test_non_normalised_and_duplicates():
     corpus = synth.make_corpus(8000, 384, normalise=False, dup_frac=0.2, seed=7)
     Q = synth.make_queries(corpus, 6, seed=7) * np.float32(3.0)
