@@ -327,13 +327,30 @@ def main():
     ld = (a.dim + 3) // 4 * 4
     alg_bytes = a.rows * ld * 4
     roof = None
-    if launches and ns:
+    used_tensor = (st1["queries_tensor"] - st0["queries_tensor"]) > 0
+    if launches and ns and not used_tensor:
         sec = ns * 1e-9 / launches
         achieved = alg_bytes / sec / 1e9
         roof = {"bound": "hbm", "kernel": "stream_scan_kernel", "achieved": achieved, "peak": pk["hbm_gbs"],
                 "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": None,
                 "peak_source": pk["source"], "us_per_launch": sec * 1e6, "launches": launches,
                 "algorithmic_bytes_per_launch": alg_bytes,
+                "kernel_share_of_step": (ns * 1e-6) / ms_total}
+    elif launches and ns:
+        # tensor pass: 2*D flops per scored (query,row) pair; the kernel runs inside a
+        # seconds-long loop, so the sustained cuBLAS figure is the denominator (burst also given)
+        sec = ns * 1e-9 / launches
+        q_per_launch = a.batch * a.steps / launches
+        flops = 2.0 * a.dim * q_per_launch * a.rows
+        achieved = flops / sec / 1e12
+        hbm_bytes = a.rows * ((a.dim + 63) // 64 * 64) * 2  # bf16 shadow streamed once per launch
+        roof = {"bound": "tensor", "kernel": "tensor_scan_kernel", "achieved": achieved,
+                "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                "frac": achieved / pk["bf16_tflops_sustained"], "frac_of_burst": achieved / pk["bf16_tflops"],
+                "traffic": None, "peak_source": pk["source"], "us_per_launch": sec * 1e6, "launches": launches,
+                "algorithmic_flops_per_launch": flops,
+                "hbm_floor_us": hbm_bytes / (pk["hbm_gbs"] * 1e9) * 1e6,
+                "hbm_gbs_of_shadow_stream": hbm_bytes / sec / 1e9,
                 "kernel_share_of_step": (ns * 1e-6) / ms_total}
 
     # ---- CPU baseline (rank 0, N=1 only) -------------------------------------------
