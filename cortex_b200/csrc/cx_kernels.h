@@ -75,14 +75,17 @@ cudaError_t launch_select_rescore(const StoreView& st, const QueryView& qv, uint
 // K2: tcgen05 bf16 pass over the normalised shadow matrix.  Q16 = normalised bf16 queries
 // [round_up(nq_total,128)][ld16] made by launch_query_bf16.  One launch serves at most
 // sm_count*128 queries starting at q0; `lists` is scratch of tensor_scratch_bytes().
-bool tensor_scan_eligible(uint32_t ld16, uint32_t KP);
+// cv.KP must be tensor_keep(k) (32 / 64 / 128 scores tracked per query in registers).
+uint32_t tensor_keep(uint32_t k);
+bool tensor_scan_eligible(uint32_t ld16, uint32_t k);
 void tensor_scan_shape(uint32_t nq, int sm_count, uint32_t* n_qt, uint32_t* n_es);
-size_t tensor_scratch_bytes(uint32_t KP, int sm_count);
+size_t tensor_scratch_bytes(int sm_count);
 void launch_query_bf16(const float* Q, uint32_t ldq, uint32_t dim, uint32_t nq, uint32_t nq_pad, void* Q16,
                        uint32_t ld16, cudaStream_t s);
+// check_rows: a filter is active or rows were removed -> test metadata before nominating a row
 cudaError_t launch_tensor_scan(const StoreView& st, const void* Q16, uint32_t q0, uint32_t nq,
-                               const DevFilter& flt, const CandView& cv, uint64_t* lists, int sm_count,
-                               cudaStream_t s);
+                               const DevFilter& flt, bool check_rows, const CandView& cv, uint64_t* lists,
+                               int sm_count, cudaStream_t s);
 
 // Exact path: every row scored with reference arithmetic -> keys[n_rows] for one query
 void launch_exact_keys(const StoreView& st, const QueryView& qv, uint32_t q, const DevFilter& flt,

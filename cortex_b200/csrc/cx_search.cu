@@ -129,6 +129,7 @@ struct Plan {
   uint64_t B;
   uint32_t qlen, ldq, kd;
   uint32_t G, KP;     // streaming pass: producer groups, keys kept per group
+  uint32_t KPt;       // tensor pass: scores tracked per query (32 / 64 / 128)
   uint32_t cap;       // merged-list capacity per query for the primary pass
   uint32_t cap_retry; // ... and for streaming retries of single queries after a tensor pass
   uint32_t q_per_launch;  // tensor pass: queries per launch
@@ -152,15 +153,20 @@ Plan make_plan(const cx_index* h, uint64_t B, uint32_t qlen, uint32_t ldq, uint3
            stream_scan_smem(h->ld, 8, p.KP) != 0 && select_smem(p.cap, h->ld) <= 227 * 1024 &&
            h->force_path != PATH_EXACT;
   p.tensor = false;
+  p.KPt = 0;
   if (p.fast && h->dE16 && h->force_path != PATH_STREAM &&
-      (B >= h->tensor_min_batch || h->force_path == PATH_TENSOR) && tensor_scan_eligible(h->ld16, p.KP)) {
+      (B >= h->tensor_min_batch || h->force_path == PATH_TENSOR) && tensor_scan_eligible(h->ld16, kd)) {
     p.tensor = true;
+    p.KPt = tensor_keep(kd);
     p.q_per_launch = (uint32_t)h->sm_count * 128u;
     uint32_t n_qt, n_es;
     tensor_scan_shape((uint32_t)(B < p.q_per_launch ? B : p.q_per_launch), h->sm_count, &n_qt, &n_es);
     p.cap_retry = p.cap;
-    p.cap = n_es * p.KP;
-    if (p.cap < 2 * p.KP) p.cap = 2 * p.KP;
+    // the shared cut-off is the best split-local KPt-th score, so every split appends up to about
+    // KPt keys; 50 % slack for splits that finish against an older cut-off (excess is detected
+    // by the select kernel and sent to a fallback, never lost silently)
+    p.cap = n_es * p.KPt + (n_es * p.KPt) / 2 + 64;
+    if (p.cap > 16384) p.cap = 16384;
   }
   return p;
 }
@@ -176,7 +182,7 @@ size_t carve_bufs(void* base, const cx_index* h, const Plan& pl, uint32_t n_excl
   sb->cand_keys = pl.fast ? c.take<uint64_t>((size_t)pl.B * pl.cap) : nullptr;
   if (pl.tensor) {
     sb->q16 = c.take<uint16_t>(align_up(pl.B, 128) * h->ld16);
-    sb->lists = (uint64_t*)c.take<char>(tensor_scratch_bytes(pl.KP, h->sm_count));
+    sb->lists = (uint64_t*)c.take<char>(tensor_scratch_bytes(h->sm_count));
     sb->retry_keys = c.take<uint64_t>(pl.cap_retry);
   }
   sb->n_total = c.take<uint32_t>(4);
@@ -253,9 +259,11 @@ cx_status run_search(cx_index* h, Workspace* ws, const FilterHost& fh, const Sea
     }
     if (h->profile) CU(cudaEventRecord(ws->ev0, s));
     if (pl.tensor) {
+      cv.KP = pl.KPt;
+      const bool check_rows = flt.has_kinds || flt.has_agent || flt.n_excl || h->n_live != h->n_rows;
       for (uint64_t q0 = 0; q0 < B; q0 += pl.q_per_launch) {
         const uint32_t nq = (uint32_t)(B - q0 < pl.q_per_launch ? B - q0 : pl.q_per_launch);
-        CU(launch_tensor_scan(st, sb.q16, (uint32_t)q0, nq, flt, cv, sb.lists, h->sm_count, s));
+        CU(launch_tensor_scan(st, sb.q16, (uint32_t)q0, nq, flt, check_rows, cv, sb.lists, h->sm_count, s));
         ++n_pass;
       }
     } else {
@@ -294,6 +302,7 @@ cx_status run_search(cx_index* h, Workspace* ws, const FilterHost& fh, const Sea
       cr.keys = sb.retry_keys;
       cr.cap = pl.cap_retry;
       cr.G = pl.G;
+      cr.KP = pl.KP;
       for (uint32_t b : redo) {
         cr.q_base = b;
         CU(launch_stream_scan(st, qv, b, 1, flt, cr, h->sm_count, s));

@@ -14,11 +14,12 @@
 //           accumulators in TMEM, double buffered (2 x 256 columns)
 //   warp 2  TMEM allocation
 //   warps 4-7  epilogue: lane == query.  tcgen05.ld 32 columns at a time; a running
-//           max against the query's cut-off tau is the whole common path.  Scores at or
-//           above tau are appended to the thread's private list (global scratch, L2
-//           resident); full lists are compacted to the best KP by the warp
-//           cooperatively (bitonic sort in registers), which raises tau; tau is shared
-//           between the CTAs that scan other row ranges for the same queries.
+//           max against the query's cut-off is the whole common path.  Every thread
+//           keeps the best KP scores it has seen in registers (branch-free insertion),
+//           so its cut-off is always exactly the KP-th best; scores at or above the
+//           cut-off are appended to the thread's private list (global scratch, L2
+//           resident).  The cut-off is shared between the CTAs that scan other row
+//           ranges for the same queries through one global word per query.
 // CTAs are arranged (query tile) x (row split); CTAs that differ only in the query
 // tile walk the same rows at the same time, so E streams from HBM once and is served
 // to the others from L2.
@@ -41,16 +42,18 @@ constexpr uint32_t TC_ESTAGE_BYTES = TC_BN * TC_BK * 2;  // 32 KB
 constexpr uint32_t TC_MAX_STAGES = 6;
 constexpr uint32_t TC_SMEM_LIMIT = 227 * 1024;
 constexpr uint32_t TC_TMEM_COLS = 512;
+constexpr uint32_t TC_LIST_CAP = 512;  // private list entries per (CTA, query)
 
 struct TensorParams {
   uint32_t n_rows, n_tiles, n_kc;
   uint32_t n_qt, n_es;
   uint32_t nq_valid;
-  uint32_t KP, stages;
+  uint32_t stages;
+  uint32_t check_rows;  // 0: no filter and no removed rows -> skip the per-row metadata test
   const uint32_t* meta;
   const uint32_t* agent;
   DevFilter flt;
-  uint64_t* lists;  // [grid][128][C] private candidate lists (scratch)
+  uint64_t* lists;  // [grid][128][TC_LIST_CAP] private candidate lists (scratch)
   uint64_t* keys;   // merged list per query [nq][cap]
   uint32_t* cnt;
   uint64_t* gtau;
@@ -118,69 +121,12 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 // N >> 3 at bit 17, M >> 4 at bit 24.
 constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((TC_BN >> 3) << 17) | ((TC_BM >> 4) << 24);
 
-// ---- warp-cooperative compaction of one private list --------------------------------
-// Sort (descending) the n <= NPL*32 keys at L across the warp's registers, write the best
-// KP back in order, return the KP-th key (0 if n < KP).  All lanes call it.
-template <int NPL>
-__device__ __forceinline__ uint64_t warp_compact(uint64_t* L, uint32_t n, uint32_t KP, uint32_t lane) {
-  uint64_t k[NPL];
-#pragma unroll
-  for (int i = 0; i < NPL; ++i) {
-    const uint32_t e = i * 32 + lane;
-    k[i] = e < n ? L[e] : 0ull;
-  }
-  constexpr uint32_t N = NPL * 32;
-#pragma unroll
-  for (uint32_t kk = 2; kk <= N; kk <<= 1) {
-#pragma unroll
-    for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
-      if (j >= 32) {
-        const uint32_t ji = j >> 5;
-#pragma unroll
-        for (int i = 0; i < NPL; ++i) {
-          const int pi = i ^ (int)ji;
-          if (pi > i) {
-            const uint32_t e = i * 32 + lane;
-            const bool desc = (e & kk) == 0;
-            const uint64_t a = k[i], b = k[pi];
-            const bool sw = desc ? (a < b) : (a > b);
-            k[i] = sw ? b : a;
-            k[pi] = sw ? a : b;
-          }
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < NPL; ++i) {
-          const uint32_t e = i * 32 + lane;
-          const uint64_t mine = k[i];
-          const uint64_t other = __shfl_xor_sync(0xffffffffu, mine, j);
-          const bool lower = (lane & j) == 0;           // I hold the lower index of the pair
-          const bool desc = (e & kk) == 0;
-          // descending block: lower index keeps the larger key
-          const bool keep_max = (lower == desc);
-          k[i] = keep_max ? (mine > other ? mine : other) : (mine < other ? mine : other);
-        }
-      }
-    }
-  }
-  uint64_t kth = 0ull;
-#pragma unroll
-  for (int i = 0; i < NPL; ++i) {
-    const uint32_t e = i * 32 + lane;
-    if (e < KP && e < n) L[e] = k[i];
-    const uint64_t cand = __shfl_sync(0xffffffffu, k[i], (KP - 1) & 31);
-    if ((uint32_t)i == ((KP - 1) >> 5)) kth = cand;
-  }
-  __syncwarp();
-  return n >= KP ? kth : 0ull;
-}
-
-template <int NPL>
+// KP = scores every epilogue thread tracks in registers (32, 64 or 128)
+template <int KP>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmE,
                    const TensorParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  constexpr uint32_t C = NPL * 32;
   const uint32_t S = p.stages;
   unsigned char* sQ = smem;
   unsigned char* sE = smem + (size_t)p.n_kc * TC_QCHUNK_BYTES;
@@ -267,42 +213,29 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
     const uint32_t q = qt * TC_BM + ew * 32 + lane;
     const bool valid = q < p.nq_valid;
-    uint64_t* myL = p.lists + ((size_t)blockIdx.x * TC_BM + ew * 32 + lane) * C;
+    uint64_t* myL = p.lists + ((size_t)blockIdx.x * TC_BM + ew * 32 + lane) * TC_LIST_CAP;
     uint32_t cnt = 0;
-    uint64_t tau_key = 0ull;
-    float tau_f = valid ? -INFINITY : INFINITY;
-
-    auto compact_lane = [&](uint32_t l) {
-      // warp-cooperative: sort lane l's list, keep KP, raise and share its cut-off
-      uint64_t* Ll = p.lists + ((size_t)blockIdx.x * TC_BM + ew * 32 + l) * C;
-      __syncwarp();  // lane l's appended keys must be visible to the whole warp
-      const uint32_t n_l = __shfl_sync(0xffffffffu, cnt, l);
-      const uint32_t q_l = qt * TC_BM + ew * 32 + l;
-      uint64_t kth = warp_compact<NPL>(Ll, n_l, p.KP, lane);
-      if (kth != 0ull) {
-        unsigned long long old = 0ull;
-        if (lane == 0) old = atomicMax(reinterpret_cast<unsigned long long*>(p.gtau + q_l), (unsigned long long)kth);
-        old = __shfl_sync(0xffffffffu, old, 0);
-        if (old > kth) kth = old;
-      }
-      if (lane == l) {
-        cnt = n_l < p.KP ? n_l : p.KP;
-        if (kth > tau_key) {
-          tau_key = kth;
-          tau_f = float_from_ord(key_ord(kth));
-        }
-      }
-    };
+    bool overflow = false;
+    float best[KP];  // the KP best scores this thread has seen, descending
+#pragma unroll
+    for (int i = 0; i < KP; ++i) best[i] = -INFINITY;
+    float g_f = -INFINITY;      // cut-off adopted from other CTAs
+    float pub_f = -INFINITY;    // what this thread last published
+    float tau = valid ? -INFINITY : INFINITY;
 
     for (uint32_t ti = 0; ti < n_my; ++ti) {
       const uint32_t acc = ti & 1, use = ti >> 1;
       const uint32_t row_base = (t_begin + ti) * TC_BN;
-      if (valid) {  // adopt a cut-off published by CTAs scanning other rows for this query
-        const uint64_t g = *((volatile uint64_t*)(p.gtau + q));
-        if (g > tau_key) {
-          tau_key = g;
-          tau_f = float_from_ord(key_ord(g));
+      if (valid) {
+        // share cut-offs with the CTAs scanning other rows for this query
+        if (best[KP - 1] > pub_f) {
+          pub_f = best[KP - 1];
+          atomicMax(reinterpret_cast<unsigned long long*>(p.gtau + q),
+                    (unsigned long long)make_key(ord_from_float(pub_f), 0xFFFFFFFFu));
         }
+        const uint64_t g = *((volatile uint64_t*)(p.gtau + q));
+        if (g != 0ull) g_f = fmaxf(g_f, float_from_ord(key_ord(g)));
+        tau = fmaxf(best[KP - 1], g_f);
       }
       mbar_wait(bar_tfull + 8 * acc, use & 1);
       tc_fence_after();
@@ -319,26 +252,25 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         float mx = v[0];
 #pragma unroll
         for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
-        const bool hit = mx >= tau_f;  // false for invalid lanes (tau = +inf) and all-NaN
-        if (__any_sync(0xffffffffu, hit)) {
-          // make room first: a chunk can append up to 32 keys
-          uint32_t full = __ballot_sync(0xffffffffu, cnt + 32 > C);
-          while (full) {
-            const uint32_t l = __ffs(full) - 1;
-            full &= full - 1;
-            compact_lane(l);
-          }
-          if (hit) {
-            const uint32_t r0 = row_base + ch * 32;
+        if (__any_sync(0xffffffffu, mx >= tau)) {  // false for padded lanes (tau = +inf) and NaN
+          const uint32_t r0 = row_base + ch * 32;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float s = v[j];
-              if (s >= tau_f) {
-                const uint32_t row = r0 + j;
-                if (row < p.n_rows) {
-                  const uint64_t key = make_key(ord_from_float(s), row);
-                  if (key > tau_key && row_passes(p.flt, p.meta, p.agent, row)) myL[cnt++] = key;
-                }
+          for (int j = 0; j < 32; ++j) {
+            const float s = v[j];
+            bool h = (s >= tau) && (r0 + j < p.n_rows);
+            if (p.check_rows && h) h = row_passes(p.flt, p.meta, p.agent, r0 + j);
+            if (__any_sync(0xffffffffu, h)) {
+              float x = h ? s : -INFINITY;
+#pragma unroll
+              for (int i = 0; i < KP; ++i) {  // branch-free insertion into the sorted registers
+                const float hi = fmaxf(best[i], x);
+                x = fminf(best[i], x);
+                best[i] = hi;
+              }
+              if (h) {
+                if (cnt < TC_LIST_CAP) myL[cnt++] = make_key(ord_from_float(s), r0 + j);
+                else overflow = true;
+                tau = fmaxf(best[KP - 1], g_f);
               }
             }
           }
@@ -346,19 +278,26 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     }
 
-    // final: order every list, then append what can still matter to the merged list
-    __syncwarp();
-    for (uint32_t l = 0; l < 32; ++l) compact_lane(l);
-    __syncwarp();
-    if (valid && cnt) {
+    // final: publish, then append what can still matter to the query's merged list
+    if (valid) {
+      if (best[KP - 1] > pub_f)
+        atomicMax(reinterpret_cast<unsigned long long*>(p.gtau + q),
+                  (unsigned long long)make_key(ord_from_float(best[KP - 1]), 0xFFFFFFFFu));
       const uint64_t g = *((volatile uint64_t*)(p.gtau + q));
       uint32_t m = 0;
-      while (m < cnt && myL[m] >= g) ++m;
+      for (uint32_t i = 0; i < cnt; ++i) m += myL[i] >= g;
+      if (overflow) m = p.cap + 1;  // makes cnt > cap: the select kernel sends the query to a fallback
       if (m) {
-        const uint32_t base = atomicAdd(p.cnt + q, m);
+        uint32_t pos = atomicAdd(p.cnt + q, m);
         uint64_t* out = p.keys + (size_t)q * p.cap;
-        for (uint32_t i = 0; i < m; ++i)
-          if (base + i < p.cap) out[base + i] = myL[i];
+        if (!overflow)
+          for (uint32_t i = 0; i < cnt; ++i) {
+            const uint64_t key = myL[i];
+            if (key >= g) {
+              if (pos < p.cap) out[pos] = key;
+              ++pos;
+            }
+          }
       }
     }
   }
@@ -441,11 +380,17 @@ static uint32_t tensor_stages(uint32_t n_kc, size_t* total) {
   return 0;
 }
 
-uint32_t tensor_list_cap(uint32_t KP) { return KP <= 32 ? 128u : 512u; }
+// scores tracked per query by the tensor pass for a request of k neighbours (0 = not served)
+uint32_t tensor_keep(uint32_t k) {
+  if (k + 16 <= 32) return 32;
+  if (k + 16 <= 64) return 64;
+  if (k + 16 <= 128) return 128;
+  return 0;
+}
 
-bool tensor_scan_eligible(uint32_t ld16, uint32_t KP) {
+bool tensor_scan_eligible(uint32_t ld16, uint32_t k) {
   size_t t;
-  return get_encode() != nullptr && KP + 64 <= 512 && tensor_stages(ld16 / TC_BK, &t) != 0;
+  return get_encode() != nullptr && tensor_keep(k) != 0 && tensor_stages(ld16 / TC_BK, &t) != 0;
 }
 
 void tensor_scan_shape(uint32_t nq, int sm_count, uint32_t* n_qt, uint32_t* n_es) {
@@ -457,13 +402,20 @@ void tensor_scan_shape(uint32_t nq, int sm_count, uint32_t* n_qt, uint32_t* n_es
   *n_es = es;
 }
 
-size_t tensor_scratch_bytes(uint32_t KP, int sm_count) {
-  return (size_t)sm_count * TC_BM * tensor_list_cap(KP) * 8;
+size_t tensor_scratch_bytes(int sm_count) { return (size_t)sm_count * TC_BM * TC_LIST_CAP * 8; }
+
+template <int KP>
+static cudaError_t launch_kp(const CUtensorMap& tmQ, const CUtensorMap& tmE, const TensorParams& p, uint32_t grid,
+                             size_t smem, cudaStream_t s) {
+  cudaError_t e = cudaFuncSetAttribute(tensor_scan_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  tensor_scan_kernel<KP><<<grid, TC_THREADS, smem, s>>>(tmQ, tmE, p);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_tensor_scan(const StoreView& st, const void* Q16, uint32_t q0, uint32_t nq,
-                               const DevFilter& flt, const CandView& cv, uint64_t* lists, int sm_count,
-                               cudaStream_t s) {
+                               const DevFilter& flt, bool check_rows, const CandView& cv, uint64_t* lists,
+                               int sm_count, cudaStream_t s) {
   if (!nq || !st.n_rows) return cudaSuccess;
   uint32_t n_qt, n_es;
   tensor_scan_shape(nq, sm_count, &n_qt, &n_es);
@@ -476,10 +428,10 @@ cudaError_t launch_tensor_scan(const StoreView& st, const void* Q16, uint32_t q0
   p.n_qt = n_qt;
   p.n_es = n_es;
   p.nq_valid = nq;
-  p.KP = cv.KP;
   size_t smem;
   p.stages = tensor_stages(p.n_kc, &smem);
   if (!p.stages) return cudaErrorInvalidConfiguration;
+  p.check_rows = check_rows ? 1u : 0u;
   p.meta = st.meta;
   p.agent = st.agent;
   p.flt = flt;
@@ -493,17 +445,12 @@ cudaError_t launch_tensor_scan(const StoreView& st, const void* Q16, uint32_t q0
   if (!encode_2d(&tmQ, qbase, st.ld16, (uint64_t)n_qt * TC_BM, TC_BM)) return cudaErrorInvalidValue;
   if (!encode_2d(&tmE, st.E16, st.ld16, st.n_rows, TC_BN)) return cudaErrorInvalidValue;
   const uint32_t grid = n_qt * n_es;
-  cudaError_t e;
-  if (tensor_list_cap(cv.KP) == 128) {
-    e = cudaFuncSetAttribute(tensor_scan_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    tensor_scan_kernel<4><<<grid, TC_THREADS, smem, s>>>(tmQ, tmE, p);
-  } else {
-    e = cudaFuncSetAttribute(tensor_scan_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    tensor_scan_kernel<16><<<grid, TC_THREADS, smem, s>>>(tmQ, tmE, p);
+  switch (cv.KP) {
+    case 32: return launch_kp<32>(tmQ, tmE, p, grid, smem, s);
+    case 64: return launch_kp<64>(tmQ, tmE, p, grid, smem, s);
+    case 128: return launch_kp<128>(tmQ, tmE, p, grid, smem, s);
+    default: return cudaErrorInvalidValue;
   }
-  return cudaGetLastError();
 }
 
 }  // namespace cx
