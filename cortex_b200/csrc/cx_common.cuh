@@ -167,6 +167,53 @@ __device__ __forceinline__ void bitonic_sort_desc(uint64_t* a, uint32_t n, uint3
     }
   }
 }
+// ---- block-wide k-th largest (1-based) of n uint32 values: MSB-first radix select ----
+// get(i) returns value i.  scratch: 258 words of shared memory.  All threads of the
+// block call it (it synchronises with __syncthreads); requires 1 <= k <= n.
+template <typename GetFn>
+__device__ __forceinline__ uint32_t block_kth_largest(GetFn get, uint32_t n, uint32_t k, uint32_t* scratch,
+                                                      uint32_t tid, uint32_t nthreads) {
+  uint32_t prefix = 0, mask = 0;
+#pragma unroll 1
+  for (int pass = 3; pass >= 0; --pass) {
+    const uint32_t shift = 8u * (uint32_t)pass;
+    for (uint32_t i = tid; i < 256; i += nthreads) scratch[i] = 0;
+    __syncthreads();
+    for (uint32_t i = tid; i < n; i += nthreads) {
+      const uint32_t v = get(i);
+      if ((v & mask) == prefix) atomicAdd(&scratch[(v >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (tid < 32) {  // lane l owns bins [8l, 8l+8); suffix sums over lanes pick the digit
+      uint32_t s = 0;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) s += scratch[8 * tid + b];
+      uint32_t suf = s;  // becomes sum over lanes >= tid
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_down_sync(0xffffffffu, suf, o);
+        if (tid + o < 32) suf += t;
+      }
+      const uint32_t above = suf - s;  // sum over lanes > tid
+      if (suf >= k && above < k) {
+        uint32_t acc = above;
+        int d = 7;
+        for (; d > 0; --d) {
+          if (acc + scratch[8 * tid + d] >= k) break;
+          acc += scratch[8 * tid + d];
+        }
+        scratch[256] = 8 * tid + (uint32_t)d;
+        scratch[257] = k - acc;
+      }
+    }
+    __syncthreads();
+    prefix |= scratch[256] << shift;
+    mask |= 255u << shift;
+    k = scratch[257];
+    __syncthreads();
+  }
+  return prefix;
+}
 #endif  // __CUDACC__
 
 }  // namespace cx

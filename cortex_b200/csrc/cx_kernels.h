@@ -82,6 +82,12 @@ void tensor_scan_shape(uint32_t nq, int sm_count, uint32_t* n_qt, uint32_t* n_es
 size_t tensor_scratch_bytes(int sm_count);
 void launch_query_bf16(const float* Q, uint32_t ldq, uint32_t dim, uint32_t nq, uint32_t nq_pad, void* Q16,
                        uint32_t ld16, cudaStream_t s);
+// Bootstrap of the per-query cut-off: scores of `n_slots` sampled row tiles are dumped
+// ([nq][n_slots*256] floats) and cv.gtau[q] is set to the cv.KP-th best of them.
+uint32_t tensor_sample_tiles(uint32_t n_rows, uint32_t nq);
+cudaError_t launch_tensor_bootstrap(const StoreView& st, const void* Q16, uint32_t q0, uint32_t nq,
+                                    const DevFilter& flt, bool check_rows, const CandView& cv, float* dump,
+                                    uint32_t n_slots, int sm_count, cudaStream_t s);
 // check_rows: a filter is active or rows were removed -> test metadata before nominating a row
 cudaError_t launch_tensor_scan(const StoreView& st, const void* Q16, uint32_t q0, uint32_t nq,
                                const DevFilter& flt, bool check_rows, const CandView& cv, uint64_t* lists,

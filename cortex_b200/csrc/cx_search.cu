@@ -106,6 +106,7 @@ struct SearchBufs {
   uint16_t* q16 = nullptr;        // normalised bf16 queries (tensor pass)
   uint64_t* lists = nullptr;      // tensor pass private-list scratch
   uint64_t* retry_keys = nullptr; // merged list for single-query streaming retries
+  float* dump = nullptr;          // sampled scores for the tensor pass's cut-off bootstrap
   char* res = nullptr;       // ResultBlock (device) when results are workspace-owned
   uint32_t* ok = nullptr;
   uint32_t* n = nullptr;
@@ -129,7 +130,8 @@ struct Plan {
   uint64_t B;
   uint32_t qlen, ldq, kd;
   uint32_t G, KP;     // streaming pass: producer groups, keys kept per group
-  uint32_t KPt;       // tensor pass: scores tracked per query (32 / 64 / 128)
+  uint32_t KPt;       // tensor pass: keys kept per query (32 / 64 / 128)
+  uint32_t n_slots;   // tensor pass: sampled row tiles for the cut-off bootstrap
   uint32_t cap;       // merged-list capacity per query for the primary pass
   uint32_t cap_retry; // ... and for streaming retries of single queries after a tensor pass
   uint32_t q_per_launch;  // tensor pass: queries per launch
@@ -154,6 +156,7 @@ Plan make_plan(const cx_index* h, uint64_t B, uint32_t qlen, uint32_t ldq, uint3
            h->force_path != PATH_EXACT;
   p.tensor = false;
   p.KPt = 0;
+  p.n_slots = 0;
   if (p.fast && h->dE16 && h->force_path != PATH_STREAM &&
       (B >= h->tensor_min_batch || h->force_path == PATH_TENSOR) && tensor_scan_eligible(h->ld16, kd)) {
     p.tensor = true;
@@ -162,11 +165,14 @@ Plan make_plan(const cx_index* h, uint64_t B, uint32_t qlen, uint32_t ldq, uint3
     uint32_t n_qt, n_es;
     tensor_scan_shape((uint32_t)(B < p.q_per_launch ? B : p.q_per_launch), h->sm_count, &n_qt, &n_es);
     p.cap_retry = p.cap;
-    // the shared cut-off is the best split-local KPt-th score, so every split appends up to about
-    // KPt keys; 50 % slack for splits that finish against an older cut-off (excess is detected
-    // by the select kernel and sent to a fallback, never lost silently)
-    p.cap = n_es * p.KPt + (n_es * p.KPt) / 2 + 64;
-    if (p.cap > 16384) p.cap = 16384;
+    // the cut-off comes from a sample of S rows, so about KPt * rows / S keys per query clear it;
+    // twice that plus slack (excess is detected by the select kernel and sent to a fallback,
+    // never lost silently)
+    p.n_slots = tensor_sample_tiles(n_rows, (uint32_t)(B < p.q_per_launch ? B : p.q_per_launch));
+    const uint64_t expected = (uint64_t)p.KPt * n_rows / ((uint64_t)p.n_slots * 256);
+    uint64_t cap = 2 * expected + 4 * p.KPt + 64;
+    if (cap > 16384) cap = 16384;
+    p.cap = (uint32_t)cap;
   }
   return p;
 }
@@ -184,6 +190,8 @@ size_t carve_bufs(void* base, const cx_index* h, const Plan& pl, uint32_t n_excl
     sb->q16 = c.take<uint16_t>(align_up(pl.B, 128) * h->ld16);
     sb->lists = (uint64_t*)c.take<char>(tensor_scratch_bytes(h->sm_count));
     sb->retry_keys = c.take<uint64_t>(pl.cap_retry);
+    const uint64_t nq_launch = pl.B < pl.q_per_launch ? pl.B : pl.q_per_launch;
+    sb->dump = c.take<float>(nq_launch * pl.n_slots * 256);
   }
   sb->n_total = c.take<uint32_t>(4);
   const ResultBlock rb = ResultBlock::make(pl.B, pl.kd);
@@ -263,7 +271,10 @@ cx_status run_search(cx_index* h, Workspace* ws, const FilterHost& fh, const Sea
       const bool check_rows = flt.has_kinds || flt.has_agent || flt.n_excl || h->n_live != h->n_rows;
       for (uint64_t q0 = 0; q0 < B; q0 += pl.q_per_launch) {
         const uint32_t nq = (uint32_t)(B - q0 < pl.q_per_launch ? B - q0 : pl.q_per_launch);
+        CU(launch_tensor_bootstrap(st, sb.q16, (uint32_t)q0, nq, flt, check_rows, cv, sb.dump, pl.n_slots,
+                                   h->sm_count, s));
         CU(launch_tensor_scan(st, sb.q16, (uint32_t)q0, nq, flt, check_rows, cv, sb.lists, h->sm_count, s));
+        h->launches += 2;
         ++n_pass;
       }
     } else {

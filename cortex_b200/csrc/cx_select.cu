@@ -25,6 +25,8 @@ namespace cx {
 constexpr int SEL_THREADS = 512;
 constexpr int SEL_BATCH = 32;    // rows rescored per staging round
 constexpr int SEL_MAX_KS = 256;
+constexpr uint32_t SEL_DIRECT_MAX = 512;  // up to this many candidates are sorted directly
+constexpr uint32_t SEL_K2 = 2048;         // capacity after the radix-select cut
 
 struct SelectParams {
   StoreView st;
@@ -48,7 +50,7 @@ static uint32_t pow2_at_least(uint32_t x) {
 }
 
 struct SelectLayout {
-  size_t keys, q, stage, e, total;
+  size_t keys, keys2, q, stage, e, total;
 };
 
 __host__ __device__ inline SelectLayout select_layout(uint32_t NKmax, uint32_t ld) {
@@ -56,6 +58,8 @@ __host__ __device__ inline SelectLayout select_layout(uint32_t NKmax, uint32_t l
   size_t o = 0;
   L.keys = o;
   o += (size_t)NKmax * 8;
+  L.keys2 = o;
+  o += (size_t)(NKmax > 512 ? 2048 : 0) * 8;
   L.q = o;
   o += (size_t)ld * 4;
   L.stage = o;
@@ -78,6 +82,8 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) select_rescore_kernel(const Se
   float* edist = esim + SEL_MAX_KS;
   float* escore = edist + SEL_MAX_KS;
   __shared__ float s_na, s_simk, s_scorek;
+  __shared__ uint32_t scratch[258];
+  uint64_t* keys2 = reinterpret_cast<uint64_t*>(smem_raw + L.keys2);
 
   const uint32_t q = blockIdx.x, tid = threadIdx.x;
   const uint32_t ld = p.st.ld, dim = p.st.dim;
@@ -93,21 +99,6 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) select_rescore_kernel(const Se
     s_m = 0;
   }
   for (uint32_t d = tid; d < ld; d += SEL_THREADS) q_s[d] = d < p.qlen ? p.Q[(size_t)q * p.ldq + d] : 0.0f;
-  __syncthreads();
-  // keep only keys at or above the final cut-off (groups appended against older, lower ones)
-  for (uint32_t i = tid; i < n_src; i += SEL_THREADS) {
-    const uint64_t key = src[i];
-    if (key >= gt) {
-      const uint32_t pos = atomicAdd(&s_m, 1u);
-      if (pos < p.NKmax) keys[pos] = key;
-    }
-  }
-  __syncthreads();
-  const uint32_t M = min(s_m, p.NKmax);
-  const bool truncated = s_m > p.NKmax;
-  uint32_t NK = 32;
-  while (NK < M) NK <<= 1;
-  for (uint32_t i = M + tid; i < NK; i += SEL_THREADS) keys[i] = 0ull;
   __syncthreads();
   if (tid == SEL_THREADS - 1) {  // query norm, reference order
     float acc = 0.0f;
@@ -126,12 +117,48 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) select_rescore_kernel(const Se
     p.qnorm[q] = na;
     p.rqnorm[q] = __frcp_rn(na);
   }
-  bitonic_sort_desc(keys, NK, tid, SEL_THREADS, [] { __syncthreads(); });
+  // keep only keys at or above the final cut-off (groups appended against older, lower ones)
+  for (uint32_t i = tid; i < n_src; i += SEL_THREADS) {
+    const uint64_t key = src[i];
+    if (key >= gt) {
+      const uint32_t pos = atomicAdd(&s_m, 1u);
+      if (pos < p.NKmax) keys[pos] = key;
+    }
+  }
+  __syncthreads();
+  uint32_t M = min(s_m, p.NKmax);
+  bool truncated = s_m > p.NKmax;
+  unsigned long long U = gt;
+  uint64_t* skeys = keys;
+  if (M > SEL_DIRECT_MAX) {
+    // many candidates: radix-select the KP-th best score, keep only keys at or above it
+    const uint32_t t = block_kth_largest([&](uint32_t i) { return key_ord(keys[i]); }, M, min(p.KP, M), scratch,
+                                         tid, SEL_THREADS);
+    if (tid == 0) s_m = 0;
+    __syncthreads();
+    for (uint32_t i = tid; i < M; i += SEL_THREADS) {
+      const uint64_t key = keys[i];
+      if (key_ord(key) >= t) {
+        const uint32_t pos = atomicAdd(&s_m, 1u);
+        if (pos < SEL_K2) keys2[pos] = key;
+      }
+    }
+    __syncthreads();
+    truncated = truncated || s_m > SEL_K2;
+    M = min(s_m, (uint32_t)SEL_K2);
+    skeys = keys2;
+    const unsigned long long left = (unsigned long long)t << 32;  // everything left behind scores below t
+    if (left > U) U = left;
+  }
+  uint32_t NK = 32;
+  while (NK < M) NK <<= 1;
+  for (uint32_t i = M + tid; i < NK; i += SEL_THREADS) skeys[i] = 0ull;
+  __syncthreads();
+  bitonic_sort_desc(skeys, NK, tid, SEL_THREADS, [] { __syncthreads(); });
   __syncthreads();
   const float na = s_na;
   const uint32_t KS = min(min(M, p.KP), (uint32_t)SEL_MAX_KS);
-  unsigned long long U = gt;
-  if (M > KS && keys[KS] > U) U = keys[KS];
+  if (M > KS && skeys[KS] > U) U = skeys[KS];
 
   // exact rescore, SEL_BATCH rows per round
   const uint32_t warp = tid >> 5, lane = tid & 31, nwarps = SEL_THREADS / 32;
@@ -139,7 +166,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) select_rescore_kernel(const Se
   for (uint32_t base = 0; base < KS; base += SEL_BATCH) {
     const uint32_t nb = min((uint32_t)SEL_BATCH, KS - base);
     for (uint32_t j = warp; j < nb; j += nwarps) {
-      const uint32_t row = key_row(keys[base + j]);
+      const uint32_t row = key_row(skeys[base + j]);
       const float* g = p.st.E + (size_t)row * ld;
       uint32_t d = lane;
       for (; d + 7 * 32 < ld; d += 8 * 32) {  // eight loads in flight per lane
@@ -153,7 +180,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) select_rescore_kernel(const Se
     }
     __syncthreads();
     if (tid < nb) {
-      const uint32_t row = key_row(keys[base + tid]);
+      const uint32_t row = key_row(skeys[base + tid]);
       const float* r = stage + tid * sstride;
       const uint32_t n = p.qlen < dim ? p.qlen : dim;
       float dot = 0.0f;

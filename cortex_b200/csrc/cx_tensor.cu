@@ -13,13 +13,17 @@
 //   warp 1  one thread issues tcgen05.mma (M=128 queries x N=256 rows x K=16),
 //           accumulators in TMEM, double buffered (2 x 256 columns)
 //   warp 2  TMEM allocation
-//   warps 4-7  epilogue: lane == query.  tcgen05.ld 32 columns at a time; a running
-//           max against the query's cut-off is the whole common path.  Every thread
-//           keeps the best KP scores it has seen in registers (branch-free insertion),
-//           so its cut-off is always exactly the KP-th best; scores at or above the
-//           cut-off are appended to the thread's private list (global scratch, L2
-//           resident).  The cut-off is shared between the CTAs that scan other row
-//           ranges for the same queries through one global word per query.
+//   warps 4-7  epilogue: lane == query, tcgen05.ld 32 columns at a time.
+//
+// The pass runs in two modes over the same pipeline:
+//   DUMP  scores of a strided sample of row tiles are written out; tau_select_kernel
+//         turns them into a per-query cut-off tau0 = KP-th best sampled score (a valid
+//         lower bound of the KP-th best over the whole corpus)
+//   SCAN  every row; the common path of the epilogue is a running max against the
+//         query's cut-off.  Scores at or above it are appended to the thread's private
+//         list (global scratch, L2 resident).  A list that fills up is reduced to its
+//         best KP by the warp cooperatively (bitonic sort in registers), which raises
+//         that thread's cut-off and publishes it.
 // CTAs are arranged (query tile) x (row split); CTAs that differ only in the query
 // tile walk the same rows at the same time, so E streams from HBM once and is served
 // to the others from L2.
@@ -42,14 +46,20 @@ constexpr uint32_t TC_ESTAGE_BYTES = TC_BN * TC_BK * 2;  // 32 KB
 constexpr uint32_t TC_MAX_STAGES = 6;
 constexpr uint32_t TC_SMEM_LIMIT = 227 * 1024;
 constexpr uint32_t TC_TMEM_COLS = 512;
-constexpr uint32_t TC_LIST_CAP = 512;  // private list entries per (CTA, query)
+constexpr uint32_t TC_NPL = 16;                 // list entries per lane in a cooperative sort
+constexpr uint32_t TC_LIST_CAP = TC_NPL * 32;   // private list entries per (CTA, query) = 512
+
+enum { TC_MODE_SCAN = 0, TC_MODE_DUMP = 1 };
 
 struct TensorParams {
   uint32_t n_rows, n_tiles, n_kc;
+  uint32_t n_slots;     // tiles visited: n_tiles in SCAN mode, the sample size in DUMP mode
   uint32_t n_qt, n_es;
   uint32_t nq_valid;
   uint32_t stages;
+  uint32_t mode;
   uint32_t check_rows;  // 0: no filter and no removed rows -> skip the per-row metadata test
+  uint32_t KP;
   const uint32_t* meta;
   const uint32_t* agent;
   DevFilter flt;
@@ -58,6 +68,7 @@ struct TensorParams {
   uint32_t* cnt;
   uint64_t* gtau;
   uint32_t cap;
+  float* dump;      // DUMP mode: [nq][n_slots * 256] sampled scores (-inf where not eligible)
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------
@@ -121,8 +132,62 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 // N >> 3 at bit 17, M >> 4 at bit 24.
 constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((TC_BN >> 3) << 17) | ((TC_BM >> 4) << 24);
 
-// KP = scores every epilogue thread tracks in registers (32, 64 or 128)
-template <int KP>
+// ---- warp-cooperative reduction of one private list --------------------------------
+// Sort (descending) the n <= 512 keys at L across the warp's registers, write the best KP
+// back in order, return the KP-th key (0 if n < KP).  All lanes call it.
+__device__ __noinline__ uint64_t warp_compact(uint64_t* L, uint32_t n, uint32_t KP, uint32_t lane) {
+  constexpr int NPL = TC_NPL;
+  uint64_t k[NPL];
+#pragma unroll
+  for (int i = 0; i < NPL; ++i) {
+    const uint32_t e = i * 32 + lane;
+    k[i] = e < n ? L[e] : 0ull;
+  }
+  constexpr uint32_t N = NPL * 32;
+#pragma unroll
+  for (uint32_t kk = 2; kk <= N; kk <<= 1) {
+#pragma unroll
+    for (uint32_t j = kk >> 1; j > 0; j >>= 1) {
+      if (j >= 32) {
+        const uint32_t ji = j >> 5;
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) {
+          const int pi = i ^ (int)ji;
+          if (pi > i) {
+            const uint32_t e = i * 32 + lane;
+            const bool desc = (e & kk) == 0;
+            const uint64_t a = k[i], b = k[pi];
+            const bool sw = desc ? (a < b) : (a > b);
+            k[i] = sw ? b : a;
+            k[pi] = sw ? a : b;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < NPL; ++i) {
+          const uint32_t e = i * 32 + lane;
+          const uint64_t mine = k[i];
+          const uint64_t other = __shfl_xor_sync(0xffffffffu, mine, j);
+          const bool lower = (lane & j) == 0;  // I hold the lower index of the pair
+          const bool desc = (e & kk) == 0;     // descending block: lower index keeps the larger key
+          const bool keep_max = (lower == desc);
+          k[i] = keep_max ? (mine > other ? mine : other) : (mine < other ? mine : other);
+        }
+      }
+    }
+  }
+  uint64_t kth = 0ull;
+#pragma unroll
+  for (int i = 0; i < NPL; ++i) {
+    const uint32_t e = i * 32 + lane;
+    if (e < KP && e < n) L[e] = k[i];
+    const uint64_t cand = __shfl_sync(0xffffffffu, k[i], (KP - 1) & 31);
+    if ((uint32_t)i == ((KP - 1) >> 5)) kth = cand;
+  }
+  __syncwarp();
+  return n >= KP ? kth : 0ull;
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmE,
                    const TensorParams p) {
@@ -158,20 +223,23 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
 
+  // this CTA: query tile qt, slots [s_begin, s_end); slot -> tile is the identity in SCAN
+  // mode and a stride over the whole corpus in DUMP mode
   const uint32_t qt = blockIdx.x % p.n_qt, es = blockIdx.x / p.n_qt;
-  const uint32_t t_begin = (uint32_t)(((uint64_t)es * p.n_tiles) / p.n_es);
-  const uint32_t t_end = (uint32_t)(((uint64_t)(es + 1) * p.n_tiles) / p.n_es);
-  const uint32_t n_my = t_end - t_begin;
+  const uint32_t s_begin = (uint32_t)(((uint64_t)es * p.n_slots) / p.n_es);
+  const uint32_t s_end = (uint32_t)(((uint64_t)(es + 1) * p.n_slots) / p.n_es);
+  const uint32_t n_my = s_end - s_begin;
+  auto tile_of = [&](uint32_t slot) { return (uint32_t)(((uint64_t)slot * p.n_tiles) / p.n_slots); };
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
-    if (lane == 0) {
+    if (lane == 0 && n_my) {
       mbar_arrive_expect_tx(bar_q, p.n_kc * TC_QCHUNK_BYTES);
       for (uint32_t kc = 0; kc < p.n_kc; ++kc)
         tma_load_2d(smem_u32(sQ + (size_t)kc * TC_QCHUNK_BYTES), &tmQ, (int)(kc * TC_BK), (int)(qt * TC_BM), bar_q);
       uint32_t it = 0;
       for (uint32_t ti = 0; ti < n_my; ++ti) {
-        const int row0 = (int)((t_begin + ti) * TC_BN);
+        const int row0 = (int)(tile_of(s_begin + ti) * TC_BN);
         for (uint32_t kc = 0; kc < p.n_kc; ++kc, ++it) {
           const uint32_t stage = it % S;
           if (it >= S) mbar_wait(bar_empty + 8 * stage, ((it / S) - 1) & 1);
@@ -183,7 +251,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer --------------------------------
-    if (lane == 0) {
+    if (lane == 0 && n_my) {
       mbar_wait(bar_q, 0);
       tc_fence_after();
       uint32_t it = 0;
@@ -213,30 +281,19 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
     const uint32_t q = qt * TC_BM + ew * 32 + lane;
     const bool valid = q < p.nq_valid;
-    uint64_t* myL = p.lists + ((size_t)blockIdx.x * TC_BM + ew * 32 + lane) * TC_LIST_CAP;
+    const uint32_t list_slot = blockIdx.x * TC_BM + ew * 32;
+    uint64_t* myL = p.lists + ((size_t)list_slot + lane) * TC_LIST_CAP;
     uint32_t cnt = 0;
-    bool overflow = false;
-    float best[KP];  // the KP best scores this thread has seen, descending
-#pragma unroll
-    for (int i = 0; i < KP; ++i) best[i] = -INFINITY;
-    float g_f = -INFINITY;      // cut-off adopted from other CTAs
-    float pub_f = -INFINITY;    // what this thread last published
+    uint64_t tau_key = 0ull;
     float tau = valid ? -INFINITY : INFINITY;
+    if (valid && p.mode == TC_MODE_SCAN) {
+      tau_key = *((volatile uint64_t*)(p.gtau + q));
+      if (tau_key != 0ull) tau = float_from_ord(key_ord(tau_key));
+    }
 
     for (uint32_t ti = 0; ti < n_my; ++ti) {
       const uint32_t acc = ti & 1, use = ti >> 1;
-      const uint32_t row_base = (t_begin + ti) * TC_BN;
-      if (valid) {
-        // share cut-offs with the CTAs scanning other rows for this query
-        if (best[KP - 1] > pub_f) {
-          pub_f = best[KP - 1];
-          atomicMax(reinterpret_cast<unsigned long long*>(p.gtau + q),
-                    (unsigned long long)make_key(ord_from_float(pub_f), 0xFFFFFFFFu));
-        }
-        const uint64_t g = *((volatile uint64_t*)(p.gtau + q));
-        if (g != 0ull) g_f = fmaxf(g_f, float_from_ord(key_ord(g)));
-        tau = fmaxf(best[KP - 1], g_f);
-      }
+      const uint32_t row_base = tile_of(s_begin + ti) * TC_BN;
       mbar_wait(bar_tfull + 8 * acc, use & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((ew * 32u) << 16) + acc * TC_BN;
@@ -249,28 +306,59 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
         }
+        const uint32_t r0 = row_base + ch * 32;
+        if (p.mode == TC_MODE_DUMP) {
+          if (valid) {
+            float* out = p.dump + (size_t)q * ((size_t)p.n_slots * TC_BN) + (size_t)(s_begin + ti) * TC_BN + ch * 32;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 o;
+              float* po = reinterpret_cast<float*>(&o);
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const uint32_t row = r0 + j + u;
+                bool okr = row < p.n_rows;
+                if (okr && p.check_rows) okr = row_passes(p.flt, p.meta, p.agent, row);
+                po[u] = okr ? v[j + u] : -INFINITY;
+              }
+              *reinterpret_cast<float4*>(out + j) = o;
+            }
+          }
+          continue;
+        }
         float mx = v[0];
 #pragma unroll
         for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
-        if (__any_sync(0xffffffffu, mx >= tau)) {  // false for padded lanes (tau = +inf) and NaN
-          const uint32_t r0 = row_base + ch * 32;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float s = v[j];
-            bool h = (s >= tau) && (r0 + j < p.n_rows);
-            if (p.check_rows && h) h = row_passes(p.flt, p.meta, p.agent, r0 + j);
-            if (__any_sync(0xffffffffu, h)) {
-              float x = h ? s : -INFINITY;
-#pragma unroll
-              for (int i = 0; i < KP; ++i) {  // branch-free insertion into the sorted registers
-                const float hi = fmaxf(best[i], x);
-                x = fminf(best[i], x);
-                best[i] = hi;
+        const bool hit = mx >= tau;  // false for padded lanes (tau = +inf) and all-NaN chunks
+        if (__any_sync(0xffffffffu, hit)) {
+          // make room first: a chunk can append up to 32 keys
+          uint32_t full = __ballot_sync(0xffffffffu, cnt + 32 > TC_LIST_CAP);
+          while (full) {
+            const uint32_t l = __ffs(full) - 1;
+            full &= full - 1;
+            __syncwarp();  // lane l's appended keys must be visible to the whole warp
+            const uint32_t n_l = __shfl_sync(0xffffffffu, cnt, l);
+            uint64_t kth = warp_compact(p.lists + ((size_t)list_slot + l) * TC_LIST_CAP, n_l, p.KP, lane);
+            if (lane == l) {
+              cnt = n_l < p.KP ? n_l : p.KP;
+              if (kth > tau_key) {
+                tau_key = kth;
+                tau = float_from_ord(key_ord(kth));
+                atomicMax(reinterpret_cast<unsigned long long*>(p.gtau + q), (unsigned long long)kth);
               }
-              if (h) {
-                if (cnt < TC_LIST_CAP) myL[cnt++] = make_key(ord_from_float(s), r0 + j);
-                else overflow = true;
-                tau = fmaxf(best[KP - 1], g_f);
+            }
+          }
+          if (hit) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float s = v[j];
+              if (s >= tau) {
+                const uint32_t row = r0 + j;
+                if (row < p.n_rows) {
+                  const uint64_t key = make_key(ord_from_float(s), row);
+                  if (key >= tau_key && (!p.check_rows || row_passes(p.flt, p.meta, p.agent, row)))
+                    myL[cnt++] = key;
+                }
               }
             }
           }
@@ -278,26 +366,21 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
     }
 
-    // final: publish, then append what can still matter to the query's merged list
-    if (valid) {
-      if (best[KP - 1] > pub_f)
-        atomicMax(reinterpret_cast<unsigned long long*>(p.gtau + q),
-                  (unsigned long long)make_key(ord_from_float(best[KP - 1]), 0xFFFFFFFFu));
+    // final (SCAN): append what can still matter to the query's merged list
+    if (p.mode == TC_MODE_SCAN && valid && cnt) {
       const uint64_t g = *((volatile uint64_t*)(p.gtau + q));
       uint32_t m = 0;
       for (uint32_t i = 0; i < cnt; ++i) m += myL[i] >= g;
-      if (overflow) m = p.cap + 1;  // makes cnt > cap: the select kernel sends the query to a fallback
       if (m) {
         uint32_t pos = atomicAdd(p.cnt + q, m);
         uint64_t* out = p.keys + (size_t)q * p.cap;
-        if (!overflow)
-          for (uint32_t i = 0; i < cnt; ++i) {
-            const uint64_t key = myL[i];
-            if (key >= g) {
-              if (pos < p.cap) out[pos] = key;
-              ++pos;
-            }
+        for (uint32_t i = 0; i < cnt; ++i) {
+          const uint64_t key = myL[i];
+          if (key >= g) {
+            if (pos < p.cap) out[pos] = key;
+            ++pos;
           }
+        }
       }
     }
   }
@@ -308,6 +391,31 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tc_fence_after();
     tmem_dealloc(tmem_base, TC_TMEM_COLS);
   }
+}
+
+// ---- cut-off from the sampled scores: tau0[q] = KP-th largest of dump[q][0..S) --------
+__global__ void __launch_bounds__(256) tau_select_kernel(const float* __restrict__ dump, uint32_t S, uint32_t KP,
+                                                         uint64_t* __restrict__ gtau) {
+  __shared__ uint32_t scratch[258];
+  __shared__ uint32_t s_valid;
+  const uint32_t q = blockIdx.x, tid = threadIdx.x;
+  const float* d = dump + (size_t)q * S;
+  if (tid == 0) s_valid = 0;
+  __syncthreads();
+  uint32_t nv = 0;
+  for (uint32_t i = tid; i < S; i += 256) nv += d[i] > -INFINITY;  // false for NaN as well
+  if (nv) atomicAdd(&s_valid, nv);
+  __syncthreads();
+  if (s_valid < KP) {  // not enough eligible sampled rows: no cut-off
+    if (tid == 0) gtau[q] = 0ull;
+    return;
+  }
+  auto get = [&](uint32_t i) {
+    const float x = d[i];
+    return x > -INFINITY ? ord_from_float(x) : 0u;
+  };
+  const uint32_t t = block_kth_largest(get, S, KP, scratch, tid, 256);
+  if (tid == 0) gtau[q] = (uint64_t)t << 32;  // the lowest key with that score
 }
 
 // ---- query preparation: normalise + convert to bf16, zero padded to [n_qt*128][ld16] --
@@ -380,7 +488,7 @@ static uint32_t tensor_stages(uint32_t n_kc, size_t* total) {
   return 0;
 }
 
-// scores tracked per query by the tensor pass for a request of k neighbours (0 = not served)
+// keys kept per query by the tensor pass for a request of k neighbours (0 = not served)
 uint32_t tensor_keep(uint32_t k) {
   if (k + 16 <= 32) return 32;
   if (k + 16 <= 64) return 64;
@@ -404,26 +512,24 @@ void tensor_scan_shape(uint32_t nq, int sm_count, uint32_t* n_qt, uint32_t* n_es
 
 size_t tensor_scratch_bytes(int sm_count) { return (size_t)sm_count * TC_BM * TC_LIST_CAP * 8; }
 
-template <int KP>
-static cudaError_t launch_kp(const CUtensorMap& tmQ, const CUtensorMap& tmE, const TensorParams& p, uint32_t grid,
-                             size_t smem, cudaStream_t s) {
-  cudaError_t e = cudaFuncSetAttribute(tensor_scan_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  tensor_scan_kernel<KP><<<grid, TC_THREADS, smem, s>>>(tmQ, tmE, p);
-  return cudaGetLastError();
+// sampled row tiles for the cut-off bootstrap: more when few queries share the cost
+uint32_t tensor_sample_tiles(uint32_t n_rows, uint32_t nq) {
+  const uint32_t n_tiles = (n_rows + TC_BN - 1) / TC_BN;
+  uint32_t want = nq <= 128 ? 256 : nq <= 512 ? 64 : 32;  // 65536 / 16384 / 8192 rows
+  return want < n_tiles ? want : n_tiles;
 }
 
-cudaError_t launch_tensor_scan(const StoreView& st, const void* Q16, uint32_t q0, uint32_t nq,
-                               const DevFilter& flt, bool check_rows, const CandView& cv, uint64_t* lists,
-                               int sm_count, cudaStream_t s) {
-  if (!nq || !st.n_rows) return cudaSuccess;
+static cudaError_t launch_mode(const StoreView& st, const void* Q16, uint32_t q0, uint32_t nq, const DevFilter& flt,
+                               bool check_rows, const CandView& cv, uint64_t* lists, float* dump, uint32_t n_slots,
+                               uint32_t mode, int sm_count, cudaStream_t s) {
   uint32_t n_qt, n_es;
   tensor_scan_shape(nq, sm_count, &n_qt, &n_es);
   if (nq > n_qt * TC_BM) return cudaErrorInvalidValue;  // caller splits larger batches
   TensorParams p;
   p.n_rows = st.n_rows;
   p.n_tiles = (st.n_rows + TC_BN - 1) / TC_BN;
-  if (n_es > p.n_tiles) n_es = p.n_tiles;
+  p.n_slots = mode == TC_MODE_SCAN ? p.n_tiles : n_slots;
+  if (n_es > p.n_slots) n_es = p.n_slots;
   p.n_kc = st.ld16 / TC_BK;
   p.n_qt = n_qt;
   p.n_es = n_es;
@@ -431,7 +537,9 @@ cudaError_t launch_tensor_scan(const StoreView& st, const void* Q16, uint32_t q0
   size_t smem;
   p.stages = tensor_stages(p.n_kc, &smem);
   if (!p.stages) return cudaErrorInvalidConfiguration;
+  p.mode = mode;
   p.check_rows = check_rows ? 1u : 0u;
+  p.KP = cv.KP;
   p.meta = st.meta;
   p.agent = st.agent;
   p.flt = flt;
@@ -440,17 +548,34 @@ cudaError_t launch_tensor_scan(const StoreView& st, const void* Q16, uint32_t q0
   p.cnt = cv.cnt + q0;
   p.gtau = cv.gtau + q0;
   p.cap = cv.cap;
+  p.dump = dump;
   CUtensorMap tmQ, tmE;
   const __nv_bfloat16* qbase = (const __nv_bfloat16*)Q16 + (size_t)q0 * st.ld16;
   if (!encode_2d(&tmQ, qbase, st.ld16, (uint64_t)n_qt * TC_BM, TC_BM)) return cudaErrorInvalidValue;
   if (!encode_2d(&tmE, st.E16, st.ld16, st.n_rows, TC_BN)) return cudaErrorInvalidValue;
-  const uint32_t grid = n_qt * n_es;
-  switch (cv.KP) {
-    case 32: return launch_kp<32>(tmQ, tmE, p, grid, smem, s);
-    case 64: return launch_kp<64>(tmQ, tmE, p, grid, smem, s);
-    case 128: return launch_kp<128>(tmQ, tmE, p, grid, smem, s);
-    default: return cudaErrorInvalidValue;
-  }
+  cudaError_t e = cudaFuncSetAttribute(tensor_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  tensor_scan_kernel<<<n_qt * n_es, TC_THREADS, smem, s>>>(tmQ, tmE, p);
+  return cudaGetLastError();
+}
+
+// Bootstrap: sample scores -> per-query cut-off in cv.gtau[q0 .. q0+nq).  dump holds
+// nq * n_slots * 256 floats.
+cudaError_t launch_tensor_bootstrap(const StoreView& st, const void* Q16, uint32_t q0, uint32_t nq,
+                                    const DevFilter& flt, bool check_rows, const CandView& cv, float* dump,
+                                    uint32_t n_slots, int sm_count, cudaStream_t s) {
+  if (!nq || !st.n_rows || !n_slots) return cudaSuccess;
+  cudaError_t e = launch_mode(st, Q16, q0, nq, flt, check_rows, cv, nullptr, dump, n_slots, TC_MODE_DUMP, sm_count, s);
+  if (e != cudaSuccess) return e;
+  tau_select_kernel<<<nq, 256, 0, s>>>(dump, n_slots * TC_BN, cv.KP, cv.gtau + q0);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_tensor_scan(const StoreView& st, const void* Q16, uint32_t q0, uint32_t nq,
+                               const DevFilter& flt, bool check_rows, const CandView& cv, uint64_t* lists,
+                               int sm_count, cudaStream_t s) {
+  if (!nq || !st.n_rows) return cudaSuccess;
+  return launch_mode(st, Q16, q0, nq, flt, check_rows, cv, lists, nullptr, 0, TC_MODE_SCAN, sm_count, s);
 }
 
 }  // namespace cx
