@@ -7,13 +7,14 @@
 // self-join (linker/dedup.rs:72-88) all become  scores[B, N] = Qn[B, D] . En[N, D]^T
 // on the NORMALISED bf16 copies (so a score is an approximate cosine).
 //
-// One CTA per SM, 8 warps:
+// One CTA per SM, 12 warps:
 //   warp 0  TMA producer: the CTA's 128-query tile once (resident in smem for the
 //           whole pass), then [256 rows x 64] bf16 boxes of E through a ring of stages
 //   warp 1  one thread issues tcgen05.mma (M=128 queries x N=256 rows x K=16),
 //           accumulators in TMEM, double buffered (2 x 256 columns)
 //   warp 2  TMEM allocation
-//   warps 4-7  epilogue: lane == query, tcgen05.ld 32 columns at a time.
+//   warps 4-11 epilogue: lane == query, two warps per TMEM lane quarter (each takes half
+//           of the 256 columns), tcgen05.ld 32 columns at a time.
 //
 // The pass runs in two modes over the same pipeline:
 //   DUMP  scores of a strided sample of row tiles are written out; tau_select_kernel
@@ -40,7 +41,7 @@ constexpr uint32_t TC_BM = 128;       // queries per CTA (UMMA M, TMEM lanes)
 constexpr uint32_t TC_BN = 256;       // corpus rows per tile (UMMA N, TMEM columns)
 constexpr uint32_t TC_BK = 64;        // bf16 per K chunk = one 128 B swizzle atom
 constexpr uint32_t TC_UK = 16;        // K of one tcgen05.mma for 16-bit inputs
-constexpr uint32_t TC_THREADS = 256;
+constexpr uint32_t TC_THREADS = 384;      // 4 control warps + 8 epilogue warps
 constexpr uint32_t TC_QCHUNK_BYTES = TC_BM * TC_BK * 2;  // 16 KB
 constexpr uint32_t TC_ESTAGE_BYTES = TC_BN * TC_BK * 2;  // 32 KB
 constexpr uint32_t TC_MAX_STAGES = 6;
@@ -213,7 +214,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     for (uint32_t a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, 4);
+      mbar_init(bar_tempty + 8 * a, 8);
     }
     fence_mbar_init();
   }
@@ -278,10 +279,11 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
   } else if (warp >= 4) {
     // ------------------------------ epilogue ----------------------------------
-    const uint32_t ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may read
+    // two warps per TMEM lane quarter: warp w may read lanes 32*(w%4)..; each takes half the columns
+    const uint32_t ew = warp & 3, half = (warp - 4) >> 2;
     const uint32_t q = qt * TC_BM + ew * 32 + lane;
     const bool valid = q < p.nq_valid;
-    const uint32_t list_slot = blockIdx.x * TC_BM + ew * 32;
+    const uint32_t list_slot = blockIdx.x * (2 * TC_BM) + (warp - 4) * 32;
     uint64_t* myL = p.lists + ((size_t)list_slot + lane) * TC_LIST_CAP;
     uint32_t cnt = 0;
     uint64_t tau_key = 0ull;
@@ -290,6 +292,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tau_key = *((volatile uint64_t*)(p.gtau + q));
       if (tau_key != 0ull) tau = float_from_ord(key_ord(tau_key));
     }
+    constexpr uint32_t CH_PER_WARP = TC_BN / 32 / 2;
 
     for (uint32_t ti = 0; ti < n_my; ++ti) {
       const uint32_t acc = ti & 1, use = ti >> 1;
@@ -298,10 +301,11 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((ew * 32u) << 16) + acc * TC_BN;
 #pragma unroll 1
-      for (uint32_t ch = 0; ch < TC_BN / 32; ++ch) {
+      for (uint32_t c = 0; c < CH_PER_WARP; ++c) {
+        const uint32_t ch = half * CH_PER_WARP + c;
         float v[32];
         tmem_ld32(taddr + ch * 32, v);
-        if (ch == TC_BN / 32 - 1) {  // accumulator drained: hand it back to the MMA warp
+        if (c == CH_PER_WARP - 1) {  // this warp's share of the accumulator is drained
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
@@ -326,11 +330,11 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           }
           continue;
         }
-        float mx = v[0];
+        // branch-free hit mask: bit j set when v[j] >= tau (never for padded lanes or NaN)
+        uint32_t m = 0;
 #pragma unroll
-        for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
-        const bool hit = mx >= tau;  // false for padded lanes (tau = +inf) and all-NaN chunks
-        if (__any_sync(0xffffffffu, hit)) {
+        for (int j = 0; j < 32; ++j) m |= (v[j] >= tau ? 1u : 0u) << j;
+        if (__any_sync(0xffffffffu, m != 0)) {
           // make room first: a chunk can append up to 32 keys
           uint32_t full = __ballot_sync(0xffffffffu, cnt + 32 > TC_LIST_CAP);
           while (full) {
@@ -348,18 +352,18 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
               }
             }
           }
-          if (hit) {
+          // per-hit loop; the scores go through a local copy so they can be indexed by bit number
+          float lv[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float s = v[j];
-              if (s >= tau) {
-                const uint32_t row = r0 + j;
-                if (row < p.n_rows) {
-                  const uint64_t key = make_key(ord_from_float(s), row);
-                  if (key >= tau_key && (!p.check_rows || row_passes(p.flt, p.meta, p.agent, row)))
-                    myL[cnt++] = key;
-                }
-              }
+          for (int j = 0; j < 32; ++j) lv[j] = v[j];
+          while (m) {
+            const uint32_t j = __ffs(m) - 1;
+            m &= m - 1;
+            const float s = lv[j];
+            const uint32_t row = r0 + j;
+            if (s >= tau && row < p.n_rows) {
+              const uint64_t key = make_key(ord_from_float(s), row);
+              if (key >= tau_key && (!p.check_rows || row_passes(p.flt, p.meta, p.agent, row))) myL[cnt++] = key;
             }
           }
         }
@@ -510,7 +514,7 @@ void tensor_scan_shape(uint32_t nq, int sm_count, uint32_t* n_qt, uint32_t* n_es
   *n_es = es;
 }
 
-size_t tensor_scratch_bytes(int sm_count) { return (size_t)sm_count * TC_BM * TC_LIST_CAP * 8; }
+size_t tensor_scratch_bytes(int sm_count) { return (size_t)sm_count * 2 * TC_BM * TC_LIST_CAP * 8; }
 
 // sampled row tiles for the cut-off bootstrap: more when few queries share the cost
 uint32_t tensor_sample_tiles(uint32_t n_rows, uint32_t nq) {
