@@ -168,44 +168,81 @@ __device__ __forceinline__ void bitonic_sort_desc(uint64_t* a, uint32_t n, uint3
   }
 }
 // ---- block-wide k-th largest (1-based) of n uint32 values: MSB-first radix select ----
-// get(i) returns value i.  scratch: 258 words of shared memory.  All threads of the
-// block call it (it synchronises with __syncthreads); requires 1 <= k <= n.
+// get(i) returns value i (typically from global memory).  After the first (top byte)
+// pass the values that share the selected byte are compacted into `stage` (shared
+// memory, cap_stage words) so the remaining three passes do not touch global memory
+// again; if they do not fit, those passes re-read get().  scratch: 260 words of shared
+// memory.  All threads of the block call it (it synchronises with __syncthreads);
+// requires 1 <= k <= n.
+__device__ __forceinline__ void radix_pick_digit(uint32_t* scratch, uint32_t k, uint32_t tid) {
+  // scratch[0..255] = histogram; writes scratch[256] = digit, scratch[257] = rank inside it
+  if (tid < 32) {  // lane l owns bins [8l, 8l+8); suffix sums over lanes pick the digit
+    uint32_t s = 0;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) s += scratch[8 * tid + b];
+    uint32_t suf = s;  // becomes the sum over lanes >= tid
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_down_sync(0xffffffffu, suf, o);
+      if (tid + o < 32) suf += t;
+    }
+    const uint32_t above = suf - s;  // sum over lanes > tid
+    if (suf >= k && above < k) {
+      uint32_t acc = above;
+      int d = 7;
+      for (; d > 0; --d) {
+        if (acc + scratch[8 * tid + d] >= k) break;
+        acc += scratch[8 * tid + d];
+      }
+      scratch[256] = 8 * tid + (uint32_t)d;
+      scratch[257] = k - acc;
+    }
+  }
+}
+
 template <typename GetFn>
 __device__ __forceinline__ uint32_t block_kth_largest(GetFn get, uint32_t n, uint32_t k, uint32_t* scratch,
-                                                      uint32_t tid, uint32_t nthreads) {
-  uint32_t prefix = 0, mask = 0;
+                                                      uint32_t* stage, uint32_t cap_stage, uint32_t tid,
+                                                      uint32_t nthreads) {
+  // pass over the top byte
+  for (uint32_t i = tid; i < 256; i += nthreads) scratch[i] = 0;
+  if (tid == 0) scratch[258] = 0;
+  __syncthreads();
+  for (uint32_t i = tid; i < n; i += nthreads) atomicAdd(&scratch[get(i) >> 24], 1u);
+  __syncthreads();
+  radix_pick_digit(scratch, k, tid);
+  __syncthreads();
+  uint32_t prefix = scratch[256] << 24, mask = 0xFF000000u;
+  k = scratch[257];
+  // compact the survivors into shared memory
+  for (uint32_t i = tid; i < n; i += nthreads) {
+    const uint32_t v = get(i);
+    if ((v & mask) == prefix) {
+      const uint32_t pos = atomicAdd(&scratch[258], 1u);
+      if (pos < cap_stage) stage[pos] = v;
+    }
+  }
+  __syncthreads();
+  const uint32_t n_st = scratch[258];
+  const bool staged = n_st <= cap_stage;
 #pragma unroll 1
-  for (int pass = 3; pass >= 0; --pass) {
+  for (int pass = 2; pass >= 0; --pass) {
     const uint32_t shift = 8u * (uint32_t)pass;
     for (uint32_t i = tid; i < 256; i += nthreads) scratch[i] = 0;
     __syncthreads();
-    for (uint32_t i = tid; i < n; i += nthreads) {
-      const uint32_t v = get(i);
-      if ((v & mask) == prefix) atomicAdd(&scratch[(v >> shift) & 255u], 1u);
+    if (staged) {
+      for (uint32_t i = tid; i < n_st; i += nthreads) {
+        const uint32_t v = stage[i];
+        if ((v & mask) == prefix) atomicAdd(&scratch[(v >> shift) & 255u], 1u);
+      }
+    } else {
+      for (uint32_t i = tid; i < n; i += nthreads) {
+        const uint32_t v = get(i);
+        if ((v & mask) == prefix) atomicAdd(&scratch[(v >> shift) & 255u], 1u);
+      }
     }
     __syncthreads();
-    if (tid < 32) {  // lane l owns bins [8l, 8l+8); suffix sums over lanes pick the digit
-      uint32_t s = 0;
-#pragma unroll
-      for (int b = 0; b < 8; ++b) s += scratch[8 * tid + b];
-      uint32_t suf = s;  // becomes sum over lanes >= tid
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_down_sync(0xffffffffu, suf, o);
-        if (tid + o < 32) suf += t;
-      }
-      const uint32_t above = suf - s;  // sum over lanes > tid
-      if (suf >= k && above < k) {
-        uint32_t acc = above;
-        int d = 7;
-        for (; d > 0; --d) {
-          if (acc + scratch[8 * tid + d] >= k) break;
-          acc += scratch[8 * tid + d];
-        }
-        scratch[256] = 8 * tid + (uint32_t)d;
-        scratch[257] = k - acc;
-      }
-    }
+    radix_pick_digit(scratch, k, tid);
     __syncthreads();
     prefix |= scratch[256] << shift;
     mask |= 255u << shift;

@@ -1,11 +1,14 @@
 // cx_select.cu -- K5 + K3: order the nominated candidates, rescore the head with
 // reference arithmetic, verify, emit.
 //
-// One CTA per query.
-//   1. load the query's merged candidate list (approximate keys), block-wide bitonic
-//      sort (descending) of the next power of two; meanwhile one thread computes the
-//      query norm in reference order (index.rs:173)
-//   2. the KS = min(#candidates, KP) best are rescored exactly: rows are staged into
+// One CTA per query (small shared-memory footprint so several queries share an SM).
+//   1. the query's merged candidate list (approximate keys, global memory) is cut down
+//      to the keys that can still reach the top KP: everything at or above the pass's
+//      final cut-off, and -- when that is still more than a few hundred -- at or above
+//      the KP-th best score found by a radix select.  The survivors are sorted
+//      (block-wide bitonic sort).  Meanwhile one thread computes the query norm in
+//      reference order (index.rs:173)
+//   2. the KS = min(#survivors, KP) best are rescored exactly: rows are staged into
 //      shared memory with coalesced loads, then one thread per row runs the
 //      reference's strict left-to-right fp32 fold (index.rs:172) -- so scores and
 //      distances that leave here are bit-identical to the reference's
@@ -13,20 +16,21 @@
 //      descending sort of index.rs:287-292 with row order as the (reference-
 //      unspecified) tie order -- and the first k are emitted
 //   4. verification: U = best approximate cosine among everything NOT rescored (the
-//      next key of the list and the pass's global cut-off).  The result is exact if
-//      sim_k > U + eps, where eps bounds |approximate - reference| for the pass that
-//      nominated the candidates, and score_k > 0 (below that the clamp of
+//      next key of the list, the radix cut and the pass's global cut-off).  The result
+//      is exact if sim_k > U + eps, where eps bounds |approximate - reference| for the
+//      pass that nominated the candidates, and score_k > 0 (below that the clamp of
 //      index.rs:255 creates ties the approximate order cannot see).  Otherwise
-//      ok[q] = 0 and the host reruns the query on the exact path.
+//      ok[q] = 0 and the host reruns the query on a tighter path.
 #include "cx_kernels.h"
 
 namespace cx {
 
 constexpr int SEL_THREADS = 512;
-constexpr int SEL_BATCH = 32;    // rows rescored per staging round
+constexpr int SEL_BATCH = 16;             // rows rescored per staging round
 constexpr int SEL_MAX_KS = 256;
-constexpr uint32_t SEL_DIRECT_MAX = 512;  // up to this many candidates are sorted directly
-constexpr uint32_t SEL_K2 = 2048;         // capacity after the radix-select cut
+constexpr uint32_t SEL_DIRECT_MAX = 1024; // lists up to this long skip the radix select
+constexpr uint32_t SEL_K2 = 2048;         // survivors that can be sorted
+constexpr uint32_t SEL_STAGE = 4096;      // radix-select staging words
 
 struct SelectParams {
   StoreView st;
@@ -37,29 +41,23 @@ struct SelectParams {
   const uint64_t* keys;  // [nq][cap]
   uint32_t* cnt;         // [nq]   (re-zeroed on exit)
   uint64_t* gtau;        // [nq]   (re-zeroed on exit)
-  uint32_t cap, KP, NKmax;
+  uint32_t cap, KP;
   ResultView rv;         // pointers already offset to the first query of this launch
   float eps;
   int scale_by_rqn;      // pass keys are cosine * |q| (streaming pass) rather than cosine
 };
 
-static uint32_t pow2_at_least(uint32_t x) {
-  uint32_t p = 1;
-  while (p < x) p <<= 1;
-  return p;
-}
-
 struct SelectLayout {
-  size_t keys, keys2, q, stage, e, total;
+  size_t keys, rstage, q, stage, e, total;
 };
 
-__host__ __device__ inline SelectLayout select_layout(uint32_t NKmax, uint32_t ld) {
+__host__ __device__ inline SelectLayout select_layout(uint32_t ld) {
   SelectLayout L;
   size_t o = 0;
   L.keys = o;
-  o += (size_t)NKmax * 8;
-  L.keys2 = o;
-  o += (size_t)(NKmax > 512 ? 2048 : 0) * 8;
+  o += (size_t)SEL_K2 * 8;
+  L.rstage = o;
+  o += (size_t)SEL_STAGE * 4;
   L.q = o;
   o += (size_t)ld * 4;
   L.stage = o;
@@ -71,10 +69,11 @@ __host__ __device__ inline SelectLayout select_layout(uint32_t NKmax, uint32_t l
   return L;
 }
 
-__global__ void __launch_bounds__(SEL_THREADS, 1) select_rescore_kernel(const SelectParams p) {
+__global__ void __launch_bounds__(SEL_THREADS) select_rescore_kernel(const SelectParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const SelectLayout L = select_layout(p.NKmax, p.st.ld);
+  const SelectLayout L = select_layout(p.st.ld);
   uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw + L.keys);
+  uint32_t* rstage = reinterpret_cast<uint32_t*>(smem_raw + L.rstage);
   float* q_s = reinterpret_cast<float*>(smem_raw + L.q);
   float* stage = reinterpret_cast<float*>(smem_raw + L.stage);
   uint64_t* ekey = reinterpret_cast<uint64_t*>(smem_raw + L.e);
@@ -82,12 +81,11 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) select_rescore_kernel(const Se
   float* edist = esim + SEL_MAX_KS;
   float* escore = edist + SEL_MAX_KS;
   __shared__ float s_na, s_simk, s_scorek;
-  __shared__ uint32_t scratch[258];
-  uint64_t* keys2 = reinterpret_cast<uint64_t*>(smem_raw + L.keys2);
+  __shared__ uint32_t scratch[260];
+  __shared__ uint32_t s_m;
 
   const uint32_t q = blockIdx.x, tid = threadIdx.x;
   const uint32_t ld = p.st.ld, dim = p.st.dim;
-  __shared__ uint32_t s_m;
   const uint32_t n_app = p.cnt[q];
   const unsigned long long gt = p.gtau[q];  // final cut-off: nothing below it can reach the top KP
   const bool overflow = n_app > p.cap;
@@ -100,7 +98,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) select_rescore_kernel(const Se
   }
   for (uint32_t d = tid; d < ld; d += SEL_THREADS) q_s[d] = d < p.qlen ? p.Q[(size_t)q * p.ldq + d] : 0.0f;
   __syncthreads();
-  if (tid == SEL_THREADS - 1) {  // query norm, reference order
+  if (tid == SEL_THREADS - 1) {  // query norm, reference order (overlaps the list reads below)
     float acc = 0.0f;
     const uint32_t n = p.qlen < ld ? p.qlen : ld;
     uint32_t d = 0;
@@ -117,56 +115,46 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) select_rescore_kernel(const Se
     p.qnorm[q] = na;
     p.rqnorm[q] = __frcp_rn(na);
   }
-  // keep only keys at or above the final cut-off (groups appended against older, lower ones)
-  for (uint32_t i = tid; i < n_src; i += SEL_THREADS) {
-    const uint64_t key = src[i];
-    if (key >= gt) {
-      const uint32_t pos = atomicAdd(&s_m, 1u);
-      if (pos < p.NKmax) keys[pos] = key;
-    }
-  }
-  __syncthreads();
-  uint32_t M = min(s_m, p.NKmax);
-  bool truncated = s_m > p.NKmax;
+
+  // ---- 1. survivors -> keys[0..M) ---------------------------------------------------
   unsigned long long U = gt;
-  uint64_t* skeys = keys;
-  if (M > SEL_DIRECT_MAX) {
-    // many candidates: radix-select the KP-th best score, keep only keys at or above it
-    const uint32_t t = block_kth_largest([&](uint32_t i) { return key_ord(keys[i]); }, M, min(p.KP, M), scratch,
-                                         tid, SEL_THREADS);
-    if (tid == 0) s_m = 0;
-    __syncthreads();
-    for (uint32_t i = tid; i < M; i += SEL_THREADS) {
-      const uint64_t key = keys[i];
-      if (key_ord(key) >= t) {
-        const uint32_t pos = atomicAdd(&s_m, 1u);
-        if (pos < SEL_K2) keys2[pos] = key;
-      }
-    }
-    __syncthreads();
-    truncated = truncated || s_m > SEL_K2;
-    M = min(s_m, (uint32_t)SEL_K2);
-    skeys = keys2;
-    const unsigned long long left = (unsigned long long)t << 32;  // everything left behind scores below t
+  uint32_t cut = 0;  // radix cut (score ord); 0 = none
+  if (n_src > SEL_DIRECT_MAX) {
+    auto get = [&](uint32_t i) {
+      const uint64_t key = src[i];
+      return key >= gt ? key_ord(key) : 0u;
+    };
+    cut = block_kth_largest(get, n_src, min(p.KP, n_src), scratch, rstage, SEL_STAGE, tid, SEL_THREADS);
+    const unsigned long long left = (unsigned long long)cut << 32;  // what is left behind scores below `cut`
     if (left > U) U = left;
   }
+  for (uint32_t i = tid; i < n_src; i += SEL_THREADS) {
+    const uint64_t key = src[i];
+    if (key >= gt && key_ord(key) >= cut) {
+      const uint32_t pos = atomicAdd(&s_m, 1u);
+      if (pos < SEL_K2) keys[pos] = key;
+    }
+  }
+  __syncthreads();
+  const uint32_t M = min(s_m, SEL_K2);
+  const bool truncated = s_m > SEL_K2;
   uint32_t NK = 32;
   while (NK < M) NK <<= 1;
-  for (uint32_t i = M + tid; i < NK; i += SEL_THREADS) skeys[i] = 0ull;
+  for (uint32_t i = M + tid; i < NK; i += SEL_THREADS) keys[i] = 0ull;
   __syncthreads();
-  bitonic_sort_desc(skeys, NK, tid, SEL_THREADS, [] { __syncthreads(); });
+  bitonic_sort_desc(keys, NK, tid, SEL_THREADS, [] { __syncthreads(); });
   __syncthreads();
   const float na = s_na;
   const uint32_t KS = min(min(M, p.KP), (uint32_t)SEL_MAX_KS);
-  if (M > KS && skeys[KS] > U) U = skeys[KS];
+  if (M > KS && keys[KS] > U) U = keys[KS];
 
-  // exact rescore, SEL_BATCH rows per round
+  // ---- 2. exact rescore, SEL_BATCH rows per round -------------------------------------
   const uint32_t warp = tid >> 5, lane = tid & 31, nwarps = SEL_THREADS / 32;
   const uint32_t sstride = ld + 1;
   for (uint32_t base = 0; base < KS; base += SEL_BATCH) {
     const uint32_t nb = min((uint32_t)SEL_BATCH, KS - base);
     for (uint32_t j = warp; j < nb; j += nwarps) {
-      const uint32_t row = key_row(skeys[base + j]);
+      const uint32_t row = key_row(keys[base + j]);
       const float* g = p.st.E + (size_t)row * ld;
       uint32_t d = lane;
       for (; d + 7 * 32 < ld; d += 8 * 32) {  // eight loads in flight per lane
@@ -180,7 +168,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) select_rescore_kernel(const Se
     }
     __syncthreads();
     if (tid < nb) {
-      const uint32_t row = key_row(skeys[base + tid]);
+      const uint32_t row = key_row(keys[base + tid]);
       const float* r = stage + tid * sstride;
       const uint32_t n = p.qlen < dim ? p.qlen : dim;
       float dot = 0.0f;
@@ -208,7 +196,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) select_rescore_kernel(const Se
     __syncthreads();
   }
 
-  // order by exact key (all distinct: the row is part of the key), emit the first k
+  // ---- 3. order by exact key (all distinct: the row is part of the key), emit the first k
   const uint32_t k = p.rv.k;
   const uint32_t n_out = min(k, KS);
   if (tid < KS) {
@@ -231,6 +219,7 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) select_rescore_kernel(const Se
     }
   }
   __syncthreads();
+  // ---- 4. verify ---------------------------------------------------------------------
   if (tid == 0) {
     p.rv.n[q] = n_out;
     bool ok = KS >= k && !overflow && !truncated;
@@ -250,9 +239,8 @@ __global__ void __launch_bounds__(SEL_THREADS, 1) select_rescore_kernel(const Se
 }
 
 size_t select_smem(uint32_t cap, uint32_t ld) {
-  uint32_t nk = pow2_at_least(cap < 32 ? 32 : cap);
-  if (nk > 16384) nk = 16384;
-  return select_layout(nk, ld).total;
+  (void)cap;
+  return select_layout(ld).total + 2048;
 }
 
 cudaError_t launch_select_rescore(const StoreView& st, const QueryView& qv, uint32_t q0, uint32_t nq,
@@ -271,8 +259,6 @@ cudaError_t launch_select_rescore(const StoreView& st, const QueryView& qv, uint
   p.gtau = cv.gtau + q0;
   p.cap = cv.cap;
   p.KP = cv.KP;
-  p.NKmax = pow2_at_least(cv.cap < 32 ? 32 : cv.cap);
-  if (p.NKmax > 16384) p.NKmax = 16384;
   p.rv = rv;
   p.rv.rows += (size_t)q0 * rv.k;
   p.rv.score += (size_t)q0 * rv.k;
@@ -282,8 +268,8 @@ cudaError_t launch_select_rescore(const StoreView& st, const QueryView& qv, uint
   p.rv.ok += q0;
   p.eps = eps_cos;
   p.scale_by_rqn = scale_by_rqn;
-  const size_t smem = select_layout(p.NKmax, st.ld).total;
-  if (smem > 227 * 1024 || cv.KP > SEL_MAX_KS) return cudaErrorInvalidConfiguration;
+  const size_t smem = select_layout(st.ld).total;
+  if (smem > 200 * 1024 || cv.KP > SEL_MAX_KS) return cudaErrorInvalidConfiguration;
   cudaError_t e =
       cudaFuncSetAttribute(select_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;

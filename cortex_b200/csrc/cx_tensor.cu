@@ -133,6 +133,20 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 // N >> 3 at bit 17, M >> 4 at bit 24.
 constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((TC_BN >> 3) << 17) | ((TC_BM >> 4) << 24);
 
+// v[j] for a run-time j without spilling v to local memory: 31 selects
+__device__ __forceinline__ float pick32(const float (&v)[32], uint32_t j) {
+  float a[16], b[8], c[4], d[2];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) a[i] = (j & 1u) ? v[2 * i + 1] : v[2 * i];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) b[i] = (j & 2u) ? a[2 * i + 1] : a[2 * i];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) c[i] = (j & 4u) ? b[2 * i + 1] : b[2 * i];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) d[i] = (j & 8u) ? c[2 * i + 1] : c[2 * i];
+  return (j & 16u) ? d[1] : d[0];
+}
+
 // ---- warp-cooperative reduction of one private list --------------------------------
 // Sort (descending) the n <= 512 keys at L across the warp's registers, write the best KP
 // back in order, return the KP-th key (0 if n < KP).  All lanes call it.
@@ -352,14 +366,11 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
               }
             }
           }
-          // per-hit loop; the scores go through a local copy so they can be indexed by bit number
-          float lv[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) lv[j] = v[j];
+          // per-hit loop; v[j] for a run-time j comes from a 5-level select tree (registers only)
           while (m) {
             const uint32_t j = __ffs(m) - 1;
             m &= m - 1;
-            const float s = lv[j];
+            const float s = pick32(v, j);
             const uint32_t row = r0 + j;
             if (s >= tau && row < p.n_rows) {
               const uint64_t key = make_key(ord_from_float(s), row);
@@ -400,26 +411,18 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 // ---- cut-off from the sampled scores: tau0[q] = KP-th largest of dump[q][0..S) --------
 __global__ void __launch_bounds__(256) tau_select_kernel(const float* __restrict__ dump, uint32_t S, uint32_t KP,
                                                          uint64_t* __restrict__ gtau) {
-  __shared__ uint32_t scratch[258];
-  __shared__ uint32_t s_valid;
+  __shared__ uint32_t scratch[260];
+  __shared__ uint32_t stage[4096];
   const uint32_t q = blockIdx.x, tid = threadIdx.x;
   const float* d = dump + (size_t)q * S;
-  if (tid == 0) s_valid = 0;
-  __syncthreads();
-  uint32_t nv = 0;
-  for (uint32_t i = tid; i < S; i += 256) nv += d[i] > -INFINITY;  // false for NaN as well
-  if (nv) atomicAdd(&s_valid, nv);
-  __syncthreads();
-  if (s_valid < KP) {  // not enough eligible sampled rows: no cut-off
-    if (tid == 0) gtau[q] = 0ull;
-    return;
-  }
+  // ineligible entries (-inf, NaN) map to 0, below every real score: if fewer than KP sampled
+  // rows are eligible the KP-th largest is 0 and the query simply gets no cut-off
   auto get = [&](uint32_t i) {
     const float x = d[i];
     return x > -INFINITY ? ord_from_float(x) : 0u;
   };
-  const uint32_t t = block_kth_largest(get, S, KP, scratch, tid, 256);
-  if (tid == 0) gtau[q] = (uint64_t)t << 32;  // the lowest key with that score
+  const uint32_t t = S >= KP ? block_kth_largest(get, S, KP, scratch, stage, 4096u, tid, 256) : 0u;
+  if (tid == 0) gtau[q] = (uint64_t)t << 32;  // the lowest key with that score (0 = none)
 }
 
 // ---- query preparation: normalise + convert to bf16, zero padded to [n_qt*128][ld16] --
@@ -519,7 +522,7 @@ size_t tensor_scratch_bytes(int sm_count) { return (size_t)sm_count * 2 * TC_BM 
 // sampled row tiles for the cut-off bootstrap: more when few queries share the cost
 uint32_t tensor_sample_tiles(uint32_t n_rows, uint32_t nq) {
   const uint32_t n_tiles = (n_rows + TC_BN - 1) / TC_BN;
-  uint32_t want = nq <= 128 ? 256 : nq <= 512 ? 64 : 32;  // 65536 / 16384 / 8192 rows
+  uint32_t want = nq <= 512 ? 64 : 32;  // 16384 / 8192 rows
   return want < n_tiles ? want : n_tiles;
 }
 
