@@ -152,14 +152,18 @@ __global__ void __launch_bounds__(SC_THREADS, 1) stream_scan_kernel(const Stream
   if (warp == SC_CW) {
     // ---------------- producer ----------------
     if (lane == 0) {
-      uint32_t it = 0;
+      // Each consumer group owns its own sub-ring of S/2 stages, so a stage's barriers are
+      // only ever waited on by one group and phases cannot be skipped (parity would alias).
+      const uint32_t SG = S / SC_GROUPS;
       for (uint32_t i = 0; i < my_tiles; ++i) {
         const uint32_t t = blockIdx.x + i * gridDim.x;
         const uint32_t r0 = t * SC_TILE_ROWS;
         const uint32_t rows_here = min((uint32_t)SC_TILE_ROWS, p.st.n_rows - r0);
-        for (uint32_t sl = 0; sl < p.n_slices; ++sl, ++it) {
-          const uint32_t stage = it % S;
-          if (it >= S) mbar_wait(empty0 + 8 * stage, ((it / S) - 1) & 1);
+        const uint32_t g = i % SC_GROUPS, jbase = (i / SC_GROUPS) * p.n_slices;
+        for (uint32_t sl = 0; sl < p.n_slices; ++sl) {
+          const uint32_t j = jbase + sl;
+          const uint32_t stage = g * SG + (j % SG);
+          if (j >= SG) mbar_wait(empty0 + 8 * stage, ((j / SG) - 1) & 1);
           const uint32_t dst = smem_u32(tiles + (size_t)stage * tile_floats);
           const uint32_t k0 = sl * p.kslice;
           const uint32_t klen = min(p.kslice, ld - k0);
@@ -236,9 +240,10 @@ __global__ void __launch_bounds__(SC_THREADS, 1) stream_scan_kernel(const Stream
 
     float my_rn = 0.0f;
     for (uint32_t sl = 0; sl < p.n_slices; ++sl) {
-      const uint32_t it = i * p.n_slices + sl;
-      const uint32_t stage = it % S;
-      mbar_wait(full0 + 8 * stage, (it / S) & 1);
+      const uint32_t SG = S / SC_GROUPS;  // this group's sub-ring (see the producer)
+      const uint32_t j = (i / SC_GROUPS) * p.n_slices + sl;
+      const uint32_t stage = grp * SG + (j % SG);
+      mbar_wait(full0 + 8 * stage, (j / SG) & 1);
       const float4* tile4 = reinterpret_cast<const float4*>(tiles + (size_t)stage * tile_floats) +
                             (size_t)(gwarp * SC_R) * kslice4;
       const uint32_t k0_4 = (sl * p.kslice) >> 2;
@@ -377,7 +382,7 @@ static uint32_t stream_list_cap(uint32_t KP) { return pow2_at_least(2 * KP + SC_
 static uint32_t stream_pick_stages(uint32_t ld, uint32_t nq, uint32_t KP, size_t* total) {
   uint32_t kslice = stream_pick_kslice(ld);
   uint32_t C = stream_list_cap(KP);
-  for (uint32_t s = SC_MAX_STAGES; s >= 2; --s) {
+  for (uint32_t s = SC_MAX_STAGES; s >= 2; s -= SC_GROUPS) {  // even: each consumer group owns s/2 stages
     StreamLayout L = stream_layout(ld, nq, C, s, kslice);
     if (L.total <= SC_SMEM_LIMIT) {
       *total = L.total;
