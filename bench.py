@@ -44,7 +44,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=1_000_000, help="corpus rows per GPU")
     ap.add_argument("--dim", type=int, default=384)
-    ap.add_argument("--batch", type=int, default=8)
+    ap.add_argument("--batch", type=int, default=1024)
+    ap.add_argument("--no-small-probe", action="store_true", help="skip the extra B=1 measurement")
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--cpu-queries", type=int, default=0, help="queries per CPU-baseline step (0 = one per thread)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -315,6 +316,36 @@ def main():
     h2d = a.batch * a.dim * 4
     d2h = a.batch * a.k * (16 + 4 + 4) + a.batch * 4
 
+    # ---- small-batch probe (B=1 interactive search, the HBM-bound streaming pass) ----
+    small = None
+    if a.batch != 1 and not a.no_small_probe:
+        q1 = d_q[:1].contiguous()
+        o1 = None
+        for _ in range(5):
+            o1 = ix.search_batch_device(q1, a.k, stream=stream.cuda_stream, out=o1)
+        torch.cuda.synchronize()
+        s0 = ix.stats()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n1 = 100
+        ev0.record()
+        for _ in range(n1):
+            o1 = ix.search_batch_device(q1, a.k, stream=stream.cuda_stream, out=o1)
+        ev1.record()
+        torch.cuda.synchronize()
+        s1 = ix.stats()
+        pk1 = peaks()
+        l1 = s1["pass_kernel_launches"] - s0["pass_kernel_launches"]
+        ns1 = s1["pass_kernel_ns"] - s0["pass_kernel_ns"]
+        if l1 and ns1:
+            bytes1 = a.rows * ((a.dim + 3) // 4 * 4) * 4
+            gbs = bytes1 / (ns1 * 1e-9 / l1) / 1e9
+            small = {"batch": 1, "queries_per_s": n1 / (ev0.elapsed_time(ev1) * 1e-3),
+                     "ms_per_query": ev0.elapsed_time(ev1) / n1,
+                     "roofline": {"bound": "hbm", "kernel": "stream_scan_kernel", "achieved": gbs,
+                                  "peak": pk1["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk1["hbm_gbs"],
+                                  "frac_of_nominal_8TBs": gbs / 8000.0, "us_per_launch": ns1 * 1e-3 / l1,
+                                  "algorithmic_bytes_per_launch": bytes1, "peak_source": pk1["source"]}}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -367,7 +398,7 @@ def main():
                    "seed": SEED, "parallelism": f"row-shard x{world}",
                    "cache": "inputs larger than L2: the 1.5 GB corpus shard is streamed from HBM every step",
                    "value_counts": "per-shard query scans (batch x n_gpus per step)"},
-        "roofline": roof, "cpu_baseline": cpu,
+        "roofline": roof, "small_batch": small, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": st1["kernel_launches"] - st0["kernel_launches"],
         "clocks": clk,

@@ -265,19 +265,24 @@ cx_status run_search(cx_index* h, Workspace* ws, const FilterHost& fh, const Sea
       launch_query_bf16(sb.dQ, pl.ldq, h->dim, (uint32_t)B, (uint32_t)align_up(B, 128), sb.q16, h->ld16, s);
       h->launches += 1;
     }
-    if (h->profile) CU(cudaEventRecord(ws->ev0, s));
     if (pl.tensor) {
       cv.KP = pl.KPt;
       const bool check_rows = flt.has_kinds || flt.has_agent || flt.n_excl || h->n_live != h->n_rows;
+      // cut-off bootstrap for every launch group first (the sample buffer is reused in stream order)
       for (uint64_t q0 = 0; q0 < B; q0 += pl.q_per_launch) {
         const uint32_t nq = (uint32_t)(B - q0 < pl.q_per_launch ? B - q0 : pl.q_per_launch);
         CU(launch_tensor_bootstrap(st, sb.q16, (uint32_t)q0, nq, flt, check_rows, cv, sb.dump, pl.n_slots,
                                    h->sm_count, s));
-        CU(launch_tensor_scan(st, sb.q16, (uint32_t)q0, nq, flt, check_rows, cv, sb.lists, h->sm_count, s));
         h->launches += 2;
+      }
+      if (h->profile) CU(cudaEventRecord(ws->ev0, s));
+      for (uint64_t q0 = 0; q0 < B; q0 += pl.q_per_launch) {
+        const uint32_t nq = (uint32_t)(B - q0 < pl.q_per_launch ? B - q0 : pl.q_per_launch);
+        CU(launch_tensor_scan(st, sb.q16, (uint32_t)q0, nq, flt, check_rows, cv, sb.lists, h->sm_count, s));
         ++n_pass;
       }
     } else {
+      if (h->profile) CU(cudaEventRecord(ws->ev0, s));
       for (uint64_t q0 = 0; q0 < B; q0 += 8) {
         const uint32_t nq = (uint32_t)(B - q0 < 8 ? B - q0 : 8);
         CU(launch_stream_scan(st, qv, (uint32_t)q0, nq, flt, cv, h->sm_count, s));
