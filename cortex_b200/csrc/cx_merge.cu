@@ -1,0 +1,98 @@
+// cx_merge.cu -- the exchange step of the row-sharded search:
+//   pack   : a rank's local top-k (shard-local rows, exact scores) -> fixed-size payload
+//   merge  : the all-gathered payloads of W ranks -> global top-k per query
+// Order = the single-index order: score descending, NaN last, then GLOBAL row ascending
+// (shards are contiguous blocks in insertion order), i.e. the stable descending sort of
+// vector/index.rs:287-292 with row order as tie order.
+#include "cx_index.h"
+
+namespace cx {
+
+// payload per (query, slot): word0 = score-order key (high 32) | distance bits (low 32),
+//                            word1 = global row; word0 == 0 marks an empty slot
+__global__ void pack_topk_kernel(const uint32_t* __restrict__ rows, const float* __restrict__ score,
+                                 const float* __restrict__ dist, const uint32_t* __restrict__ n, uint32_t B,
+                                 uint32_t k, uint64_t row_offset, uint64_t* __restrict__ payload) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * k) return;
+  const uint32_t b = i / k, j = i % k;
+  uint64_t w0 = 0, w1 = 0;
+  if (j < n[b]) {
+    w0 = ((uint64_t)ord_from_score(score[i]) << 32) | (uint64_t)__float_as_uint(dist[i]);
+    w1 = row_offset + rows[i];
+  }
+  payload[2 * (size_t)i] = w0;
+  payload[2 * (size_t)i + 1] = w1;
+}
+
+// one CTA per query; W*k candidates ranked by counting (all (ord,row) pairs are distinct)
+__global__ void merge_topk_kernel(const uint64_t* __restrict__ gathered, uint32_t W, uint32_t B, uint32_t k,
+                                  int64_t* __restrict__ out_rows, float* __restrict__ out_score,
+                                  float* __restrict__ out_dist, uint32_t* __restrict__ out_n) {
+  extern __shared__ uint64_t sm[];  // [W*k][2]
+  const uint32_t b = blockIdx.x, tid = threadIdx.x, n = W * k;
+  __shared__ uint32_t s_valid;
+  if (tid == 0) s_valid = 0;
+  for (uint32_t i = tid; i < n; i += blockDim.x) {
+    const uint32_t w = i / k, j = i % k;
+    const uint64_t* src = gathered + 2 * (((size_t)w * B + b) * k + j);
+    sm[2 * i] = src[0];
+    sm[2 * i + 1] = src[1];
+  }
+  __syncthreads();
+  uint32_t valid = 0;
+  for (uint32_t i = tid; i < n; i += blockDim.x) {
+    const uint64_t w0 = sm[2 * i], w1 = sm[2 * i + 1];
+    if (w0 == 0) continue;
+    ++valid;
+    const uint32_t ord = (uint32_t)(w0 >> 32);
+    uint32_t rank = 0;
+    for (uint32_t j = 0; j < n; ++j) {
+      const uint64_t x0 = sm[2 * j];
+      if (x0 == 0) continue;
+      const uint32_t xo = (uint32_t)(x0 >> 32);
+      rank += (xo > ord) || (xo == ord && sm[2 * j + 1] < w1);
+    }
+    if (rank < k) {
+      const size_t o = (size_t)b * k + rank;
+      out_rows[o] = (int64_t)w1;
+      out_dist[o] = __uint_as_float((uint32_t)w0);
+      // the score is re-derived from the distance with the reference's own two operations
+      out_score[o] = ref_score_from_distance(__uint_as_float((uint32_t)w0));
+    }
+  }
+  if (valid) atomicAdd(&s_valid, valid);
+  __syncthreads();
+  if (tid == 0) out_n[b] = s_valid < k ? s_valid : k;
+}
+
+}  // namespace cx
+
+using namespace cx;
+
+extern "C" cx_status cx_pack_topk_device(const uint32_t* d_rows, const float* d_score, const float* d_distance,
+                                         const uint32_t* d_n, uint64_t B, uint64_t k, uint64_t row_offset,
+                                         uint64_t* d_payload, void* stream) {
+  if (!d_rows || !d_score || !d_distance || !d_n || !d_payload) return fail(CX_ERR_VALIDATION, "null device buffer");
+  if (!B || !k) return CX_OK;
+  const uint64_t total = B * k;
+  pack_topk_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      d_rows, d_score, d_distance, d_n, (uint32_t)B, (uint32_t)k, row_offset, d_payload);
+  CU(cudaGetLastError());
+  return CX_OK;
+}
+
+extern "C" cx_status cx_merge_topk_device(const uint64_t* d_gathered, uint32_t world, uint64_t B, uint64_t k,
+                                          int64_t* d_out_rows, float* d_out_score, float* d_out_distance,
+                                          uint32_t* d_out_n, void* stream) {
+  if (!d_gathered || !d_out_rows || !d_out_score || !d_out_distance || !d_out_n)
+    return fail(CX_ERR_VALIDATION, "null device buffer");
+  if (!B || !k || !world) return CX_OK;
+  const size_t smem = (size_t)world * k * 16;
+  if (smem > 200 * 1024) return fail(CX_ERR_VALIDATION, "world * k too large for the merge kernel");
+  CU(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  merge_topk_kernel<<<(unsigned)B, 128, smem, (cudaStream_t)stream>>>(d_gathered, world, (uint32_t)B, (uint32_t)k,
+                                                                      d_out_rows, d_out_score, d_out_distance, d_out_n);
+  CU(cudaGetLastError());
+  return CX_OK;
+}

@@ -67,11 +67,45 @@ class ShardedSearch:
         self.row_offset = int(row_offset)
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self._bufs = {}
+
+    def _search_cuda(self, rows, score, d, n, k):
+        """GPU exchange: pack kernel -> one NCCL all_gather -> merge kernel (cx_merge.cu)."""
+        import ctypes as C
+
+        from . import _capi
+        L = _capi.load()
+        B = rows.shape[0]
+        dev = rows.device
+        stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        key = (B, k, str(dev))
+        buf = self._bufs.get(key)
+        if buf is None:
+            buf = (torch.empty((B, k, 2), dtype=torch.int64, device=dev),
+                   torch.empty((self.world, B, k, 2), dtype=torch.int64, device=dev),
+                   torch.empty((B, k), dtype=torch.int64, device=dev),
+                   torch.empty((B, k), dtype=torch.float32, device=dev),
+                   torch.empty((B, k), dtype=torch.float32, device=dev),
+                   torch.empty((B,), dtype=torch.int32, device=dev))
+            self._bufs[key] = buf
+        payload, gathered, grow, gscore, gdist, gn = buf
+        st = L.cx_pack_topk_device(rows.data_ptr(), score.data_ptr(), d.data_ptr(), n.data_ptr(), B, k,
+                                   self.row_offset, payload.data_ptr(), stream)
+        if st != 0:
+            raise RuntimeError(L.cx_last_error().decode())
+        dist.all_gather_into_tensor(gathered.view(self.world * B, k, 2), payload, group=self.group)
+        st = L.cx_merge_topk_device(gathered.data_ptr(), self.world, B, k, grow.data_ptr(), gscore.data_ptr(),
+                                    gdist.data_ptr(), gn.data_ptr(), stream)
+        if st != 0:
+            raise RuntimeError(L.cx_last_error().decode())
+        return grow, gscore, gdist, gn
 
     def search(self, queries: torch.Tensor, k: int):
         rows, score, d, n = self.local_search(queries, k)
         if self.world == 1:  # nothing to exchange: the local list is already the answer
             return rows.to(torch.int64) + self.row_offset, score, d, n
+        if rows.is_cuda:
+            return self._search_cuda(rows, score, d, n, k)
         key = pack_keys(rows, score, n, self.row_offset)
         payload = torch.stack([key, d.contiguous().view(torch.int32).to(torch.int64)], dim=0)  # [2,B,k]
         flat = torch.empty((self.world * 2,) + tuple(payload.shape[1:]), dtype=payload.dtype,

@@ -117,6 +117,19 @@ cx_status cx_search_batch_device(cx_index* h, const float* d_queries, uint64_t B
                                  const cx_filter* filter, uint32_t* d_out_rows, float* d_out_score,
                                  float* d_out_distance, uint8_t* d_out_ids, uint32_t* d_out_n, void* stream);
 
+/* Row-sharded search (one process per GPU): the exchange step around the
+ * caller's all-gather.  pack: a rank's device-resident local top-k -> payload
+ * [B][k][2] u64 (score-order key | distance bits, global row = row_offset + local row).
+ * merge: the gathered payloads [world][B][k][2] -> global top-k per query in the
+ * single-index order (score desc, NaN last, global row asc).  No reference counterpart:
+ * the reference is single-process (ARCHITECTURE.md:38). */
+cx_status cx_pack_topk_device(const uint32_t* d_rows, const float* d_score, const float* d_distance,
+                              const uint32_t* d_n, uint64_t B, uint64_t k, uint64_t row_offset,
+                              uint64_t* d_payload, void* stream);
+cx_status cx_merge_topk_device(const uint64_t* d_gathered, uint32_t world, uint64_t B, uint64_t k,
+                               int64_t* d_out_rows, float* d_out_score, float* d_out_distance,
+                               uint32_t* d_out_n, void* stream);
+
 /* VectorIndex::save / load, index.rs:437-472: bincode 1.3 layout of
  * (HashMap<Uuid,Vec<f32>>, HashMap<Uuid,NodeMetadata>, usize). */
 cx_status cx_save(const cx_index* h, const char* path);

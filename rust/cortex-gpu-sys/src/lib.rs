@@ -1,0 +1,66 @@
+//! Raw bindings of include/cortex_gpu.h, one declaration per exported symbol.
+#![allow(non_camel_case_types)]
+use libc::{c_char, c_int, c_void};
+
+#[repr(C)]
+pub struct cx_index { _private: [u8; 0] }
+
+#[repr(C)]
+pub struct cx_filter {
+    pub has_kinds: i32,
+    pub kinds: *const *const c_char,
+    pub n_kinds: u32,
+    pub has_exclude: i32,
+    pub exclude_ids: *const u8,
+    pub n_exclude: u32,
+    pub has_source_agent: i32,
+    pub source_agent: *const c_char,
+}
+
+#[repr(C)]
+#[derive(Default, Debug, Clone, Copy)]
+pub struct cx_stats {
+    pub kernel_launches: u64,
+    pub queries_stream: u64,
+    pub queries_tensor: u64,
+    pub queries_exact: u64,
+    pub fallbacks: u64,
+    pub h2d_bytes: u64,
+    pub d2h_bytes: u64,
+    pub pass_kernel_ns: u64,
+    pub pass_kernel_launches: u64,
+}
+
+pub const CX_OK: c_int = 0;
+
+extern "C" {
+    pub fn cx_index_create(dimension: u32, device: c_int, out: *mut *mut cx_index) -> c_int;
+    pub fn cx_index_destroy(h: *mut cx_index);
+    pub fn cx_insert(h: *mut cx_index, id: *const u8, embedding: *const f32, len: u32) -> c_int;
+    pub fn cx_insert_batch(h: *mut cx_index, ids: *const u8, rows: *const f32, n: u64, len: u32) -> c_int;
+    pub fn cx_remove(h: *mut cx_index, id: *const u8) -> c_int;
+    pub fn cx_set_metadata(h: *mut cx_index, id: *const u8, kind: *const c_char, agent: *const c_char) -> c_int;
+    pub fn cx_len(h: *const cx_index) -> u64;
+    pub fn cx_dimension(h: *const cx_index) -> u32;
+    pub fn cx_rebuild(h: *mut cx_index) -> c_int;
+    pub fn cx_reserve(h: *mut cx_index, n_rows: u64) -> c_int;
+    pub fn cx_search(h: *mut cx_index, query: *const f32, qlen: u32, k: u64, filter: *const cx_filter,
+                     out_ids: *mut u8, out_score: *mut f32, out_distance: *mut f32, out_n: *mut u64) -> c_int;
+    pub fn cx_search_threshold(h: *mut cx_index, query: *const f32, qlen: u32, threshold: f32,
+                               filter: *const cx_filter, cap: u64, out_ids: *mut u8, out_score: *mut f32,
+                               out_distance: *mut f32, out_n: *mut u64, out_total: *mut u64) -> c_int;
+    pub fn cx_search_batch(h: *mut cx_index, queries: *const f32, b: u64, qlen: u32, k: u64,
+                           filter: *const cx_filter, out_ids: *mut u8, out_score: *mut f32,
+                           out_distance: *mut f32, out_n: *mut u64) -> c_int;
+    pub fn cx_search_batch_device(h: *mut cx_index, d_queries: *const f32, b: u64, k: u64,
+                                  filter: *const cx_filter, d_out_rows: *mut u32, d_out_score: *mut f32,
+                                  d_out_distance: *mut f32, d_out_ids: *mut u8, d_out_n: *mut u32,
+                                  stream: *mut c_void) -> c_int;
+    pub fn cx_save(h: *const cx_index, path: *const c_char) -> c_int;
+    pub fn cx_load(path: *const c_char, device: c_int, out: *mut *mut cx_index) -> c_int;
+    pub fn cx_row_id(h: *const cx_index, row: u32, out_id: *mut u8) -> c_int;
+    pub fn cx_get_stats(h: *const cx_index, out: *mut cx_stats) -> c_int;
+    pub fn cx_set_option(h: *mut cx_index, key: *const c_char, value: i64) -> c_int;
+    pub fn cx_last_error() -> *const c_char;
+    pub fn cx_version() -> *const c_char;
+}

@@ -1,0 +1,168 @@
+//! GpuVectorIndex: cortex_core::vector::VectorIndex over the B200 scan engine.
+//!
+//! Every trait method is one FFI call; any non-zero status becomes
+//! CortexError::Validation(cx_last_error()) -- the only error variant the reference
+//! index raises (crates/cortex-core/src/vector/index.rs:299-305, 438-459).
+use cortex_core::error::{CortexError, Result};
+use cortex_core::types::{Embedding, NodeId, NodeKind};
+use cortex_core::vector::{SimilarityResult, VectorFilter, VectorIndex};
+use cortex_gpu_sys as sys;
+use std::collections::HashMap;
+use std::ffi::{CStr, CString};
+use std::path::Path;
+use std::ptr;
+
+pub struct GpuVectorIndex {
+    h: *mut sys::cx_index,
+}
+// search* are re-entrant in the library (per-call workspace + stream); mutators take &mut self.
+unsafe impl Send for GpuVectorIndex {}
+unsafe impl Sync for GpuVectorIndex {}
+
+fn check(st: i32) -> Result<()> {
+    if st == sys::CX_OK {
+        return Ok(());
+    }
+    let msg = unsafe { CStr::from_ptr(sys::cx_last_error()) }.to_string_lossy().into_owned();
+    Err(CortexError::Validation(msg))
+}
+
+struct CFilter {
+    raw: sys::cx_filter,
+    _kinds: Vec<CString>,
+    _kind_ptrs: Vec<*const libc::c_char>,
+    _excl: Vec<u8>,
+    _agent: Option<CString>,
+}
+
+fn c_filter(f: &VectorFilter) -> CFilter {
+    let kinds: Vec<CString> = f.kinds.iter().flatten().map(|k| CString::new(k.as_str()).unwrap()).collect();
+    let kind_ptrs: Vec<_> = kinds.iter().map(|c| c.as_ptr()).collect();
+    let excl: Vec<u8> = f.exclude.iter().flatten().flat_map(|id| id.as_bytes().to_vec()).collect();
+    let agent = f.source_agent.as_ref().map(|a| CString::new(a.as_str()).unwrap());
+    let raw = sys::cx_filter {
+        has_kinds: f.kinds.is_some() as i32,
+        kinds: kind_ptrs.as_ptr(),
+        n_kinds: kind_ptrs.len() as u32,
+        has_exclude: f.exclude.is_some() as i32,
+        exclude_ids: excl.as_ptr(),
+        n_exclude: (excl.len() / 16) as u32,
+        has_source_agent: f.source_agent.is_some() as i32,
+        source_agent: agent.as_ref().map_or(ptr::null(), |a| a.as_ptr()),
+    };
+    CFilter { raw, _kinds: kinds, _kind_ptrs: kind_ptrs, _excl: excl, _agent: agent }
+}
+
+impl GpuVectorIndex {
+    /// HnswIndex::new(dimension), index.rs:204-211
+    pub fn new(dimension: usize) -> Result<Self> {
+        Self::on_device(dimension, 0)
+    }
+    pub fn on_device(dimension: usize, device: i32) -> Result<Self> {
+        let mut h = ptr::null_mut();
+        check(unsafe { sys::cx_index_create(dimension as u32, device, &mut h) })?;
+        Ok(Self { h })
+    }
+    /// HnswIndex::set_metadata, index.rs:219-222
+    pub fn set_metadata(&mut self, id: NodeId, kind: NodeKind, source_agent: String) {
+        let k = CString::new(kind.as_str()).unwrap();
+        let a = CString::new(source_agent).unwrap();
+        unsafe { sys::cx_set_metadata(self.h, id.as_bytes().as_ptr(), k.as_ptr(), a.as_ptr()) };
+    }
+    /// Bulk form of the startup loop serve.rs:111-117
+    pub fn insert_batch(&mut self, ids: &[NodeId], rows: &[f32], dim: usize) -> Result<()> {
+        let flat: Vec<u8> = ids.iter().flat_map(|i| i.as_bytes().to_vec()).collect();
+        check(unsafe { sys::cx_insert_batch(self.h, flat.as_ptr(), rows.as_ptr(), ids.len() as u64, dim as u32) })
+    }
+    fn collect(ids: &[u8], score: &[f32], dist: &[f32], n: usize) -> Vec<SimilarityResult> {
+        (0..n)
+            .map(|i| SimilarityResult {
+                node_id: NodeId::from_slice(&ids[16 * i..16 * i + 16]).unwrap(),
+                score: score[i],
+                distance: dist[i],
+            })
+            .collect()
+    }
+}
+
+impl Drop for GpuVectorIndex {
+    fn drop(&mut self) {
+        unsafe { sys::cx_index_destroy(self.h) }
+    }
+}
+
+impl VectorIndex for GpuVectorIndex {
+    fn insert(&mut self, id: NodeId, embedding: &Embedding) -> Result<()> {
+        check(unsafe { sys::cx_insert(self.h, id.as_bytes().as_ptr(), embedding.as_ptr(), embedding.len() as u32) })
+    }
+    fn remove(&mut self, id: NodeId) -> Result<()> {
+        check(unsafe { sys::cx_remove(self.h, id.as_bytes().as_ptr()) })
+    }
+    fn search(&self, query: &Embedding, k: usize, filter: Option<&VectorFilter>) -> Result<Vec<SimilarityResult>> {
+        let kk = k.min(self.len()).max(1);
+        let (mut ids, mut sc, mut di, mut n) = (vec![0u8; 16 * kk], vec![0f32; kk], vec![0f32; kk], 0u64);
+        let cf = filter.map(c_filter);
+        check(unsafe {
+            sys::cx_search(self.h, query.as_ptr(), query.len() as u32, k.min(kk) as u64,
+                           cf.as_ref().map_or(ptr::null(), |c| &c.raw), ids.as_mut_ptr(), sc.as_mut_ptr(),
+                           di.as_mut_ptr(), &mut n)
+        })?;
+        Ok(Self::collect(&ids, &sc, &di, n as usize))
+    }
+    fn search_threshold(&self, query: &Embedding, threshold: f32, filter: Option<&VectorFilter>)
+        -> Result<Vec<SimilarityResult>> {
+        let cf = filter.map(c_filter);
+        let mut cap = self.len().clamp(1, 4096);
+        loop {
+            let (mut ids, mut sc, mut di) = (vec![0u8; 16 * cap], vec![0f32; cap], vec![0f32; cap]);
+            let (mut n, mut total) = (0u64, 0u64);
+            check(unsafe {
+                sys::cx_search_threshold(self.h, query.as_ptr(), query.len() as u32, threshold,
+                                         cf.as_ref().map_or(ptr::null(), |c| &c.raw), cap as u64,
+                                         ids.as_mut_ptr(), sc.as_mut_ptr(), di.as_mut_ptr(), &mut n, &mut total)
+            })?;
+            if total as usize <= cap {
+                return Ok(Self::collect(&ids, &sc, &di, n as usize));
+            }
+            cap = total as usize;
+        }
+    }
+    fn search_batch(&self, queries: &[(NodeId, Embedding)], k: usize, filter: Option<&VectorFilter>)
+        -> Result<HashMap<NodeId, Vec<SimilarityResult>>> {
+        if queries.is_empty() {
+            return Ok(HashMap::new());
+        }
+        let (b, dim) = (queries.len(), queries[0].1.len());
+        let flat: Vec<f32> = queries.iter().flat_map(|(_, e)| e.iter().copied()).collect();
+        let (mut ids, mut sc, mut di, mut n) =
+            (vec![0u8; 16 * b * k], vec![0f32; b * k], vec![0f32; b * k], vec![0u64; b]);
+        let cf = filter.map(c_filter);
+        check(unsafe {
+            sys::cx_search_batch(self.h, flat.as_ptr(), b as u64, dim as u32, k as u64,
+                                 cf.as_ref().map_or(ptr::null(), |c| &c.raw), ids.as_mut_ptr(),
+                                 sc.as_mut_ptr(), di.as_mut_ptr(), n.as_mut_ptr())
+        })?;
+        let mut map = HashMap::with_capacity(b);
+        for (i, (qid, _)) in queries.iter().enumerate() {
+            let r = Self::collect(&ids[16 * i * k..], &sc[i * k..], &di[i * k..], n[i] as usize);
+            map.insert(*qid, r);
+        }
+        Ok(map)
+    }
+    fn len(&self) -> usize {
+        unsafe { sys::cx_len(self.h) as usize }
+    }
+    fn rebuild(&mut self) -> Result<()> {
+        check(unsafe { sys::cx_rebuild(self.h) })
+    }
+    fn save(&self, path: &Path) -> Result<()> {
+        let p = CString::new(path.to_string_lossy().as_bytes()).unwrap();
+        check(unsafe { sys::cx_save(self.h, p.as_ptr()) })
+    }
+    fn load(path: &Path) -> Result<Self> {
+        let p = CString::new(path.to_string_lossy().as_bytes()).unwrap();
+        let mut h = ptr::null_mut();
+        check(unsafe { sys::cx_load(p.as_ptr(), 0, &mut h) })?;
+        Ok(Self { h })
+    }
+}

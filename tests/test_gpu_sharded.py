@@ -1,0 +1,89 @@
+"""The CUDA exchange kernels of the row-sharded search (cx_merge.cu) against the torch
+reference merge that the world_size-2 gloo test validates against the single-index
+oracle, plus a simulated 4-shard search on one GPU compared with the oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from cortex_b200 import GpuVectorIndex, _capi, synth
+from cortex_b200.sharded import merge_gathered, pack_keys
+from oracle.binding import OracleIndex
+
+pytestmark = pytest.mark.gpu
+
+
+def cuda_pack(L, rows, score, dist, n, offset):
+    B, k = rows.shape
+    payload = torch.empty((B, k, 2), dtype=torch.int64, device=rows.device)
+    st = L.cx_pack_topk_device(rows.data_ptr(), score.data_ptr(), dist.data_ptr(), n.data_ptr(), B, k, offset,
+                               payload.data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert st == 0, L.cx_last_error()
+    return payload
+
+
+def cuda_merge(L, gathered, k):
+    W, B = gathered.shape[0], gathered.shape[1]
+    dev = gathered.device
+    grow = torch.empty((B, k), dtype=torch.int64, device=dev)
+    gs = torch.empty((B, k), dtype=torch.float32, device=dev)
+    gd = torch.empty((B, k), dtype=torch.float32, device=dev)
+    gn = torch.empty((B,), dtype=torch.int32, device=dev)
+    st = L.cx_merge_topk_device(gathered.data_ptr(), W, B, k, grow.data_ptr(), gs.data_ptr(), gd.data_ptr(),
+                                gn.data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    assert st == 0, L.cx_last_error()
+    torch.cuda.synchronize()
+    return grow, gs, gd, gn
+
+
+def test_four_simulated_shards_match_single_index_oracle():
+    L = _capi.load()
+    n, d, b, k, W = 8000, 384, 33, 10, 4
+    corpus = synth.make_corpus(n, d, zero_row=True, dup_frac=0.05, seed=77)
+    ids = synth.make_ids(n)
+    Q = synth.make_queries(corpus, b, seed=77)
+    per = n // W
+    payloads = []
+    dq = torch.from_numpy(Q).cuda()
+    for w in range(W):
+        g = GpuVectorIndex(d)
+        g.insert_batch(ids[w * per:(w + 1) * per], corpus[w * per:(w + 1) * per])
+        rows, sc, di, nn = g.search_batch_device(dq, k, stream=torch.cuda.current_stream().cuda_stream)
+        payloads.append(cuda_pack(L, rows, sc, di, nn, w * per))
+    grow, gs, gd, gn = cuda_merge(L, torch.stack(payloads).contiguous(), k)
+    o = OracleIndex(d, faithful_copy=False)
+    o.insert_batch(ids, corpus)
+    _, osc, odi, orow, on = o.search_batch(Q, k)
+    assert np.array_equal(gn.cpu().numpy(), on.astype(np.int32))
+    assert np.array_equal(grow.cpu().numpy(), orow.astype(np.int64))
+    a, bb = gs.cpu().numpy(), osc
+    assert np.all((a.view(np.uint32) == bb.view(np.uint32)) | (np.isnan(a) & np.isnan(bb)))
+    a, bb = gd.cpu().numpy(), odi
+    assert np.all((a.view(np.uint32) == bb.view(np.uint32)) | (np.isnan(a) & np.isnan(bb)))
+
+
+def test_cuda_merge_equals_torch_merge_with_ties_nan_and_short_lists():
+    L = _capi.load()
+    torch.manual_seed(5)
+    W, B, k = 3, 40, 7
+    payloads, keys, dists = [], [], []
+    for w in range(W):
+        dist = (torch.randint(0, 6, (B, k)).float() * 0.25)  # few distinct values -> many ties
+        dist[torch.rand(B, k) < 0.1] = float("nan")
+        dist, _ = torch.sort(dist, dim=1)
+        score = (1.0 - dist).clamp(0, 1)
+        rows = torch.stack([torch.randperm(1000)[:k] for _ in range(B)]).int()
+        n = torch.randint(0, k + 1, (B,)).int()
+        r, s, dd, nn = rows.cuda(), score.cuda(), dist.cuda(), n.cuda()
+        payloads.append(cuda_pack(L, r, s, dd, nn, w * 1000))
+        keys.append(pack_keys(rows, score, n, w * 1000))
+        dists.append(dist)
+    grow, gs, gd, gn = cuda_merge(L, torch.stack(payloads).contiguous(), k)
+    trow, ts, td, tn = merge_gathered(torch.stack(keys), torch.stack(dists), k)
+    assert torch.equal(gn.cpu(), tn)
+    for b in range(B):
+        m = int(tn[b])
+        assert torch.equal(grow.cpu()[b, :m], trow[b, :m])
+        x, y = gs.cpu()[b, :m], ts[b, :m]
+        assert torch.all((x == y) | (torch.isnan(x) & torch.isnan(y)))
