@@ -182,7 +182,21 @@ def cpu_reference_leg(corpus_np, queries_np, k, steps, warmup, n_queries):
     return qps, cores, 1e3 * tot / len(times), sample
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line goes to the real stdout; everything else (NCCL banners, library
+    chatter) was redirected to stderr at start-up."""
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # fd 1 -> stderr for the rest of the run
     a = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -198,14 +212,14 @@ def main():
         corpus = make_corpus_torch(a.rows, a.dim, SEED, "cpu")
         queries = make_queries_torch(corpus, max(256, a.batch), SEED).numpy()
         qps, cores, ms, sample = cpu_reference_leg(corpus.numpy(), queries, a.k, a.steps, a.warmup, a.cpu_queries)
-        print(json.dumps({
+        emit({
             "impl": "reference", "metric": "queries/s", "value": qps, "unit": "queries/s", "n_gpus": a.gpus,
             "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload, "seed": SEED},
             "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        }))
+        })
         return
 
     import torch
@@ -407,7 +421,7 @@ def main():
                   "exact": st1["queries_exact"] - st0["queries_exact"],
                   "fallbacks": st1["fallbacks"] - st0["fallbacks"]},
     }
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

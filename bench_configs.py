@@ -1,0 +1,253 @@
+#!/usr/bin/env python
+"""bench_configs.py -- the BASELINE.json configs beyond bench.py's headline line.
+
+Writes one JSON document (default profiles/results_r1.json) with a section per config:
+  cfg1  10k x 384, 100 queries, top-10: GPU vs CPU oracle, ids/score bits compared
+  cfg2  1M x 384, query batch sweep 1..1024, top-10: queries/s, kernel roofline per batch
+  cfg3  auto-link cycle: B new nodes x N-row corpus, k=100 (+ threshold 0.75): scored pairs/s
+  cfg5  streaming ingest: 256-node batches searched (k=100) then appended to a growing corpus,
+        p50/p99 latency per batch
+cfg4 (50M x 1024 bf16 on 8 GPUs) is not run: see DESIGN.md §8.
+All timing is CUDA events on the caller's stream around the public device API.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import bench  # noqa: E402  (synthetic data + peaks)
+
+
+def ids_for(n, start=0):
+    ids = np.zeros((n, 16), np.uint8)
+    ids[:, 8:] = (np.arange(n, dtype=np.uint64) + start).astype(">u8").view(np.uint8).reshape(-1, 8)
+    return ids
+
+
+def timed(fn, steps, warmup, torch):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps  # ms per call
+
+
+def cfg1(torch, out):
+    from cortex_b200 import GpuVectorIndex, synth
+    from oracle.binding import OracleIndex, max_threads
+
+    corpus = synth.make_corpus(10_000, 384, zero_row=True)
+    Q = synth.make_queries(corpus, 100)
+    ids = synth.make_ids(10_000)
+    g = GpuVectorIndex(384)
+    g.insert_batch(ids, corpus)
+    o = OracleIndex(384, faithful_copy=True)
+    o.insert_batch(ids, corpus)
+    t0 = time.perf_counter()
+    oi, osc, od, _, on = o.search_batch(Q, 10, n_threads=max_threads())
+    t_cpu = time.perf_counter() - t0
+    gi, gs, gd, gn = g.search_batch_arrays(Q, 10)
+    t0 = time.perf_counter()
+    for _ in range(20):
+        g.search_batch_arrays(Q, 10)
+    t_gpu = (time.perf_counter() - t0) / 20
+    same = (np.array_equal(gi, oi) and np.array_equal(gn, on)
+            and bool(np.all((gs.view(np.uint32) == osc.view(np.uint32)) | (np.isnan(gs) & np.isnan(osc)))))
+    out["cfg1"] = {"workload": "10k x 384, 100 queries, top-10", "ids_and_score_bits_identical_to_oracle": same,
+                   "gpu_ms_per_batch_host_to_host": t_gpu * 1e3, "gpu_queries_per_s": 100 / t_gpu,
+                   "cpu_oracle_ms_per_batch": t_cpu * 1e3, "cpu_queries_per_s": 100 / t_cpu,
+                   "cpu_threads": max_threads(), "paths": g.stats()}
+
+
+def cfg2(torch, out, rows):
+    from cortex_b200 import GpuVectorIndex
+
+    dev = torch.device("cuda", 0)
+    corpus = bench.make_corpus_torch(rows, 384, bench.SEED, dev)
+    q_all = bench.make_queries_torch(corpus, 1024, bench.SEED)
+    ix = GpuVectorIndex(384)
+    ix.reserve(rows)
+    ix.insert_batch_device(ids_for(rows), corpus)
+    del corpus
+    torch.cuda.empty_cache()
+    ix.set_option("profile", 1)
+    pk = bench.peaks()
+    s = torch.cuda.current_stream().cuda_stream
+    res = []
+    for B in (1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024):
+        dq = q_all[:B].contiguous()
+        hq = dq.cpu().numpy()
+        buf = [None]
+
+        def dev_step():
+            buf[0] = ix.search_batch_device(dq, 10, stream=s, out=buf[0])
+
+        steps = 50 if B <= 64 else 20
+        dev_step()
+        st0 = ix.stats()
+        ms = timed(dev_step, steps, 3, torch)
+        st1 = ix.stats()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            ix.search_batch_arrays(hq, 10)
+        ms_host = (time.perf_counter() - t0) / steps * 1e3
+        launches = st1["pass_kernel_launches"] - st0["pass_kernel_launches"]
+        ns = st1["pass_kernel_ns"] - st0["pass_kernel_ns"]
+        tensor = st1["queries_tensor"] > st0["queries_tensor"]
+        us = ns * 1e-3 / max(1, launches)
+        row = {"batch": B, "queries_per_s": B / (ms * 1e-3), "ms_per_batch": ms,
+               "host_to_host_queries_per_s": B / (ms_host * 1e-3), "pass": "tensor" if tensor else "stream",
+               "scan_kernel_us": us, "fallbacks": st1["fallbacks"] - st0["fallbacks"]}
+        if tensor:
+            tf = 2.0 * 384 * B * rows / (us * 1e-6) / 1e12
+            row["tflops"] = tf
+            row["frac_of_sustained_bf16"] = tf / pk["bf16_tflops_sustained"]
+            row["shadow_stream_gbs"] = rows * 384 * 2 / (us * 1e-6) / 1e9
+            row["frac_of_hbm_for_shadow_stream"] = row["shadow_stream_gbs"] / pk["hbm_gbs"]
+        else:
+            gbs = rows * 384 * 4 / (us * 1e-6) / 1e9  # the fp32 matrix is read once per launch
+            row["hbm_gbs"] = gbs
+            row["frac_of_measured_hbm"] = gbs / pk["hbm_gbs"]
+        res.append(row)
+    out["cfg2"] = {"workload": f"{rows} x 384 fp32, top-10, query batch sweep", "rows": res}
+    return ix, q_all
+
+
+def cfg3(torch, out, rows, n_new):
+    """auto-link cycle: every new node searches the corpus for its 100 nearest neighbours
+    (linker/auto_linker.rs:215-222), candidates with score >= 0.75 become links (rules.rs:50)."""
+    from cortex_b200 import GpuVectorIndex
+
+    dev = torch.device("cuda", 0)
+    ix = GpuVectorIndex(384)
+    ix.reserve(rows)
+    chunk = 2_000_000
+    for s0 in range(0, rows, chunk):
+        n = min(chunk, rows - s0)
+        c = bench.make_corpus_torch(n, 384, bench.SEED + 31 * (s0 // chunk), dev)
+        ix.insert_batch_device(ids_for(n, s0), c)
+        if s0 == 0:
+            q_src = c[:max(n_new, 1024)].clone() if n >= n_new else c.clone()
+        del c
+    torch.cuda.empty_cache()
+    g = torch.Generator(device=dev)
+    g.manual_seed(7)
+    reps = (n_new + q_src.shape[0] - 1) // q_src.shape[0]
+    Q = q_src.repeat(reps, 1)[:n_new].clone()
+    Q += torch.randn(Q.shape, generator=g, device=dev) * 0.03
+    Q /= Q.norm(dim=1, keepdim=True)
+    Q = Q.contiguous()
+    s = torch.cuda.current_stream().cuda_stream
+    buf = [None]
+
+    def step():
+        buf[0] = ix.search_batch_device(Q, 100, stream=s, out=buf[0])
+
+    step()
+    st0 = ix.stats()
+    ms = timed(step, 2, 0, torch)
+    st1 = ix.stats()
+    rows_t, score, dist, n = buf[0]
+    links = int((score >= 0.75).sum().item())
+    pairs = float(n_new) * rows
+    tf = 2.0 * 384 * pairs / (ms * 1e-3) / 1e12
+    pk = bench.peaks()
+    out["cfg3"] = {"workload": f"auto-link cycle: {n_new} new nodes x {rows}-row corpus, k=100, threshold 0.75",
+                   "ms_per_cycle": ms, "scored_pairs_per_s": pairs / (ms * 1e-3), "tflops": tf,
+                   "frac_of_sustained_bf16": tf / pk["bf16_tflops_sustained"],
+                   "link_candidates_at_0.75": links,
+                   "tensor_queries": st1["queries_tensor"] - st0["queries_tensor"],
+                   "stream_retries": st1["queries_stream"] - st0["queries_stream"],
+                   "exact_fallbacks": st1["queries_exact"] - st0["queries_exact"]}
+
+
+def cfg5(torch, out, final_rows):
+    """streaming ingest: 256-node batches; each batch is searched (k=100) against the corpus so far
+    and then appended (the auto-linker's steady state)."""
+    from cortex_b200 import GpuVectorIndex
+
+    dev = torch.device("cuda", 0)
+    ix = GpuVectorIndex(384)
+    ix.reserve(final_rows)
+    s = torch.cuda.current_stream().cuda_stream
+    seed_rows = 4096
+    c = bench.make_corpus_torch(seed_rows, 384, bench.SEED + 5, dev)
+    ix.insert_batch_device(ids_for(seed_rows), c)
+    pool = bench.make_corpus_torch(1 << 18, 384, bench.SEED + 6, dev)
+    marks = [100_000, 500_000, 1_000_000, 2_000_000, 5_000_000]
+    lat = {m: [] for m in marks if m <= final_rows}
+    n_rows = seed_rows
+    buf = None
+    b = 0
+    t_all = time.perf_counter()
+    while n_rows + 256 <= final_rows:
+        rows = pool[(b * 256) % (pool.shape[0] - 256):][:256].contiguous()
+        near = [m for m in lat if 0 <= m - n_rows < 256 * 200]  # the 200 batches before each mark
+        if near:
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+        buf = ix.search_batch_device(rows, 100, stream=s, out=buf)
+        ix.insert_batch_device(ids_for(256, n_rows), rows)
+        if near:
+            torch.cuda.synchronize()
+            lat[near[0]].append((time.perf_counter() - t0) * 1e3)
+        n_rows += 256
+        b += 1
+    total_s = time.perf_counter() - t_all
+    out["cfg5"] = {"workload": f"256-node batches, search k=100 then append, corpus grows to {final_rows}",
+                   "batches": b, "total_s": total_s, "batches_per_s": b / total_s,
+                   "latency_ms_at_rows": {str(m): {"p50": float(np.percentile(v, 50)), "p99": float(np.percentile(v, 99)),
+                                                    "n": len(v)} for m, v in lat.items() if v}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "results_r1.json"))
+    ap.add_argument("--only", default="1,2,3,5")
+    ap.add_argument("--cfg2-rows", type=int, default=1_000_000)
+    ap.add_argument("--cfg3-rows", type=int, default=10_000_000)
+    ap.add_argument("--cfg3-new", type=int, default=100_000)
+    ap.add_argument("--cfg5-rows", type=int, default=5_000_000)
+    a = ap.parse_args()
+    import torch
+
+    torch.cuda.set_device(0)
+    out = {"gpu": torch.cuda.get_device_name(0), "peaks": bench.peaks(), "seed": bench.SEED,
+           "host_threads": os.cpu_count()}
+    only = set(a.only.split(","))
+    if "1" in only:
+        cfg1(torch, out)
+        print("cfg1", json.dumps(out["cfg1"])[:400], file=sys.stderr)
+    if "2" in only:
+        cfg2(torch, out, a.cfg2_rows)
+        for r in out["cfg2"]["rows"]:
+            print("cfg2", json.dumps(r), file=sys.stderr)
+        torch.cuda.empty_cache()
+    if "3" in only:
+        cfg3(torch, out, a.cfg3_rows, a.cfg3_new)
+        print("cfg3", json.dumps(out["cfg3"]), file=sys.stderr)
+        torch.cuda.empty_cache()
+    if "5" in only:
+        cfg5(torch, out, a.cfg5_rows)
+        print("cfg5", json.dumps(out["cfg5"]), file=sys.stderr)
+    os.makedirs(os.path.dirname(a.out), exist_ok=True)
+    with open(a.out, "w") as fp:
+        json.dump(out, fp, indent=1)
+    print(json.dumps({"wrote": a.out}))
+
+
+if __name__ == "__main__":
+    main()

@@ -50,6 +50,7 @@ SYMBOLS = {
     "cx_index_destroy": (None, [C.c_void_p]),
     "cx_insert": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
     "cx_insert_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32]),
+    "cx_insert_batch_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32]),
     "cx_remove": (C.c_int, [C.c_void_p, C.c_void_p]),
     "cx_set_metadata": (C.c_int, [C.c_void_p, C.c_void_p, C.c_char_p, C.c_char_p]),
     "cx_len": (C.c_uint64, [C.c_void_p]),

@@ -284,6 +284,57 @@ extern "C" cx_status cx_insert_batch(cx_index* h, const uint8_t* ids, const floa
   return CX_OK;
 }
 
+// Bulk append of rows that already live in device memory (row-major [n][len] f32): the
+// "mmap'd vectors bulk-uploaded once" path of the north star without a host round trip.
+// All ids must be new (this is an append, not an upsert).
+extern "C" cx_status cx_insert_batch_device(cx_index* h, const uint8_t* ids, const float* d_rows, uint64_t n,
+                                            uint32_t len) {
+  if (!h) return fail(CX_ERR_VALIDATION, "null index");
+  if (len != h->dim)
+    return fail(CX_ERR_VALIDATION, "Embedding dimension mismatch: expected %u, got %u", h->dim, len);
+  if (!n) return CX_OK;
+  if (!ids || !d_rows) return fail(CX_ERR_VALIDATION, "null ids/rows");
+  for (uint64_t i = 0; i < n; ++i)
+    if (h->id2row.count(load_id(ids + 16 * i)))
+      return fail(CX_ERR_VALIDATION, "cx_insert_batch_device appends only: id %llu already present",
+                  (unsigned long long)i);
+  CU(cudaSetDevice(h->device));
+  cx_status st = grow(h, h->n_rows + n);
+  if (st != CX_OK) return st;
+  cudaStream_t s = h->mut_stream;
+  const uint64_t first_new = h->n_rows;
+  h->h_ids.insert(h->h_ids.end(), ids, ids + 16 * n);
+  for (uint64_t i = 0; i < n; ++i) {
+    Id128 key = load_id(ids + 16 * i);
+    if (!h->id2row.emplace(key, (uint32_t)(first_new + i)).second) {
+      return fail(CX_ERR_VALIDATION, "duplicate id inside the batch at %llu", (unsigned long long)i);
+    }
+    uint32_t mw = 0, ag = 0;
+    auto om = h->orphan_meta.find(key);
+    if (om != h->orphan_meta.end()) {
+      mw = meta_word(true, om->second.first);
+      ag = om->second.second;
+      h->orphan_meta.erase(om);
+    }
+    h->h_meta.push_back(mw);
+    h->h_agent.push_back(ag);
+  }
+  h->n_rows += n;
+  h->n_live += n;
+  // the caller's buffer may have been produced on another stream: order after the device
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy2DAsync(h->dE + first_new * h->ld, h->ld * sizeof(float), d_rows, len * sizeof(float),
+                       len * sizeof(float), n, cudaMemcpyDeviceToDevice, s));
+  CU(cudaMemcpyAsync(h->dIds + first_new * 16, h->h_ids.data() + first_new * 16, n * 16, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(h->dMeta + first_new, h->h_meta.data() + first_new, n * 4, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(h->dAgent + first_new, h->h_agent.data() + first_new, n * 4, cudaMemcpyHostToDevice, s));
+  launch_prepare_rows(h->dE, h->dNorm, h->dRnorm, h->dE16, h->dim, h->ld, h->ld16, (uint32_t)first_new, (uint32_t)n, s);
+  h->launches += h->dE16 ? 2 : 1;
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(s));
+  return CX_OK;
+}
+
 extern "C" cx_status cx_insert(cx_index* h, const uint8_t id[16], const float* embedding, uint32_t len) {
   return cx_insert_batch(h, id, embedding, 1, len);
 }

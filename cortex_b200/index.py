@@ -156,6 +156,13 @@ class GpuVectorIndex:
             raise CortexError("insert_batch needs ids [n,16] and rows [n,dim]")
         _check(self._L.cx_insert_batch(self._h, ids.ctypes.data, rows.ctypes.data, rows.shape[0], rows.shape[1]))
 
+    def insert_batch_device(self, ids: np.ndarray, d_rows) -> None:
+        """Append rows that already live in HBM (torch.float32 CUDA tensor [n, dim]); ids on the host."""
+        ids = np.ascontiguousarray(ids, dtype=np.uint8).reshape(-1, 16)
+        assert d_rows.is_cuda and d_rows.is_contiguous() and d_rows.shape[0] == ids.shape[0]
+        _check(self._L.cx_insert_batch_device(self._h, ids.ctypes.data, d_rows.data_ptr(), d_rows.shape[0],
+                                              d_rows.shape[1]))
+
     def remove(self, node_id) -> None:
         _check(self._L.cx_remove(self._h, _id16(node_id).ctypes.data))
 

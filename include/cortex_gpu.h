@@ -77,6 +77,9 @@ void cx_index_destroy(cx_index* h);
 cx_status cx_insert(cx_index* h, const uint8_t id[16], const float* embedding, uint32_t len);
 /* Bulk form of the startup loop serve.rs:111-117 / api.rs:55-69: n rows, row-major. */
 cx_status cx_insert_batch(cx_index* h, const uint8_t* ids, const float* rows, uint64_t n, uint32_t len);
+/* Same, for rows already resident in device memory ([n][len] f32, row-major); append only
+ * (every id must be new).  ids stay host-side. */
+cx_status cx_insert_batch_device(cx_index* h, const uint8_t* ids, const float* d_rows, uint64_t n, uint32_t len);
 /* VectorIndex::remove, index.rs:316-323.  Unknown id is not an error. */
 cx_status cx_remove(cx_index* h, const uint8_t id[16]);
 /* HnswIndex::set_metadata, index.rs:219-222. */

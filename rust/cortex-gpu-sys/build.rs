@@ -12,7 +12,7 @@ fn main() {
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "static", "--expt-relaxed-constexpr"])
         .arg("-I").arg(root.join("include")).arg("-I").arg(&csrc)
         .arg("-o").arg(&lib);
-    for f in ["cx_index.cu", "cx_search.cu", "cx_exact.cu", "cx_stream.cu", "cx_tensor.cu", "cx_select.cu"] {
+    for f in ["cx_index.cu", "cx_search.cu", "cx_exact.cu", "cx_stream.cu", "cx_tensor.cu", "cx_select.cu", "cx_merge.cu"] {
         println!("cargo:rerun-if-changed={}", csrc.join(f).display());
         cmd.arg(csrc.join(f));
     }

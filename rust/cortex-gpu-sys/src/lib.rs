@@ -38,6 +38,7 @@ extern "C" {
     pub fn cx_index_destroy(h: *mut cx_index);
     pub fn cx_insert(h: *mut cx_index, id: *const u8, embedding: *const f32, len: u32) -> c_int;
     pub fn cx_insert_batch(h: *mut cx_index, ids: *const u8, rows: *const f32, n: u64, len: u32) -> c_int;
+    pub fn cx_insert_batch_device(h: *mut cx_index, ids: *const u8, d_rows: *const f32, n: u64, len: u32) -> c_int;
     pub fn cx_remove(h: *mut cx_index, id: *const u8) -> c_int;
     pub fn cx_set_metadata(h: *mut cx_index, id: *const u8, kind: *const c_char, agent: *const c_char) -> c_int;
     pub fn cx_len(h: *const cx_index) -> u64;
@@ -56,6 +57,11 @@ extern "C" {
                                   filter: *const cx_filter, d_out_rows: *mut u32, d_out_score: *mut f32,
                                   d_out_distance: *mut f32, d_out_ids: *mut u8, d_out_n: *mut u32,
                                   stream: *mut c_void) -> c_int;
+    pub fn cx_pack_topk_device(d_rows: *const u32, d_score: *const f32, d_distance: *const f32, d_n: *const u32,
+                               b: u64, k: u64, row_offset: u64, d_payload: *mut u64, stream: *mut c_void) -> c_int;
+    pub fn cx_merge_topk_device(d_gathered: *const u64, world: u32, b: u64, k: u64, d_out_rows: *mut i64,
+                                d_out_score: *mut f32, d_out_distance: *mut f32, d_out_n: *mut u32,
+                                stream: *mut c_void) -> c_int;
     pub fn cx_save(h: *const cx_index, path: *const c_char) -> c_int;
     pub fn cx_load(path: *const c_char, device: c_int, out: *mut *mut cx_index) -> c_int;
     pub fn cx_row_id(h: *const cx_index, row: u32, out_id: *mut u8) -> c_int;
