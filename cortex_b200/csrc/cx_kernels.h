@@ -105,6 +105,12 @@ void launch_exact_emit(const StoreView& st, const QueryView& qv, uint32_t q, con
                        uint32_t n_keys, uint32_t k, uint32_t min_ord, uint32_t* rows, float* score,
                        float* dist, uint8_t* ids, uint32_t* n_out, uint32_t* n_total, cudaStream_t s);
 
+// auto-link candidate post-pass over device-resident search results (cx_merge.cu)
+void launch_autolink_filter(const uint32_t* rows, const float* score, const uint32_t* n, const uint32_t* self_rows,
+                            const uint8_t* ids, uint32_t B, uint32_t k, float threshold, uint32_t max_edges,
+                            uint32_t* out_rows, float* out_score, uint8_t* out_ids, uint32_t* out_n,
+                            cudaStream_t s);
+
 // compaction helper for rebuild(): dst[i] = src[live[i]] for all per-row arrays
 void launch_gather_rows(const StoreView& src, float* E, float* norm, float* rnorm, uint32_t* meta,
                         uint32_t* agent, uint8_t* ids, void* E16, const uint32_t* live, uint32_t n_live,

@@ -66,6 +66,45 @@ __global__ void merge_topk_kernel(const uint64_t* __restrict__ gathered, uint32_
   if (tid == 0) out_n[b] = s_valid < k ? s_valid : k;
 }
 
+// ---- auto-link candidate post-pass ------------------------------------------------------
+// Per new node b: walk its k results in order (best first), skip the node itself, keep
+// score >= threshold (SimilarityLinkRule, linker/rules.rs:50), stop at max_edges
+// (linker/auto_linker.rs:261).  One thread per node; k is ~100.
+__global__ void autolink_filter_kernel(const uint32_t* __restrict__ rows, const float* __restrict__ score,
+                                       const uint32_t* __restrict__ n, const uint32_t* __restrict__ self_rows,
+                                       const uint8_t* __restrict__ ids, uint32_t B, uint32_t k, float threshold,
+                                       uint32_t max_edges, uint32_t* __restrict__ out_rows,
+                                       float* __restrict__ out_score, uint8_t* __restrict__ out_ids,
+                                       uint32_t* __restrict__ out_n) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const uint32_t self = self_rows ? self_rows[b] : 0xFFFFFFFFu;
+  const uint32_t nb = n[b] < k ? n[b] : k;
+  uint32_t m = 0;
+  for (uint32_t j = 0; j < nb && m < max_edges; ++j) {
+    const uint32_t r = rows[(size_t)b * k + j];
+    const float s = score[(size_t)b * k + j];
+    if (r == self) continue;
+    if (!(s >= threshold)) continue;  // false for NaN
+    const size_t o = (size_t)b * max_edges + m;
+    out_rows[o] = r;
+    out_score[o] = s;
+    if (out_ids)
+      *reinterpret_cast<uint4*>(out_ids + o * 16) = *reinterpret_cast<const uint4*>(ids + (size_t)r * 16);
+    ++m;
+  }
+  out_n[b] = m;
+}
+
+void launch_autolink_filter(const uint32_t* rows, const float* score, const uint32_t* n, const uint32_t* self_rows,
+                            const uint8_t* ids, uint32_t B, uint32_t k, float threshold, uint32_t max_edges,
+                            uint32_t* out_rows, float* out_score, uint8_t* out_ids, uint32_t* out_n,
+                            cudaStream_t s) {
+  if (!B) return;
+  autolink_filter_kernel<<<(B + 127) / 128, 128, 0, s>>>(rows, score, n, self_rows, ids, B, k, threshold, max_edges,
+                                                         out_rows, out_score, out_ids, out_n);
+}
+
 }  // namespace cx
 
 using namespace cx;

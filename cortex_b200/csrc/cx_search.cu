@@ -508,3 +508,87 @@ extern "C" cx_status cx_search_batch_device(cx_index* h, const float* d_queries,
   // run_search returned with its stream idle: the results are complete and visible
   return st;
 }
+
+// ------------------------------------------------------------------------------
+// The scan step of AutoLinker::run_cycle (linker/auto_linker.rs:215-264) for a batch of
+// new nodes, restricted to what the similarity scan decides: search(emb, k) (k = 100 in the
+// reference, :221), skip the node itself (:235-237), SimilarityLinkRule `score >= threshold`
+// (linker/rules.rs:50), at most max_edges_per_node (:261).  Everything else in that loop
+// (storage lookups, structural rules, dedupe against existing edges) stays on the host.
+extern "C" cx_status cx_autolink_batch_device(cx_index* h, const float* d_embeddings, uint64_t B, uint64_t k,
+                                              float threshold, uint32_t max_edges_per_node,
+                                              const uint32_t* d_self_rows, uint32_t* d_scratch_rows,
+                                              float* d_scratch_score, float* d_scratch_distance,
+                                              uint32_t* d_scratch_n, uint32_t* d_out_rows, float* d_out_score,
+                                              uint8_t* d_out_ids, uint32_t* d_out_n, void* stream) {
+  if (!h) return fail(CX_ERR_VALIDATION, "null index");
+  if (!d_scratch_rows || !d_scratch_score || !d_scratch_distance || !d_scratch_n || !d_out_rows || !d_out_score ||
+      !d_out_n)
+    return fail(CX_ERR_VALIDATION, "null device buffer");
+  if (!B) return CX_OK;
+  if (h->n_live == 0) {
+    CU(cudaMemsetAsync(d_out_n, 0, B * 4, (cudaStream_t)stream));
+    return CX_OK;
+  }
+  const uint64_t kk = k < h->n_rows ? k : h->n_rows;
+  cx_status st = cx_search_batch_device(h, d_embeddings, B, kk, nullptr, d_scratch_rows, d_scratch_score,
+                                        d_scratch_distance, nullptr, d_scratch_n, stream);
+  if (st != CX_OK) return st;
+  launch_autolink_filter(d_scratch_rows, d_scratch_score, d_scratch_n, d_self_rows, h->dIds, (uint32_t)B, (uint32_t)kk,
+                         threshold, max_edges_per_node, d_out_rows, d_out_score, d_out_ids, d_out_n,
+                         (cudaStream_t)stream);
+  h->launches += 1;
+  CU(cudaGetLastError());
+  return CX_OK;
+}
+
+extern "C" cx_status cx_autolink_batch(cx_index* h, const uint8_t* new_ids, const float* embeddings, uint64_t B,
+                                       uint32_t len, uint64_t k, float threshold, uint32_t max_edges_per_node,
+                                       uint8_t* out_to_ids, float* out_score, uint32_t* out_n) {
+  if (!h) return fail(CX_ERR_VALIDATION, "null index");
+  if (!out_n || (B && (!embeddings || !out_to_ids || !out_score))) return fail(CX_ERR_VALIDATION, "null argument");
+  if (len != h->dim)
+    return fail(CX_ERR_VALIDATION, "Embedding dimension mismatch: expected %u, got %u", h->dim, len);
+  for (uint64_t b = 0; b < B; ++b) out_n[b] = 0;
+  if (!B || h->n_live == 0 || !max_edges_per_node || !k) return CX_OK;
+  CU(cudaSetDevice(h->device));
+  const uint64_t kk = k < h->n_rows ? k : h->n_rows;
+  const uint32_t me = max_edges_per_node;
+  std::vector<uint32_t> self(B, 0xFFFFFFFFu);
+  if (new_ids)
+    for (uint64_t b = 0; b < B; ++b) {
+      auto it = h->id2row.find(load_id(new_ids + 16 * b));
+      if (it != h->id2row.end()) self[b] = it->second;
+    }
+  // one device block for everything this call needs
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  const size_t o_q = take(B * h->dim * 4), o_self = take(B * 4), o_rows = take(B * kk * 4), o_sc = take(B * kk * 4),
+               o_di = take(B * kk * 4), o_n = take(B * 4), o_or = take(B * me * 4), o_os = take(B * me * 4),
+               o_oi = take(B * me * 16), o_on = take(B * 4);
+  char* d = nullptr;
+  CU(cudaMalloc((void**)&d, off));
+  cudaStream_t s = h->mut_stream;  // not a mutation, but a stream this handle owns; callers serialise cycles
+  cx_status st = CX_OK;
+  do {
+    if (cudaMemcpyAsync(d + o_q, embeddings, B * h->dim * 4, cudaMemcpyHostToDevice, s) != cudaSuccess ||
+        cudaMemcpyAsync(d + o_self, self.data(), B * 4, cudaMemcpyHostToDevice, s) != cudaSuccess) {
+      st = fail(CX_ERR_CUDA, "upload failed in cx_autolink_batch");
+      break;
+    }
+    st = cx_autolink_batch_device(h, (const float*)(d + o_q), B, kk, threshold, me, (const uint32_t*)(d + o_self),
+                                  (uint32_t*)(d + o_rows), (float*)(d + o_sc), (float*)(d + o_di),
+                                  (uint32_t*)(d + o_n), (uint32_t*)(d + o_or), (float*)(d + o_os),
+                                  (uint8_t*)(d + o_oi), (uint32_t*)(d + o_on), s);
+    if (st != CX_OK) break;
+    if (cudaMemcpyAsync(out_score, d + o_os, B * me * 4, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaMemcpyAsync(out_to_ids, d + o_oi, B * me * 16, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaMemcpyAsync(out_n, d + o_on, B * 4, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaStreamSynchronize(s) != cudaSuccess)
+      st = fail(CX_ERR_CUDA, "download failed in cx_autolink_batch");
+  } while (0);
+  cudaFree(d);
+  h->h2d += B * h->dim * 4;
+  h->d2h += B * me * 20 + B * 4;
+  return st;
+}

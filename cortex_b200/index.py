@@ -268,6 +268,25 @@ class GpuVectorIndex:
                                               n.data_ptr(), C.c_void_p(stream)))
         return out
 
+    def autolink_batch(self, new_nodes: Iterable[Tuple[bytes, Sequence[float]]], threshold: float = 0.75,
+                       k: int = 100, max_edges_per_node: int = 50) -> Dict[bytes, List[Tuple[bytes, float]]]:
+        """The scan step of AutoLinker::run_cycle (linker/auto_linker.rs:215-264) for a batch of new
+        nodes: {node id: [(neighbour id, score)...]} with score >= threshold, best first, self
+        skipped, at most max_edges_per_node each (defaults: linker/config.rs:59-66, auto_linker.rs:221)."""
+        new_nodes = list(new_nodes)
+        if not new_nodes:
+            return {}
+        E = np.ascontiguousarray(np.stack([np.asarray(e, dtype=np.float32) for _, e in new_nodes]))
+        ids = np.ascontiguousarray(np.stack([_id16(i) for i, _ in new_nodes]))
+        B, me = E.shape[0], int(max_edges_per_node)
+        to = np.zeros((B, me, 16), np.uint8)
+        sc = np.zeros((B, me), np.float32)
+        n = np.zeros(B, np.uint32)
+        _check(self._L.cx_autolink_batch(self._h, ids.ctypes.data, E.ctypes.data, B, E.shape[1], int(k),
+                                         C.c_float(threshold), me, to.ctypes.data, sc.ctypes.data, n.ctypes.data))
+        return {bytes(nid): [(to[b, j].tobytes(), float(sc[b, j])) for j in range(int(n[b]))]
+                for b, (nid, _) in enumerate(new_nodes)}
+
     def row_id(self, row: int) -> bytes:
         buf = np.zeros(16, np.uint8)
         _check(self._L.cx_row_id(self._h, int(row), buf.ctypes.data))

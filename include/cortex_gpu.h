@@ -120,6 +120,25 @@ cx_status cx_search_batch_device(cx_index* h, const float* d_queries, uint64_t B
                                  const cx_filter* filter, uint32_t* d_out_rows, float* d_out_score,
                                  float* d_out_distance, uint8_t* d_out_ids, uint32_t* d_out_n, void* stream);
 
+/* The scan step of AutoLinker::run_cycle (linker/auto_linker.rs:215-264) for a batch of B new
+ * nodes: search(embedding, k) (k = 100 in the reference, :221), skip the node itself
+ * (:235-237, found through new_ids; NULL = none of them is in the index), keep
+ * `score >= threshold` (SimilarityLinkRule, linker/rules.rs:50) in best-first order, at most
+ * max_edges_per_node per node (:261).  Outputs are [B][max_edges_per_node]; out_n[b] = links
+ * proposed for node b (to-id, score = edge weight).  Storage lookups, structural rules and
+ * de-duplication against existing edges stay with the caller. */
+cx_status cx_autolink_batch(cx_index* h, const uint8_t* new_ids, const float* embeddings, uint64_t B,
+                            uint32_t len, uint64_t k, float threshold, uint32_t max_edges_per_node,
+                            uint8_t* out_to_ids, float* out_score, uint32_t* out_n);
+/* Device-resident form: embeddings [B][dim] f32 and optional d_self_rows [B] (0xFFFFFFFF = not
+ * in the index) in HBM; d_scratch_* are [B][k] / [B] work buffers for the search results;
+ * outputs [B][max_edges_per_node] (d_out_ids may be NULL). */
+cx_status cx_autolink_batch_device(cx_index* h, const float* d_embeddings, uint64_t B, uint64_t k, float threshold,
+                                   uint32_t max_edges_per_node, const uint32_t* d_self_rows,
+                                   uint32_t* d_scratch_rows, float* d_scratch_score, float* d_scratch_distance,
+                                   uint32_t* d_scratch_n, uint32_t* d_out_rows, float* d_out_score,
+                                   uint8_t* d_out_ids, uint32_t* d_out_n, void* stream);
+
 /* Row-sharded search (one process per GPU): the exchange step around the
  * caller's all-gather.  pack: a rank's device-resident local top-k -> payload
  * [B][k][2] u64 (score-order key | distance bits, global row = row_offset + local row).
