@@ -60,8 +60,10 @@ void launch_prepare_queries(const float* Q, float* qnorm, float* rqnorm, uint32_
 // Returns the number of producer groups it will write (G) for a store of n_rows.
 uint32_t stream_scan_groups(uint32_t n_rows, int sm_count);
 size_t stream_scan_smem(uint32_t ld, uint32_t nq_pass, uint32_t KP);
+// qmap (device, optional, q0 must be 0): pass-local query b is query qmap[b]; its candidate list is slot b
 cudaError_t launch_stream_scan(const StoreView& st, const QueryView& qv, uint32_t q0, uint32_t nq_pass,
-                               const DevFilter& flt, const CandView& cv, int sm_count, cudaStream_t s);
+                               const DevFilter& flt, const CandView& cv, int sm_count, cudaStream_t s,
+                               const uint32_t* qmap = nullptr);
 
 // K5 + K3: merge candidate lists, exact rescore, verify, emit results.
 // eps_cos: bound on |approx - reference| cosine for the pass that produced the candidates.
@@ -70,7 +72,7 @@ cudaError_t launch_stream_scan(const StoreView& st, const QueryView& qv, uint32_
 size_t select_smem(uint32_t cap, uint32_t ld);
 cudaError_t launch_select_rescore(const StoreView& st, const QueryView& qv, uint32_t q0, uint32_t nq,
                                   const CandView& cv, const ResultView& rv, float eps_cos, int scale_by_rqn,
-                                  cudaStream_t s);
+                                  cudaStream_t s, const uint32_t* qmap = nullptr);
 
 // K2: tcgen05 bf16 pass over the normalised shadow matrix.  Q16 = normalised bf16 queries
 // [round_up(nq_total,128)][ld16] made by launch_query_bf16.  One launch serves at most

@@ -11,6 +11,8 @@
 //
 // Whatever the path, emitted scores/distances come from the reference's operation
 // sequence, and ids follow (score desc, NaN last, row asc).
+#include <algorithm>
+
 #include "cx_index.h"
 
 using namespace cx;
@@ -57,6 +59,8 @@ uint32_t keep_count(uint32_t k, uint32_t G) {
   while (KP > k && (uint64_t)KP * G > 16384) --KP;
   return KP;
 }
+
+constexpr uint32_t RETRY_CHUNK = 256;  // unverified tensor-pass queries retried per select launch
 
 // bound on |approximate - reference| cosine for the fp32 streaming pass
 float eps_stream(uint32_t dim) { return (2.1f * (float)dim + 16.0f) * 5.9604645e-8f; }
@@ -105,7 +109,8 @@ struct SearchBufs {
   uint64_t* cand_keys = nullptr;
   uint16_t* q16 = nullptr;        // normalised bf16 queries (tensor pass)
   uint64_t* lists = nullptr;      // tensor pass private-list scratch
-  uint64_t* retry_keys = nullptr; // merged list for single-query streaming retries
+  uint64_t* retry_keys = nullptr; // merged lists for streaming retries of unverified queries
+  uint32_t* qmap = nullptr;       // their query indices
   float* dump = nullptr;          // sampled scores for the tensor pass's cut-off bootstrap
   char* res = nullptr;       // ResultBlock (device) when results are workspace-owned
   uint32_t* ok = nullptr;
@@ -189,7 +194,8 @@ size_t carve_bufs(void* base, const cx_index* h, const Plan& pl, uint32_t n_excl
   if (pl.tensor) {
     sb->q16 = c.take<uint16_t>(align_up(pl.B, 128) * h->ld16);
     sb->lists = (uint64_t*)c.take<char>(tensor_scratch_bytes(h->sm_count));
-    sb->retry_keys = c.take<uint64_t>(pl.cap_retry);
+    sb->retry_keys = c.take<uint64_t>((size_t)RETRY_CHUNK * pl.cap_retry);
+    sb->qmap = c.take<uint32_t>(RETRY_CHUNK);
     const uint64_t nq_launch = pl.B < pl.q_per_launch ? pl.B : pl.q_per_launch;
     sb->dump = c.take<float>(nq_launch * pl.n_slots * 256);
   }
@@ -315,15 +321,22 @@ cx_status run_search(cx_index* h, Workspace* ws, const FilterHost& fh, const Sea
       // pass one at a time (its error bound is ~100x tighter); only what still fails after
       // that is left to the exact path
       CandView cr = cv;
-      cr.keys = sb.retry_keys;
       cr.cap = pl.cap_retry;
       cr.G = pl.G;
       cr.KP = pl.KP;
-      for (uint32_t b : redo) {
-        cr.q_base = b;
-        CU(launch_stream_scan(st, qv, b, 1, flt, cr, h->sm_count, s));
-        CU(launch_select_rescore(st, qv, b, 1, cr, rv, eps_stream(h->dim), 1, s));
-        h->launches += 2;
+      cr.q_base = 0;
+      for (size_t c0 = 0; c0 < redo.size(); c0 += RETRY_CHUNK) {
+        const uint32_t nc = (uint32_t)std::min<size_t>(RETRY_CHUNK, redo.size() - c0);
+        CU(cudaMemcpyAsync(sb.qmap, redo.data() + c0, nc * 4, cudaMemcpyHostToDevice, s));
+        for (uint32_t g0 = 0; g0 < nc; g0 += 4) {  // four queries share one pass over the matrix
+          const uint32_t ng = nc - g0 < 4 ? nc - g0 : 4;
+          cr.keys = sb.retry_keys + (size_t)g0 * pl.cap_retry;
+          CU(launch_stream_scan(st, qv, 0, ng, flt, cr, h->sm_count, s, sb.qmap + g0));
+          h->launches += 1;
+        }
+        cr.keys = sb.retry_keys;
+        CU(launch_select_rescore(st, qv, 0, nc, cr, rv, eps_stream(h->dim), 1, s, sb.qmap));
+        h->launches += 1;
       }
       CU(cudaMemcpyAsync(h_ok, sb.ok, B * 4, cudaMemcpyDeviceToHost, s));
       CU(cudaStreamSynchronize(s));

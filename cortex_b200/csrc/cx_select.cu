@@ -45,6 +45,7 @@ struct SelectParams {
   ResultView rv;         // pointers already offset to the first query of this launch
   float eps;
   int scale_by_rqn;      // pass keys are cosine * |q| (streaming pass) rather than cosine
+  const uint32_t* qmap;  // optional: block i serves query qmap[i] (candidate list slot i)
 };
 
 struct SelectLayout {
@@ -84,13 +85,14 @@ __global__ void __launch_bounds__(SEL_THREADS) select_rescore_kernel(const Selec
   __shared__ uint32_t scratch[260];
   __shared__ uint32_t s_m;
 
-  const uint32_t q = blockIdx.x, tid = threadIdx.x;
+  const uint32_t tid = threadIdx.x;
+  const uint32_t q = p.qmap ? p.qmap[blockIdx.x] : blockIdx.x;  // query index (Q, state, results)
   const uint32_t ld = p.st.ld, dim = p.st.dim;
   const uint32_t n_app = p.cnt[q];
   const unsigned long long gt = p.gtau[q];  // final cut-off: nothing below it can reach the top KP
   const bool overflow = n_app > p.cap;
   const uint32_t n_src = min(n_app, p.cap);
-  const uint64_t* src = p.keys + (size_t)q * p.cap;
+  const uint64_t* src = p.keys + (size_t)blockIdx.x * p.cap;
   if (tid == 0) {
     s_simk = 0.0f;
     s_scorek = 0.0f;
@@ -145,83 +147,109 @@ __global__ void __launch_bounds__(SEL_THREADS) select_rescore_kernel(const Selec
   bitonic_sort_desc(keys, NK, tid, SEL_THREADS, [] { __syncthreads(); });
   __syncthreads();
   const float na = s_na;
-  const uint32_t KS = min(min(M, p.KP), (uint32_t)SEL_MAX_KS);
-  if (M > KS && keys[KS] > U) U = keys[KS];
+  uint32_t KS = min(min(M, p.KP), (uint32_t)SEL_MAX_KS);
 
-  // ---- 2. exact rescore, SEL_BATCH rows per round -------------------------------------
+  // ---- 2. exact rescore of keys[lo, hi), SEL_BATCH rows per round ---------------------
   const uint32_t warp = tid >> 5, lane = tid & 31, nwarps = SEL_THREADS / 32;
   const uint32_t sstride = ld + 1;
-  for (uint32_t base = 0; base < KS; base += SEL_BATCH) {
-    const uint32_t nb = min((uint32_t)SEL_BATCH, KS - base);
-    for (uint32_t j = warp; j < nb; j += nwarps) {
-      const uint32_t row = key_row(keys[base + j]);
-      const float* g = p.st.E + (size_t)row * ld;
-      uint32_t d = lane;
-      for (; d + 7 * 32 < ld; d += 8 * 32) {  // eight loads in flight per lane
-        float x[8];
+  auto rescore = [&](uint32_t lo, uint32_t hi) {
+    for (uint32_t base = lo; base < hi; base += SEL_BATCH) {
+      const uint32_t nb = min((uint32_t)SEL_BATCH, hi - base);
+      for (uint32_t j = warp; j < nb; j += nwarps) {
+        const uint32_t row = key_row(keys[base + j]);
+        const float* g = p.st.E + (size_t)row * ld;
+        uint32_t d = lane;
+        for (; d + 7 * 32 < ld; d += 8 * 32) {  // eight loads in flight per lane
+          float x[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) x[u] = __ldg(g + d + u * 32);
+          for (int u = 0; u < 8; ++u) x[u] = __ldg(g + d + u * 32);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) stage[j * sstride + d + u * 32] = x[u];
-      }
-      for (; d < ld; d += 32) stage[j * sstride + d] = __ldg(g + d);
-    }
-    __syncthreads();
-    if (tid < nb) {
-      const uint32_t row = key_row(keys[base + tid]);
-      const float* r = stage + tid * sstride;
-      const uint32_t n = p.qlen < dim ? p.qlen : dim;
-      float dot = 0.0f;
-      uint32_t d = 0;
-      for (; d + 8 <= n; d += 8) {
-        float a[8], b[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          a[j] = q_s[d + j];
-          b[j] = r[d + j];
+          for (int u = 0; u < 8; ++u) stage[j * sstride + d + u * 32] = x[u];
         }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) dot = ref_fold(dot, a[j], b[j]);
+        for (; d < ld; d += 32) stage[j * sstride + d] = __ldg(g + d);
       }
-      for (; d < n; ++d) dot = ref_fold(dot, q_s[d], r[d]);
-      const float nbm = __ldg(p.st.norm + row);
-      const float sim = __fdiv_rn(dot, __fmul_rn(na, nbm));
-      const float dist = __fsub_rn(1.0f, sim);
-      const float sc = ref_score_from_distance(dist);
-      ekey[base + tid] = make_key(ord_from_score(sc), row);
-      esim[base + tid] = sim;
-      edist[base + tid] = dist;
-      escore[base + tid] = sc;
+      __syncthreads();
+      if (tid < nb) {
+        const uint32_t row = key_row(keys[base + tid]);
+        const float* r = stage + tid * sstride;
+        const uint32_t n = p.qlen < dim ? p.qlen : dim;
+        float dot = 0.0f;
+        uint32_t d = 0;
+        for (; d + 8 <= n; d += 8) {
+          float a[8], b[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            a[j] = q_s[d + j];
+            b[j] = r[d + j];
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dot = ref_fold(dot, a[j], b[j]);
+        }
+        for (; d < n; ++d) dot = ref_fold(dot, q_s[d], r[d]);
+        const float nbm = __ldg(p.st.norm + row);
+        const float sim = __fdiv_rn(dot, __fmul_rn(na, nbm));
+        const float dist = __fsub_rn(1.0f, sim);
+        const float sc = ref_score_from_distance(dist);
+        ekey[base + tid] = make_key(ord_from_score(sc), row);
+        esim[base + tid] = sim;
+        edist[base + tid] = dist;
+        escore[base + tid] = sc;
+      }
+      __syncthreads();
+    }
+  };
+  // rank the first `n_res` rescored rows by exact key (all distinct: the row is part of the
+  // key); remember the k-th; optionally emit the first k
+  const uint32_t k = p.rv.k;
+  auto rank_rows = [&](uint32_t n_res, bool emit) {
+    const uint32_t n_out = min(k, n_res);
+    if (tid < n_res) {
+      const uint64_t mine = ekey[tid];
+      uint32_t rank = 0;
+      for (uint32_t j = 0; j < n_res; ++j) rank += ekey[j] > mine;
+      if (emit && rank < n_out) {
+        const size_t o = (size_t)q * k + rank;
+        const uint32_t row = key_row(mine);
+        p.rv.rows[o] = row;
+        p.rv.score[o] = escore[tid];
+        p.rv.dist[o] = edist[tid];
+        if (p.rv.ids)
+          *reinterpret_cast<uint4*>(p.rv.ids + o * 16) =
+              *reinterpret_cast<const uint4*>(p.st.ids + (size_t)row * 16);
+      }
+      if (rank + 1 == k) {
+        s_simk = esim[tid];
+        s_scorek = escore[tid];
+      }
     }
     __syncthreads();
-  }
+  };
 
-  // ---- 3. order by exact key (all distinct: the row is part of the key), emit the first k
-  const uint32_t k = p.rv.k;
-  const uint32_t n_out = min(k, KS);
-  if (tid < KS) {
-    const uint64_t mine = ekey[tid];
-    uint32_t rank = 0;
-    for (uint32_t j = 0; j < KS; ++j) rank += ekey[j] > mine;
-    if (rank < n_out) {
-      const size_t o = (size_t)q * k + rank;
-      const uint32_t row = key_row(mine);
-      p.rv.rows[o] = row;
-      p.rv.score[o] = escore[tid];
-      p.rv.dist[o] = edist[tid];
-      if (p.rv.ids)
-        *reinterpret_cast<uint4*>(p.rv.ids + o * 16) =
-            *reinterpret_cast<const uint4*>(p.st.ids + (size_t)row * 16);
-    }
-    if (rank + 1 == k) {
-      s_simk = esim[tid];
-      s_scorek = escore[tid];
+  rescore(0, KS);
+  // ---- 3. widen to the whole +-eps band when the list covers it ---------------------------
+  // Every candidate whose approximate cosine is within eps of the current k-th exact cosine
+  // could still belong to the top k.  The list holds all rows down to its cut-off, so if the
+  // band lies above the cut-off, rescoring the band makes the answer exact without a re-scan.
+  if (KS >= k && KS < M && p.eps > 0.0f) {
+    rank_rows(KS, false);
+    const float simk = s_simk;
+    if (simk == simk) {
+      float band = simk - p.eps;                 // cosine units
+      if (p.scale_by_rqn) band = band * na;      // streaming-pass keys are cosine * |q|
+      uint32_t KS1 = KS;
+      while (KS1 < M && KS1 < (uint32_t)SEL_MAX_KS && float_from_ord(key_ord(keys[KS1])) >= band) ++KS1;
+      if (KS1 > KS) {
+        rescore(KS, KS1);
+        KS = KS1;
+      }
     }
   }
-  __syncthreads();
+  if (M > KS && keys[KS] > U) U = keys[KS];
+  rank_rows(KS, true);
+
   // ---- 4. verify ---------------------------------------------------------------------
   if (tid == 0) {
-    p.rv.n[q] = n_out;
+    p.rv.n[q] = min(k, KS);
     bool ok = KS >= k && !overflow && !truncated;
     if (ok) {
       const float sk = s_scorek, simk = s_simk;
@@ -245,9 +273,11 @@ size_t select_smem(uint32_t cap, uint32_t ld) {
 
 cudaError_t launch_select_rescore(const StoreView& st, const QueryView& qv, uint32_t q0, uint32_t nq,
                                   const CandView& cv, const ResultView& rv, float eps_cos, int scale_by_rqn,
-                                  cudaStream_t s) {
+                                  cudaStream_t s, const uint32_t* qmap) {
   if (!nq) return cudaSuccess;
+  if (qmap && q0 != 0) return cudaErrorInvalidValue;  // a query map addresses queries absolutely
   SelectParams p;
+  p.qmap = qmap;
   p.st = st;
   p.Q = qv.Q + (size_t)q0 * qv.ldq;
   p.qnorm = const_cast<float*>(qv.qnorm) + q0;

@@ -44,6 +44,7 @@ struct StreamParams {
   uint32_t* cnt;     // &cand.cnt[q0]       its fill count        (zero before the pass)
   uint64_t* gtau;    // &cand.gtau[q0]      cross-CTA cut-off     (zero before the pass)
   uint32_t cap;
+  const uint32_t* qmap;  // optional: pass-local query b is query qmap[b] (Q row, cnt, gtau); its list slot stays b
   uint32_t G, KP, C, n_tiles, stages, kslice, n_slices;
 };
 
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) stream_scan_kernel(const Stream
   }
   for (uint32_t i = tid; i < NQ * ld; i += SC_THREADS) {
     uint32_t b = i / ld, d = i % ld;
-    q_s[i] = (b < p.nq_valid) ? p.Q[(size_t)b * p.ldq + d] : 0.0f;
+    q_s[i] = (b < p.nq_valid) ? p.Q[(size_t)(p.qmap ? p.qmap[b] : b) * p.ldq + d] : 0.0f;
   }
   for (uint32_t i = tid; i < NQ; i += SC_THREADS) {
     tau_s[i] = 0;
@@ -199,6 +200,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) stream_scan_kernel(const Stream
   const uint32_t C = p.C, KP = p.KP;
 
   auto csync = [] { named_bar_sync(1, SC_CT); };
+  auto gq = [&](uint32_t b) { return (p.qmap && b < p.nq_valid) ? p.qmap[b] : b; };  // state index of pass-local b
 
   // Keep the KP best of list[b] (rank by counting; keys are distinct), sorted, in the
   // other half of the double buffer; publish / adopt the global cut-off.
@@ -220,7 +222,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) stream_scan_kernel(const Stream
       cur_s[b] = cur ^ 1;
       if (n >= KP) {
         uint64_t t = dst[KP - 1];
-        const uint64_t g = atomicMax(reinterpret_cast<unsigned long long*>(p.gtau + b), (unsigned long long)t);
+        const uint64_t g = atomicMax(reinterpret_cast<unsigned long long*>(p.gtau + gq(b)), (unsigned long long)t);
         if (g > t) t = g;
         if (t > tau_s[b]) tau_s[b] = t;
       }
@@ -317,7 +319,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) stream_scan_kernel(const Stream
     if ((i % SC_QUAD) == (SC_QUAD - SC_GROUPS + grp) && (i / SC_QUAD) < n_quads) {
       csync();
       if (ctid < NQ) {
-        const uint64_t g = *((volatile uint64_t*)(p.gtau + ctid));
+        const uint64_t g = *((volatile uint64_t*)(p.gtau + gq(ctid)));
         if (g > tau_s[ctid]) tau_s[ctid] = g;
       }
       if (ctid == 0) {
@@ -342,11 +344,11 @@ __global__ void __launch_bounds__(SC_THREADS, 1) stream_scan_kernel(const Stream
     const uint64_t* Lb = list_s + ((size_t)b * 2 + cur_s[b]) * C;
     const uint32_t n_keep = cnt_s[b];
     if (ctid == 0) {
-      const uint64_t g = *((volatile uint64_t*)(p.gtau + b));
+      const uint64_t g = *((volatile uint64_t*)(p.gtau + gq(b)));
       uint32_t m = 0;
       while (m < n_keep && Lb[m] >= g) ++m;  // sorted descending: a prefix survives
       flag_s[1] = m;
-      flag_s[2] = m ? atomicAdd(p.cnt + b, m) : 0;
+      flag_s[2] = m ? atomicAdd(p.cnt + gq(b), m) : 0;
     }
     csync();
     const uint32_t m = flag_s[1], base = flag_s[2];
@@ -422,8 +424,10 @@ static cudaError_t launch_nq(const StreamParams& p, size_t smem, cudaStream_t s)
 }
 
 cudaError_t launch_stream_scan(const StoreView& st, const QueryView& qv, uint32_t q0, uint32_t nq_pass,
-                               const DevFilter& flt, const CandView& cv, int sm_count, cudaStream_t s) {
+                               const DevFilter& flt, const CandView& cv, int sm_count, cudaStream_t s,
+                               const uint32_t* qmap) {
   if (!st.n_rows || !nq_pass) return cudaSuccess;
+  if (qmap && q0 != 0) return cudaErrorInvalidValue;
   if (nq_pass > 8) return cudaErrorInvalidValue;
   const uint32_t nq_t = nq_pass <= 1 ? 1 : nq_pass <= 2 ? 2 : nq_pass <= 4 ? 4 : 8;
   StreamParams p;
@@ -435,6 +439,7 @@ cudaError_t launch_stream_scan(const StoreView& st, const QueryView& qv, uint32_
   p.G = cv.G;
   p.KP = cv.KP;
   p.cap = cv.cap;
+  p.qmap = qmap;
   p.keys = cv.keys + (size_t)(q0 - cv.q_base) * cv.cap;
   p.cnt = cv.cnt + q0;
   p.gtau = cv.gtau + q0;
