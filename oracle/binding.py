@@ -236,3 +236,43 @@ class OracleIndex:
 
 def max_threads() -> int:
     return int(lib().cxo_max_threads())
+
+
+class OracleHnsw:
+    """The HNSW branch of HnswIndex::search (index.rs:342-373) restated on the CPU
+    (oracle/hnsw_oracle.c): PARITY UNPINNED, parameters unverified -- used only to report
+    the reference's approximate path as recall@k against the exact scan."""
+
+    def __init__(self, vectors: np.ndarray, M: int = 32, ef_construction: int = 100, ef_search: int = 100,
+                 seed: int = 1):
+        L = lib()
+        L.cxo_hnsw_build.restype = C.c_void_p
+        L.cxo_hnsw_build.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_uint64]
+        L.cxo_hnsw_search.restype = C.c_size_t
+        L.cxo_hnsw_search.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
+        L.cxo_hnsw_distance_evals.restype = C.c_uint64
+        L.cxo_hnsw_distance_evals.argtypes = [C.c_void_p]
+        L.cxo_hnsw_free.argtypes = [C.c_void_p]
+        self._L = L
+        self._v = np.ascontiguousarray(vectors, dtype=np.float32)  # borrowed by the C side
+        self.ef_search = ef_search
+        self._h = L.cxo_hnsw_build(self._v.ctypes.data, self._v.shape[0], self._v.shape[1], M, ef_construction,
+                                   ef_search, seed)
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.cxo_hnsw_free(self._h)
+            self._h = None
+
+    def search(self, query, k: int):
+        """index.rs:345-371 without a filter: take(k*10) of the ascending results, first k."""
+        q = np.ascontiguousarray(query, dtype=np.float32)
+        m = min(self.ef_search, k * 10)
+        ids = np.zeros(m, np.uint32)
+        d = np.zeros(m, np.float32)
+        n = self._L.cxo_hnsw_search(self._h, q.ctypes.data, m, ids.ctypes.data, d.ctypes.data)
+        n = min(n, k)
+        return ids[:n], d[:n]
+
+    def distance_evals(self) -> int:
+        return int(self._L.cxo_hnsw_distance_evals(self._h))
