@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--cpu-queries", type=int, default=0, help="queries per CPU-baseline step (0 = one per thread)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], metavar="KEY=INT",
+                    help="cx_set_option before the run (A/B measurements), e.g. --opt tensor_pair=0")
     return ap.parse_args()
 
 
@@ -248,6 +250,9 @@ def main():
     del corpus
     torch.cuda.empty_cache()
     ix.set_option("profile", 1)
+    for kv in a.opt:
+        key, val = kv.split("=")
+        ix.set_option(key, int(val))
 
     stream = torch.cuda.current_stream()
     out = None

@@ -577,6 +577,19 @@ extern "C" cx_status cx_set_option(cx_index* h, const char* key, int64_t value) 
     h->profile = value != 0;
     return CX_OK;
   }
+  if (!strcmp(key, "tensor_pair")) {  // 0 = single-CTA tcgen05 form only (A/B measurements); process-wide
+    tensor_set_pair(value != 0);
+    return CX_OK;
+  }
+  if (!strcmp(key, "tensor_phase_growth")) {
+    if (value < 0 || value > 1024) return fail(CX_ERR_VALIDATION, "tensor_phase_growth must be 0..1024");
+    h->tensor_phase_growth = (uint32_t)value;
+    return CX_OK;
+  }
+  if (!strcmp(key, "tensor_debug")) {  // measurement hook: results of the tensor pass become wrong
+    tensor_set_debug((int)value);
+    return CX_OK;
+  }
   if (!strcmp(key, "tensor_min_batch")) {
     if (value < 1) return fail(CX_ERR_VALIDATION, "tensor_min_batch must be >= 1");
     h->tensor_min_batch = (uint32_t)value;

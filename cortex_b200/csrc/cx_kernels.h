@@ -80,7 +80,8 @@ cudaError_t launch_select_rescore(const StoreView& st, const QueryView& qv, uint
 // cv.KP must be tensor_keep(k) (32 / 64 / 128 scores tracked per query in registers).
 uint32_t tensor_keep(uint32_t k);
 bool tensor_scan_eligible(uint32_t ld16, uint32_t k);
-void tensor_scan_shape(uint32_t nq, int sm_count, uint32_t* n_qt, uint32_t* n_es);
+void tensor_set_debug(int mode);  // measurement hook (wrong results): 1 = no epilogue work, 2 = no hit handling
+void tensor_set_pair(int on);  // test hook: 0 = never use the CTA-pair (cta_group::2) form
 size_t tensor_scratch_bytes(int sm_count);
 void launch_query_bf16(const float* Q, uint32_t ldq, uint32_t dim, uint32_t nq, uint32_t nq_pad, void* Q16,
                        uint32_t ld16, cudaStream_t s);
@@ -90,10 +91,14 @@ uint32_t tensor_sample_tiles(uint32_t n_rows, uint32_t nq);
 cudaError_t launch_tensor_bootstrap(const StoreView& st, const void* Q16, uint32_t q0, uint32_t nq,
                                     const DevFilter& flt, bool check_rows, const CandView& cv, float* dump,
                                     uint32_t n_slots, int sm_count, cudaStream_t s);
+// One phase of the scan: row tiles [tile0, tile0 + n_tiles) of tensor_tiles(n_rows) (256 rows each).
 // check_rows: a filter is active or rows were removed -> test metadata before nominating a row
 cudaError_t launch_tensor_scan(const StoreView& st, const void* Q16, uint32_t q0, uint32_t nq,
                                const DevFilter& flt, bool check_rows, const CandView& cv, uint64_t* lists,
-                               int sm_count, cudaStream_t s);
+                               uint32_t tile0, uint32_t n_tiles, int sm_count, cudaStream_t s);
+uint32_t tensor_tiles(uint32_t n_rows);
+// Between phases: raise each query's cut-off to the cv.KP-th best key nominated so far.
+cudaError_t launch_tau_refine(const CandView& cv, uint32_t q0, uint32_t nq, cudaStream_t s);
 
 // Exact path: every row scored with reference arithmetic -> keys[n_rows] for one query
 void launch_exact_keys(const StoreView& st, const QueryView& qv, uint32_t q, const DevFilter& flt,

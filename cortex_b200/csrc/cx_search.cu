@@ -12,6 +12,7 @@
 // Whatever the path, emitted scores/distances come from the reference's operation
 // sequence, and ids follow (score desc, NaN last, row asc).
 #include <algorithm>
+#include <vector>
 
 #include "cx_index.h"
 
@@ -131,14 +132,36 @@ struct SearchBufs {
 // the sum by the product of the norms), plus fp32 accumulation and normalisation slack.
 float eps_tensor(uint32_t dim) { return 0.00390625f * 1.02f + ((float)dim + 32.0f) * 1.1920929e-7f; }
 
+// Phases of one tensor-pass scan, as tile counts.  The cut-off a phase works with comes from
+// everything scanned before it (first the bootstrap sample of S tiles), so a phase of R tiles
+// nominates about KP * R / S_before rows per query; growing the phases geometrically keeps
+// that at `growth` * KP per phase (instead of KP * n_tiles / S for a single phase).
+std::vector<uint32_t> tensor_phases(uint32_t n_tiles, uint32_t sample_tiles, uint32_t growth, double* hits_per_kp) {
+  std::vector<uint32_t> ph;
+  double hits = 0.0;
+  uint32_t done = 0, seen = sample_tiles ? sample_tiles : 1;
+  while (done < n_tiles) {
+    uint32_t left = n_tiles - done;
+    uint64_t want = growth >= 2 ? (uint64_t)growth * seen : left;
+    uint32_t take = (want * 2 >= left) ? left : (uint32_t)want;
+    ph.push_back(take);
+    hits += (double)take / (double)seen;
+    done += take;
+    seen = done;
+  }
+  if (hits_per_kp) *hits_per_kp = hits;
+  return ph;
+}
+
 struct Plan {
   uint64_t B;
   uint32_t qlen, ldq, kd;
   uint32_t G, KP;     // streaming pass: producer groups, keys kept per group
+  uint32_t KP_wide;   // ... and the wide keep count of the last retry tier (0 = no such tier)
   uint32_t KPt;       // tensor pass: keys kept per query (32 / 64 / 128)
   uint32_t n_slots;   // tensor pass: sampled row tiles for the cut-off bootstrap
   uint32_t cap;       // merged-list capacity per query for the primary pass
-  uint32_t cap_retry; // ... and for streaming retries of single queries after a tensor pass
+  uint32_t cap_retry; // ... and for the streaming retries of unverified queries (widest tier)
   uint32_t q_per_launch;  // tensor pass: queries per launch
   bool fast;          // a nominate + rescore pass is usable for this call
   bool tensor;        // ... and it is the tcgen05 pass (else the streaming pass)
@@ -162,19 +185,26 @@ Plan make_plan(const cx_index* h, uint64_t B, uint32_t qlen, uint32_t ldq, uint3
   p.tensor = false;
   p.KPt = 0;
   p.n_slots = 0;
+  p.KP_wide = 0;
+  if (p.fast) {
+    uint32_t w = 4 * p.KP;
+    if (w > 256) w = 256;  // the select kernel rescans at most 256 rows
+    while (w > p.KP && ((uint64_t)w * p.G > 16384 || stream_scan_smem(h->ld, 4, w) == 0)) w -= 2;
+    if (w > p.KP) p.KP_wide = w;
+    p.cap_retry = p.G * (p.KP_wide ? p.KP_wide : p.KP);
+  }
   if (p.fast && h->dE16 && h->force_path != PATH_STREAM &&
       (B >= h->tensor_min_batch || h->force_path == PATH_TENSOR) && tensor_scan_eligible(h->ld16, kd)) {
     p.tensor = true;
     p.KPt = tensor_keep(kd);
     p.q_per_launch = (uint32_t)h->sm_count * 128u;
-    uint32_t n_qt, n_es;
-    tensor_scan_shape((uint32_t)(B < p.q_per_launch ? B : p.q_per_launch), h->sm_count, &n_qt, &n_es);
-    p.cap_retry = p.cap;
     // the cut-off comes from a sample of S rows, so about KPt * rows / S keys per query clear it;
     // twice that plus slack (excess is detected by the select kernel and sent to a fallback,
     // never lost silently)
     p.n_slots = tensor_sample_tiles(n_rows, (uint32_t)(B < p.q_per_launch ? B : p.q_per_launch));
-    const uint64_t expected = (uint64_t)p.KPt * n_rows / ((uint64_t)p.n_slots * 256);
+    double hits_per_kp = 0.0;
+    tensor_phases(tensor_tiles(n_rows), p.n_slots, h->tensor_phase_growth, &hits_per_kp);
+    const uint64_t expected = (uint64_t)((double)p.KPt * hits_per_kp) + 1;
     uint64_t cap = 2 * expected + 4 * p.KPt + 64;
     if (cap > 16384) cap = 16384;
     p.cap = (uint32_t)cap;
@@ -191,11 +221,14 @@ size_t carve_bufs(void* base, const cx_index* h, const Plan& pl, uint32_t n_excl
   sb->rqnorm = c.take<float>(pl.B);
   sb->excl = c.take<uint32_t>(n_excl + 1);
   sb->cand_keys = pl.fast ? c.take<uint64_t>((size_t)pl.B * pl.cap) : nullptr;
+  if (pl.fast) {
+    const uint64_t chunk = pl.B < RETRY_CHUNK ? pl.B : RETRY_CHUNK;
+    sb->retry_keys = c.take<uint64_t>((size_t)chunk * pl.cap_retry);
+    sb->qmap = c.take<uint32_t>(RETRY_CHUNK);
+  }
   if (pl.tensor) {
     sb->q16 = c.take<uint16_t>(align_up(pl.B, 128) * h->ld16);
     sb->lists = (uint64_t*)c.take<char>(tensor_scratch_bytes(h->sm_count));
-    sb->retry_keys = c.take<uint64_t>((size_t)RETRY_CHUNK * pl.cap_retry);
-    sb->qmap = c.take<uint32_t>(RETRY_CHUNK);
     const uint64_t nq_launch = pl.B < pl.q_per_launch ? pl.B : pl.q_per_launch;
     sb->dump = c.take<float>(nq_launch * pl.n_slots * 256);
   }
@@ -282,10 +315,22 @@ cx_status run_search(cx_index* h, Workspace* ws, const FilterHost& fh, const Sea
         h->launches += 2;
       }
       if (h->profile) CU(cudaEventRecord(ws->ev0, s));
+      const std::vector<uint32_t> phases =
+          tensor_phases(tensor_tiles(st.n_rows), pl.n_slots, h->tensor_phase_growth, nullptr);
       for (uint64_t q0 = 0; q0 < B; q0 += pl.q_per_launch) {
         const uint32_t nq = (uint32_t)(B - q0 < pl.q_per_launch ? B - q0 : pl.q_per_launch);
-        CU(launch_tensor_scan(st, sb.q16, (uint32_t)q0, nq, flt, check_rows, cv, sb.lists, h->sm_count, s));
-        ++n_pass;
+        uint32_t tile0 = 0;
+        for (size_t ph = 0; ph < phases.size(); ++ph) {
+          if (ph) {  // tighten the cut-off with what the earlier phases found
+            CU(launch_tau_refine(cv, (uint32_t)q0, nq, s));
+            h->launches += 1;
+          }
+          CU(launch_tensor_scan(st, sb.q16, (uint32_t)q0, nq, flt, check_rows, cv, sb.lists, tile0, phases[ph],
+                                h->sm_count, s));
+          tile0 += phases[ph];
+          h->launches += 1;
+        }
+        ++n_pass;  // one scan of the whole shard (all of its phases)
       }
     } else {
       if (h->profile) CU(cudaEventRecord(ws->ev0, s));
@@ -298,7 +343,7 @@ cx_status run_search(cx_index* h, Workspace* ws, const FilterHost& fh, const Sea
     if (h->profile) CU(cudaEventRecord(ws->ev1, s));
     CU(launch_select_rescore(st, qv, 0, (uint32_t)B, cv, rv, pl.tensor ? eps_tensor(h->dim) : eps_stream(h->dim),
                              /*scale_by_rqn=*/pl.tensor ? 0 : 1, s));
-    h->launches += n_pass + 1;
+    h->launches += (pl.tensor ? 0 : n_pass) + 1;
     if (h_block) {
       CU(cudaMemcpyAsync(h_block, sb.res, rb.total, cudaMemcpyDeviceToHost, s));
       h_ok = (uint32_t*)(h_block + rb.ok);
@@ -316,21 +361,27 @@ cx_status run_search(cx_index* h, Workspace* ws, const FilterHost& fh, const Sea
       if (!h_ok[b]) redo.push_back((uint32_t)b);
     (pl.tensor ? h->q_tensor : h->q_stream) += B - redo.size();
     h->fallbacks += redo.size();
-    if (pl.tensor && !redo.empty()) {
-      // second tier: queries the bf16 pass could not verify go through the fp32 streaming
-      // pass one at a time (its error bound is ~100x tighter); only what still fails after
-      // that is left to the exact path
+    // Retry ladder for queries the primary pass could not verify: the fp32 streaming pass
+    // (error bound ~100x tighter than the bf16 pass), four queries per pass over the matrix,
+    // first with the normal keep count, then with a wide one (near-ties around rank k need
+    // more rescored rows, not a different algorithm).  What still fails goes to the exact path.
+    const uint32_t ladder[2] = {pl.tensor ? pl.KP : 0u, pl.KP_wide > pl.KP ? pl.KP_wide : 0u};
+    bool retried = false;
+    for (int tier = 0; tier < 2 && !redo.empty(); ++tier) {
+      const uint32_t KPr = ladder[tier];
+      if (!KPr) continue;
+      retried = true;
       CandView cr = cv;
-      cr.cap = pl.cap_retry;
+      cr.cap = pl.G * KPr;
       cr.G = pl.G;
-      cr.KP = pl.KP;
+      cr.KP = KPr;
       cr.q_base = 0;
       for (size_t c0 = 0; c0 < redo.size(); c0 += RETRY_CHUNK) {
         const uint32_t nc = (uint32_t)std::min<size_t>(RETRY_CHUNK, redo.size() - c0);
         CU(cudaMemcpyAsync(sb.qmap, redo.data() + c0, nc * 4, cudaMemcpyHostToDevice, s));
-        for (uint32_t g0 = 0; g0 < nc; g0 += 4) {  // four queries share one pass over the matrix
+        for (uint32_t g0 = 0; g0 < nc; g0 += 4) {
           const uint32_t ng = nc - g0 < 4 ? nc - g0 : 4;
-          cr.keys = sb.retry_keys + (size_t)g0 * pl.cap_retry;
+          cr.keys = sb.retry_keys + (size_t)g0 * cr.cap;
           CU(launch_stream_scan(st, qv, 0, ng, flt, cr, h->sm_count, s, sb.qmap + g0));
           h->launches += 1;
         }
@@ -345,8 +396,10 @@ cx_status run_search(cx_index* h, Workspace* ws, const FilterHost& fh, const Sea
         if (!h_ok[b]) still.push_back(b);
       h->q_stream += redo.size() - still.size();
       redo.swap(still);
-      if (redo.empty() && h_block) CU(cudaMemcpyAsync(h_block, sb.res, rb.total, cudaMemcpyDeviceToHost, s));
-      if (redo.empty()) CU(cudaStreamSynchronize(s));
+    }
+    if (retried && redo.empty()) {
+      if (h_block) CU(cudaMemcpyAsync(h_block, sb.res, rb.total, cudaMemcpyDeviceToHost, s));
+      CU(cudaStreamSynchronize(s));
     }
     ws->state_dirty = false;
     if (redo.empty()) return CX_OK;

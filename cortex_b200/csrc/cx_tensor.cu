@@ -43,8 +43,10 @@ constexpr uint32_t TC_BK = 64;        // bf16 per K chunk = one 128 B swizzle at
 constexpr uint32_t TC_UK = 16;        // K of one tcgen05.mma for 16-bit inputs
 constexpr uint32_t TC_THREADS = 384;      // 4 control warps + 8 epilogue warps
 constexpr uint32_t TC_QCHUNK_BYTES = TC_BM * TC_BK * 2;  // 16 KB
-constexpr uint32_t TC_ESTAGE_BYTES = TC_BN * TC_BK * 2;  // 32 KB
-constexpr uint32_t TC_MAX_STAGES = 6;
+constexpr uint32_t TC_MAX_STAGES = 8;
+// bytes of one ring stage per CTA: the whole [256 x 64] bf16 box, or -- for a CTA pair, where
+// each CTA stages half of the rows and the pair's MMA reads both halves -- [128 x 64]
+__host__ __device__ constexpr uint32_t tc_stage_bytes(bool pair) { return (pair ? TC_BN / 2 : TC_BN) * TC_BK * 2; }
 constexpr uint32_t TC_SMEM_LIMIT = 227 * 1024;
 constexpr uint32_t TC_TMEM_COLS = 512;
 constexpr uint32_t TC_NPL = 16;                 // list entries per lane in a cooperative sort
@@ -54,12 +56,15 @@ enum { TC_MODE_SCAN = 0, TC_MODE_DUMP = 1 };
 
 struct TensorParams {
   uint32_t n_rows, n_tiles, n_kc;
-  uint32_t n_slots;     // tiles visited: n_tiles in SCAN mode, the sample size in DUMP mode
+  uint32_t n_slots;     // tiles visited: a contiguous tile range in SCAN mode, the sample size in DUMP mode
+  uint32_t tile0;       // SCAN mode: first tile of this launch's range
   uint32_t n_qt, n_es;
   uint32_t nq_valid;
   uint32_t stages;
   uint32_t mode;
   uint32_t check_rows;  // 0: no filter and no removed rows -> skip the per-row metadata test
+  uint32_t debug;       // measurement hook (results become wrong): 1 = epilogue only releases the
+                        // accumulator, 2 = epilogue loads and masks but never handles a hit
   uint32_t KP;
   const uint32_t* meta;
   const uint32_t* agent;
@@ -79,6 +84,30 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// CTA-pair form: the mbarrier may live in the peer CTA (a shared::cluster address)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// shared::cta address -> shared::cluster address of the same location in CTA `rank`
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
@@ -87,6 +116,31 @@ __device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols) {
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// pair forms: executed by the same warp of both CTAs
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// M=256 over the pair (128 queries per CTA) x N=256 (128 rows staged by each CTA); leader CTA only
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at the same offset in both CTAs of the pair when the MMAs retire
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+      "h"((uint16_t)3)
+      : "memory");
 }
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
@@ -132,6 +186,7 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 // kind::f16 instruction descriptor: D=f32 (bit 4), A=B=bf16 (bits 7, 10), both K-major,
 // N >> 3 at bit 17, M >> 4 at bit 24.
 constexpr uint32_t TC_IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((TC_BN >> 3) << 17) | ((TC_BM >> 4) << 24);
+constexpr uint32_t TC_IDESC_PAIR = (1u << 4) | (1u << 7) | (1u << 10) | ((TC_BN >> 3) << 17) | (((2 * TC_BM) >> 4) << 24);
 
 // v[j] for a run-time j without spilling v to local memory: 31 selects
 __device__ __forceinline__ float pick32(const float (&v)[32], uint32_t j) {
@@ -203,14 +258,22 @@ __device__ __noinline__ uint64_t warp_compact(uint64_t* L, uint32_t n, uint32_t 
   return n >= KP ? kth : 0ull;
 }
 
+// PAIR = two CTAs of a cluster (one TPC) work as one tcgen05 cta_group::2 unit: each holds
+// its own 128-query tile (the pair's M = 256) and stages HALF of every [256 x 64] box of E;
+// the leader CTA issues the MMAs, which read both halves.  Per SM that halves the L2->SM
+// traffic and the shared-memory reads of the E operand (the binding limits of the
+// single-CTA form: 64 B/clk of TMA writes + 96 B/clk of MMA operand reads against
+// 128 B/clk of shared-memory bandwidth).
+template <bool PAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmE,
                    const TensorParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
+  constexpr uint32_t STAGE_BYTES = tc_stage_bytes(PAIR);
   const uint32_t S = p.stages;
   unsigned char* sQ = smem;
   unsigned char* sE = smem + (size_t)p.n_kc * TC_QCHUNK_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sE + (size_t)S * TC_ESTAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sE + (size_t)S * STAGE_BYTES);
   const uint32_t bar_q = smem_u32(bars);
   const uint32_t bar_full = smem_u32(bars + 1);
   const uint32_t bar_empty = smem_u32(bars + 1 + TC_MAX_STAGES);
@@ -219,6 +282,8 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 5 + 2 * TC_MAX_STAGES);
 
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;   // 0 = leader
+  const uint32_t unit = PAIR ? blockIdx.x >> 1 : blockIdx.x;  // CTA or CTA pair
 
   if (tid == 0) {
     mbar_init(bar_q, 1);
@@ -228,45 +293,74 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     for (uint32_t a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, 8);
+      mbar_init(bar_tempty + 8 * a, PAIR ? 16 : 8);  // epilogue warps (of both CTAs) that drain an accumulator
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc(smem_u32(tmem_ptr_s), TC_TMEM_COLS);
+  if (warp == 2) {
+    if (PAIR) tmem_alloc_pair(smem_u32(tmem_ptr_s), TC_TMEM_COLS);
+    else tmem_alloc(smem_u32(tmem_ptr_s), TC_TMEM_COLS);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();  // the peer's barriers must exist before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
 
-  // this CTA: query tile qt, slots [s_begin, s_end); slot -> tile is the identity in SCAN
-  // mode and a stride over the whole corpus in DUMP mode
-  const uint32_t qt = blockIdx.x % p.n_qt, es = blockIdx.x / p.n_qt;
+  // this unit: query tile group g, slots [s_begin, s_end); slot -> tile is the identity in
+  // SCAN mode and a stride over the whole corpus in DUMP mode
+  const uint32_t g = unit % p.n_qt, es = unit / p.n_qt;
+  const uint32_t qt = PAIR ? 2 * g + rank : g;
   const uint32_t s_begin = (uint32_t)(((uint64_t)es * p.n_slots) / p.n_es);
   const uint32_t s_end = (uint32_t)(((uint64_t)(es + 1) * p.n_slots) / p.n_es);
   const uint32_t n_my = s_end - s_begin;
-  auto tile_of = [&](uint32_t slot) { return (uint32_t)(((uint64_t)slot * p.n_tiles) / p.n_slots); };
+  auto tile_of = [&](uint32_t slot) {
+    return p.mode == TC_MODE_SCAN ? p.tile0 + slot : (uint32_t)(((uint64_t)slot * p.n_tiles) / p.n_slots);
+  };
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0 && n_my) {
-      mbar_arrive_expect_tx(bar_q, p.n_kc * TC_QCHUNK_BYTES);
-      for (uint32_t kc = 0; kc < p.n_kc; ++kc)
-        tma_load_2d(smem_u32(sQ + (size_t)kc * TC_QCHUNK_BYTES), &tmQ, (int)(kc * TC_BK), (int)(qt * TC_BM), bar_q);
-      uint32_t it = 0;
-      for (uint32_t ti = 0; ti < n_my; ++ti) {
-        const int row0 = (int)(tile_of(s_begin + ti) * TC_BN);
-        for (uint32_t kc = 0; kc < p.n_kc; ++kc, ++it) {
-          const uint32_t stage = it % S;
-          if (it >= S) mbar_wait(bar_empty + 8 * stage, ((it / S) - 1) & 1);
-          mbar_arrive_expect_tx(bar_full + 8 * stage, TC_ESTAGE_BYTES);
-          tma_load_2d(smem_u32(sE + (size_t)stage * TC_ESTAGE_BYTES), &tmE, (int)(kc * TC_BK), row0,
-                      bar_full + 8 * stage);
+      if (!PAIR) {
+        mbar_arrive_expect_tx(bar_q, p.n_kc * TC_QCHUNK_BYTES);
+        for (uint32_t kc = 0; kc < p.n_kc; ++kc)
+          tma_load_2d(smem_u32(sQ + (size_t)kc * TC_QCHUNK_BYTES), &tmQ, (int)(kc * TC_BK), (int)(qt * TC_BM), bar_q);
+        uint32_t it = 0;
+        for (uint32_t ti = 0; ti < n_my; ++ti) {
+          const int row0 = (int)(tile_of(s_begin + ti) * TC_BN);
+          for (uint32_t kc = 0; kc < p.n_kc; ++kc, ++it) {
+            const uint32_t stage = it % S;
+            if (it >= S) mbar_wait(bar_empty + 8 * stage, ((it / S) - 1) & 1);
+            mbar_arrive_expect_tx(bar_full + 8 * stage, STAGE_BYTES);
+            tma_load_2d(smem_u32(sE + (size_t)stage * STAGE_BYTES), &tmE, (int)(kc * TC_BK), row0,
+                        bar_full + 8 * stage);
+          }
+        }
+      } else {
+        // both CTAs load; every transfer completes on the LEADER's barrier, which the leader
+        // arms with the bytes of both halves.  A CTA reuses a stage when its own empty barrier
+        // (signalled in both CTAs by the leader's commit) says the MMAs that read it retired.
+        const uint32_t l_bar_q = mapa_u32(bar_q, 0);
+        if (rank == 0) mbar_arrive_expect_tx(bar_q, 2 * p.n_kc * TC_QCHUNK_BYTES);
+        for (uint32_t kc = 0; kc < p.n_kc; ++kc)
+          tma_load_2d_pair(smem_u32(sQ + (size_t)kc * TC_QCHUNK_BYTES), &tmQ, (int)(kc * TC_BK), (int)(qt * TC_BM),
+                           l_bar_q);
+        uint32_t it = 0;
+        for (uint32_t ti = 0; ti < n_my; ++ti) {
+          const int row0 = (int)(tile_of(s_begin + ti) * TC_BN + rank * (TC_BN / 2));
+          for (uint32_t kc = 0; kc < p.n_kc; ++kc, ++it) {
+            const uint32_t stage = it % S;
+            if (it >= S) mbar_wait(bar_empty + 8 * stage, ((it / S) - 1) & 1);
+            if (rank == 0) mbar_arrive_expect_tx(bar_full + 8 * stage, 2 * STAGE_BYTES);
+            tma_load_2d_pair(smem_u32(sE + (size_t)stage * STAGE_BYTES), &tmE, (int)(kc * TC_BK), row0,
+                             mapa_u32(bar_full + 8 * stage, 0));
+          }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------ MMA issuer --------------------------------
-    if (lane == 0 && n_my) {
+    // ------------------------------ MMA issuer (leader CTA of a pair) ----------
+    if (lane == 0 && n_my && rank == 0) {
       mbar_wait(bar_q, 0);
       tc_fence_after();
       uint32_t it = 0;
@@ -280,15 +374,20 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           mbar_wait(bar_full + 8 * stage, (it / S) & 1);
           tc_fence_after();
           const uint64_t adesc = make_sw128_desc(smem_u32(sQ + (size_t)kc * TC_QCHUNK_BYTES));
-          const uint64_t bdesc = make_sw128_desc(smem_u32(sE + (size_t)stage * TC_ESTAGE_BYTES));
+          const uint64_t bdesc = make_sw128_desc(smem_u32(sE + (size_t)stage * STAGE_BYTES));
 #pragma unroll
           for (uint32_t k = 0; k < TC_BK / TC_UK; ++k) {
             // advance 16 bf16 = 32 B inside the swizzle atom: +2 in the (addr >> 4) field
-            umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, TC_IDESC, (kc | k) != 0 ? 1u : 0u);
+            if (PAIR) umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, TC_IDESC_PAIR, (kc | k) != 0 ? 1u : 0u);
+            else umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, TC_IDESC, (kc | k) != 0 ? 1u : 0u);
           }
-          umma_commit(bar_empty + 8 * stage);  // frees the smem stage when these MMAs retire
+          // frees the smem stage (in both CTAs) when these MMAs retire
+          if (PAIR) umma_commit_pair(bar_empty + 8 * stage);
+          else umma_commit(bar_empty + 8 * stage);
         }
-        umma_commit(bar_tfull + 8 * acc);  // accumulator complete
+        // accumulator complete (in both CTAs' TMEM)
+        if (PAIR) umma_commit_pair(bar_tfull + 8 * acc);
+        else umma_commit(bar_tfull + 8 * acc);
       }
     }
   } else if (warp >= 4) {
@@ -298,6 +397,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint32_t q = qt * TC_BM + ew * 32 + lane;
     const bool valid = q < p.nq_valid;
     const uint32_t list_slot = blockIdx.x * (2 * TC_BM) + (warp - 4) * 32;
+    const uint32_t l_bar_tempty = PAIR ? mapa_u32(bar_tempty, 0) : bar_tempty;  // the MMA issuer's barrier
     uint64_t* myL = p.lists + ((size_t)list_slot + lane) * TC_LIST_CAP;
     uint32_t cnt = 0;
     uint64_t tau_key = 0ull;
@@ -314,6 +414,15 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_wait(bar_tfull + 8 * acc, use & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((ew * 32u) << 16) + acc * TC_BN;
+      if (p.debug == 1) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (PAIR) mbar_arrive_cluster(l_bar_tempty + 8 * acc);
+          else mbar_arrive(bar_tempty + 8 * acc);
+        }
+        continue;
+      }
 #pragma unroll 1
       for (uint32_t c = 0; c < CH_PER_WARP; ++c) {
         const uint32_t ch = half * CH_PER_WARP + c;
@@ -322,7 +431,10 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         if (c == CH_PER_WARP - 1) {  // this warp's share of the accumulator is drained
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+          if (lane == 0) {
+            if (PAIR) mbar_arrive_cluster(l_bar_tempty + 8 * acc);
+            else mbar_arrive(bar_tempty + 8 * acc);
+          }
         }
         const uint32_t r0 = row_base + ch * 32;
         if (p.mode == TC_MODE_DUMP) {
@@ -348,6 +460,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         uint32_t m = 0;
 #pragma unroll
         for (int j = 0; j < 32; ++j) m |= (v[j] >= tau ? 1u : 0u) << j;
+        if (p.debug == 2) m = 0;
         if (__any_sync(0xffffffffu, m != 0)) {
           // make room first: a chunk can append up to 32 keys
           uint32_t full = __ballot_sync(0xffffffffu, cnt + 32 > TC_LIST_CAP);
@@ -401,10 +514,12 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();  // neither CTA may leave (or free TMEM) while the other still uses it
+  else __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TC_TMEM_COLS);
+    if (PAIR) tmem_dealloc_pair(tmem_base, TC_TMEM_COLS);
+    else tmem_dealloc(tmem_base, TC_TMEM_COLS);
   }
 }
 
@@ -482,10 +597,10 @@ static bool encode_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-static uint32_t tensor_stages(uint32_t n_kc, size_t* total) {
+static uint32_t tensor_stages(uint32_t n_kc, bool pair, size_t* total) {
   const size_t fixed = (size_t)n_kc * TC_QCHUNK_BYTES + (6 + 2 * TC_MAX_STAGES) * 8 + 64;
   for (uint32_t s = TC_MAX_STAGES; s >= 2; --s) {
-    size_t t = fixed + (size_t)s * TC_ESTAGE_BYTES;
+    size_t t = fixed + (size_t)s * tc_stage_bytes(pair);
     if (t <= TC_SMEM_LIMIT) {
       *total = t;
       return s;
@@ -505,16 +620,7 @@ uint32_t tensor_keep(uint32_t k) {
 
 bool tensor_scan_eligible(uint32_t ld16, uint32_t k) {
   size_t t;
-  return get_encode() != nullptr && tensor_keep(k) != 0 && tensor_stages(ld16 / TC_BK, &t) != 0;
-}
-
-void tensor_scan_shape(uint32_t nq, int sm_count, uint32_t* n_qt, uint32_t* n_es) {
-  uint32_t qt = (nq + TC_BM - 1) / TC_BM;
-  if (qt > (uint32_t)sm_count) qt = (uint32_t)sm_count;
-  uint32_t es = (uint32_t)sm_count / qt;
-  if (es < 1) es = 1;
-  *n_qt = qt;
-  *n_es = es;
+  return get_encode() != nullptr && tensor_keep(k) != 0 && tensor_stages(ld16 / TC_BK, false, &t) != 0;
 }
 
 size_t tensor_scratch_bytes(int sm_count) { return (size_t)sm_count * 2 * TC_BM * TC_LIST_CAP * 8; }
@@ -526,26 +632,44 @@ uint32_t tensor_sample_tiles(uint32_t n_rows, uint32_t nq) {
   return want < n_tiles ? want : n_tiles;
 }
 
+static int g_tensor_pair = 0;  // 1 = two or more query tiles run as CTA pairs (cta_group::2); measured slower so far
+static int g_tensor_debug = 0; // measurement hook, see TensorParams::debug
+void tensor_set_pair(int on) { g_tensor_pair = on; }
+void tensor_set_debug(int mode) { g_tensor_debug = mode; }
+
 static cudaError_t launch_mode(const StoreView& st, const void* Q16, uint32_t q0, uint32_t nq, const DevFilter& flt,
                                bool check_rows, const CandView& cv, uint64_t* lists, float* dump, uint32_t n_slots,
-                               uint32_t mode, int sm_count, cudaStream_t s) {
-  uint32_t n_qt, n_es;
-  tensor_scan_shape(nq, sm_count, &n_qt, &n_es);
-  if (nq > n_qt * TC_BM) return cudaErrorInvalidValue;  // caller splits larger batches
+                               uint32_t tile0, uint32_t mode, int sm_count, cudaStream_t s) {
+  const uint32_t n_tiles_q = (nq + TC_BM - 1) / TC_BM;
+  if (n_tiles_q > (uint32_t)sm_count) return cudaErrorInvalidValue;  // caller splits larger batches
+  // two or more query tiles: CTA pairs (each pair = two query tiles walking the same rows)
+  const bool pair = g_tensor_pair && n_tiles_q >= 2 && sm_count >= 2;
+  uint32_t n_qt, n_es;  // query-tile groups (tiles, or pairs of tiles) x row splits
+  if (pair) {
+    n_qt = (n_tiles_q + 1) / 2;
+    n_es = (uint32_t)(sm_count / 2) / n_qt;
+  } else {
+    n_qt = n_tiles_q;
+    n_es = (uint32_t)sm_count / n_qt;
+  }
+  if (n_es < 1) n_es = 1;
   TensorParams p;
   p.n_rows = st.n_rows;
   p.n_tiles = (st.n_rows + TC_BN - 1) / TC_BN;
-  p.n_slots = mode == TC_MODE_SCAN ? p.n_tiles : n_slots;
+  p.n_slots = n_slots;  // SCAN: tiles [tile0, tile0 + n_slots); DUMP: sampled tiles
+  p.tile0 = tile0;
+  if (mode == TC_MODE_SCAN && (uint64_t)tile0 + n_slots > p.n_tiles) return cudaErrorInvalidValue;
   if (n_es > p.n_slots) n_es = p.n_slots;
   p.n_kc = st.ld16 / TC_BK;
   p.n_qt = n_qt;
   p.n_es = n_es;
   p.nq_valid = nq;
   size_t smem;
-  p.stages = tensor_stages(p.n_kc, &smem);
+  p.stages = tensor_stages(p.n_kc, pair, &smem);
   if (!p.stages) return cudaErrorInvalidConfiguration;
   p.mode = mode;
   p.check_rows = check_rows ? 1u : 0u;
+  p.debug = mode == TC_MODE_SCAN ? (uint32_t)g_tensor_debug : 0u;
   p.KP = cv.KP;
   p.meta = st.meta;
   p.agent = st.agent;
@@ -558,12 +682,33 @@ static cudaError_t launch_mode(const StoreView& st, const void* Q16, uint32_t q0
   p.dump = dump;
   CUtensorMap tmQ, tmE;
   const __nv_bfloat16* qbase = (const __nv_bfloat16*)Q16 + (size_t)q0 * st.ld16;
-  if (!encode_2d(&tmQ, qbase, st.ld16, (uint64_t)n_qt * TC_BM, TC_BM)) return cudaErrorInvalidValue;
-  if (!encode_2d(&tmE, st.E16, st.ld16, st.n_rows, TC_BN)) return cudaErrorInvalidValue;
-  cudaError_t e = cudaFuncSetAttribute(tensor_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // the query buffer is padded to whole 128-row tiles; a pair's missing second tile is out of
+  // bounds for the map and reads as zeros
+  if (!encode_2d(&tmQ, qbase, st.ld16, (uint64_t)n_tiles_q * TC_BM, TC_BM)) return cudaErrorInvalidValue;
+  if (!encode_2d(&tmE, st.E16, st.ld16, st.n_rows, pair ? TC_BN / 2 : TC_BN)) return cudaErrorInvalidValue;
+  if (!pair) {
+    cudaError_t e =
+        cudaFuncSetAttribute(tensor_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    tensor_scan_kernel<false><<<n_qt * n_es, TC_THREADS, smem, s>>>(tmQ, tmE, p);
+    return cudaGetLastError();
+  }
+  cudaError_t e =
+      cudaFuncSetAttribute(tensor_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  tensor_scan_kernel<<<n_qt * n_es, TC_THREADS, smem, s>>>(tmQ, tmE, p);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * n_qt * n_es, 1, 1);
+  cfg.blockDim = dim3(TC_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, tensor_scan_kernel<true>, tmQ, tmE, p);
 }
 
 // Bootstrap: sample scores -> per-query cut-off in cv.gtau[q0 .. q0+nq).  dump holds
@@ -572,7 +717,8 @@ cudaError_t launch_tensor_bootstrap(const StoreView& st, const void* Q16, uint32
                                     const DevFilter& flt, bool check_rows, const CandView& cv, float* dump,
                                     uint32_t n_slots, int sm_count, cudaStream_t s) {
   if (!nq || !st.n_rows || !n_slots) return cudaSuccess;
-  cudaError_t e = launch_mode(st, Q16, q0, nq, flt, check_rows, cv, nullptr, dump, n_slots, TC_MODE_DUMP, sm_count, s);
+  cudaError_t e =
+      launch_mode(st, Q16, q0, nq, flt, check_rows, cv, nullptr, dump, n_slots, 0, TC_MODE_DUMP, sm_count, s);
   if (e != cudaSuccess) return e;
   tau_select_kernel<<<nq, 256, 0, s>>>(dump, n_slots * TC_BN, cv.KP, cv.gtau + q0);
   return cudaGetLastError();
@@ -580,9 +726,39 @@ cudaError_t launch_tensor_bootstrap(const StoreView& st, const void* Q16, uint32
 
 cudaError_t launch_tensor_scan(const StoreView& st, const void* Q16, uint32_t q0, uint32_t nq,
                                const DevFilter& flt, bool check_rows, const CandView& cv, uint64_t* lists,
-                               int sm_count, cudaStream_t s) {
-  if (!nq || !st.n_rows) return cudaSuccess;
-  return launch_mode(st, Q16, q0, nq, flt, check_rows, cv, lists, nullptr, 0, TC_MODE_SCAN, sm_count, s);
+                               uint32_t tile0, uint32_t n_tiles, int sm_count, cudaStream_t s) {
+  if (!nq || !st.n_rows || !n_tiles) return cudaSuccess;
+  return launch_mode(st, Q16, q0, nq, flt, check_rows, cv, lists, nullptr, n_tiles, tile0, TC_MODE_SCAN, sm_count, s);
+}
+
+uint32_t tensor_tiles(uint32_t n_rows) { return (n_rows + TC_BN - 1) / TC_BN; }
+
+// ---- cut-off refinement between two phases of a scan -----------------------------------
+// The merged list of a query holds every row scanned so far whose score cleared the cut-off in
+// force when it was seen; the KP-th best of them is a (much tighter) lower bound of the KP-th
+// best over the whole corpus, so the next phase nominates far fewer rows.
+__global__ void __launch_bounds__(256) tau_refine_kernel(const uint64_t* __restrict__ keys,
+                                                         const uint32_t* __restrict__ cnt, uint32_t cap, uint32_t KP,
+                                                         uint64_t* __restrict__ gtau) {
+  __shared__ uint32_t scratch[260];
+  __shared__ uint32_t stage[4096];
+  const uint32_t q = blockIdx.x, tid = threadIdx.x;
+  const uint32_t n = min(cnt[q], cap);  // an overflowed list still holds `cap` real rows
+  if (n < KP) return;
+  const uint64_t* k = keys + (size_t)q * cap;
+  auto get = [&](uint32_t i) { return key_ord(k[i]); };
+  const uint32_t t = block_kth_largest(get, n, KP, scratch, stage, 4096u, tid, 256);
+  if (tid == 0) {
+    const uint64_t nt = (uint64_t)t << 32;  // the lowest key with that score
+    if (nt > gtau[q]) gtau[q] = nt;
+  }
+}
+
+cudaError_t launch_tau_refine(const CandView& cv, uint32_t q0, uint32_t nq, cudaStream_t s) {
+  if (!nq) return cudaSuccess;
+  tau_refine_kernel<<<nq, 256, 0, s>>>(cv.keys + (size_t)(q0 - cv.q_base) * cv.cap, cv.cnt + q0, cv.cap, cv.KP,
+                                       cv.gtau + q0);
+  return cudaGetLastError();
 }
 
 }  // namespace cx

@@ -1,0 +1,57 @@
+#!/usr/bin/env python
+"""Where does the tensor pass spend its time?  Times tensor_scan_kernel alone (CUDA events
+inside the library) with the epilogue progressively disabled, CTA pair vs single CTA.
+usage: python scripts/k2_probe.py [--rows N] [--batch B] [--k K]"""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+from cortex_b200 import GpuVectorIndex  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--rows", type=int, default=1_000_000)
+ap.add_argument("--batch", type=int, default=1024)
+ap.add_argument("--k", type=int, default=10)
+ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--debug-modes", default="0,2,1")
+ap.add_argument("--growth", default="8")
+ap.add_argument("--pairs", default="1,0")
+a = ap.parse_args()
+dev = torch.device("cuda", 0)
+corpus = bench.make_corpus_torch(a.rows, 384, bench.SEED, dev)
+q = bench.make_queries_torch(corpus, a.batch, bench.SEED)
+ids = np.zeros((a.rows, 16), np.uint8)
+ids[:, 8:] = np.arange(a.rows, dtype=np.uint64).astype(">u8").view(np.uint8).reshape(-1, 8)
+ix = GpuVectorIndex(384, device=0)
+ix.reserve(a.rows)
+ix.insert_batch_device(ids, corpus)
+ix.set_option("profile", 1)
+ix.set_option("force_path", 2)
+out = None
+for pair, growth in [(int(p), int(g)) for p in a.pairs.split(",") for g in a.growth.split(",")]:
+    for dbg in [int(x) for x in a.debug_modes.split(",")]:
+        ix.set_option("tensor_pair", pair)
+        ix.set_option("tensor_phase_growth", growth)
+        ix.set_option("tensor_debug", dbg)
+        reps = a.reps if dbg == 0 else 2
+        out = ix.search_batch_device(q, a.k, out=out)
+        torch.cuda.synchronize()
+        s0 = ix.stats()
+        for _ in range(reps):
+            out = ix.search_batch_device(q, a.k, out=out)
+        torch.cuda.synchronize()
+        s1 = ix.stats()
+        ns = s1["pass_kernel_ns"] - s0["pass_kernel_ns"]
+        n = s1["pass_kernel_launches"] - s0["pass_kernel_launches"]
+        us = ns * 1e-3 / max(n, 1)
+        tf = 2.0 * 384 * a.batch * a.rows / (us * 1e-6) / 1e12
+        print(json.dumps({"pair": pair, "growth": growth, "debug": dbg, "fallbacks": s1["fallbacks"] - s0["fallbacks"], "us_per_launch": us, "tflops": tf, "launches": n,
+                          "batch": a.batch, "k": a.k}), flush=True)
+ix.set_option("tensor_debug", 0)
+ix.set_option("tensor_pair", 0)

@@ -93,17 +93,26 @@ def test_shapes(n, d, b, k):
 @pytest.mark.parametrize("n,d,b,k", [
     (5000, 384, 16, 10), (20_000, 384, 200, 10), (3000, 128, 33, 5), (8000, 384, 130, 30),
     (50_000, 384, 1024, 10), (4000, 100, 40, 10), (6000, 640, 17, 10), (700, 384, 129, 3),
+    (30_000, 384, 300, 10), (40_000, 256, 640, 100),
 ])
-def test_tensor_pass_parity(n, d, b, k):
-    """K2 (tcgen05 bf16 pass) nominates, K3 rescores: results must equal the oracle bit for bit."""
+@pytest.mark.parametrize("pair", [1, 0])
+def test_tensor_pass_parity(n, d, b, k, pair):
+    """K2 (tcgen05 bf16 pass) nominates, K3 rescores: results must equal the oracle bit for bit.
+    pair=1: two or more query tiles run as CTA pairs (cta_group::2); pair=0: single-CTA form."""
     corpus = synth.make_corpus(n, d, zero_row=True, seed=synth.SEED + 3 * n + d)
     Q = synth.make_queries(corpus, b, seed=synth.SEED + n + 1)
     g, o, _ = build_pair(corpus)
     g.set_option("force_path", 2)
-    assert_batch_equal(g, o, Q, k)
+    g.set_option("tensor_pair", pair)
+    try:
+        assert_batch_equal(g, o, Q, k)
+    finally:
+        g.set_option("tensor_pair", 0)
     st = g.stats()
-    assert st["queries_tensor"] > 0, st
-    assert st["queries_tensor"] + st["queries_stream"] >= 0.9 * b, st  # few exact-path fallbacks
+    # the tensor pass itself must verify (almost) every query: a retry on the streaming pass would
+    # also produce the right answer and hide a wrong tile mapping
+    assert st["queries_tensor"] >= 0.9 * b, st
+    assert st["queries_exact"] <= 0.05 * b + 1, st
 
 
 def test_tensor_pass_filters_and_dead_rows():
