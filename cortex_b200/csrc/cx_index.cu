@@ -586,6 +586,10 @@ extern "C" cx_status cx_set_option(cx_index* h, const char* key, int64_t value) 
     h->tensor_phase_growth = (uint32_t)value;
     return CX_OK;
   }
+  if (!strcmp(key, "tensor_epi_warps")) {
+    tensor_set_epi_warps((int)value);
+    return CX_OK;
+  }
   if (!strcmp(key, "tensor_debug")) {  // measurement hook: results of the tensor pass become wrong
     tensor_set_debug((int)value);
     return CX_OK;

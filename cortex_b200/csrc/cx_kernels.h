@@ -81,6 +81,7 @@ cudaError_t launch_select_rescore(const StoreView& st, const QueryView& qv, uint
 uint32_t tensor_keep(uint32_t k);
 bool tensor_scan_eligible(uint32_t ld16, uint32_t k);
 void tensor_set_debug(int mode);  // measurement hook (wrong results): 1 = no epilogue work, 2 = no hit handling
+void tensor_set_epi_warps(int n);  // 8 or 16 epilogue warps per CTA
 void tensor_set_pair(int on);  // test hook: 0 = never use the CTA-pair (cta_group::2) form
 size_t tensor_scratch_bytes(int sm_count);
 void launch_query_bf16(const float* Q, uint32_t ldq, uint32_t dim, uint32_t nq, uint32_t nq_pad, void* Q16,

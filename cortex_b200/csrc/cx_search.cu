@@ -160,6 +160,7 @@ struct Plan {
   uint32_t KP_wide;   // ... and the wide keep count of the last retry tier (0 = no such tier)
   uint32_t KPt;       // tensor pass: keys kept per query (32 / 64 / 128)
   uint32_t n_slots;   // tensor pass: sampled row tiles for the cut-off bootstrap
+  uint32_t growth;    // tensor pass: phase growth factor (tensor_phases)
   uint32_t cap;       // merged-list capacity per query for the primary pass
   uint32_t cap_retry; // ... and for the streaming retries of unverified queries (widest tier)
   uint32_t q_per_launch;  // tensor pass: queries per launch
@@ -186,6 +187,7 @@ Plan make_plan(const cx_index* h, uint64_t B, uint32_t qlen, uint32_t ldq, uint3
   p.KPt = 0;
   p.n_slots = 0;
   p.KP_wide = 0;
+  p.growth = 0;
   if (p.fast) {
     uint32_t w = 4 * p.KP;
     if (w > 256) w = 256;  // the select kernel rescans at most 256 rows
@@ -203,7 +205,8 @@ Plan make_plan(const cx_index* h, uint64_t B, uint32_t qlen, uint32_t ldq, uint3
     // never lost silently)
     p.n_slots = tensor_sample_tiles(n_rows, (uint32_t)(B < p.q_per_launch ? B : p.q_per_launch));
     double hits_per_kp = 0.0;
-    tensor_phases(tensor_tiles(n_rows), p.n_slots, h->tensor_phase_growth, &hits_per_kp);
+    p.growth = h->tensor_phase_growth != 0xFFFFFFFFu ? h->tensor_phase_growth : (p.KPt <= 32 ? 8u : 4u);
+    tensor_phases(tensor_tiles(n_rows), p.n_slots, p.growth, &hits_per_kp);
     const uint64_t expected = (uint64_t)((double)p.KPt * hits_per_kp) + 1;
     uint64_t cap = 2 * expected + 4 * p.KPt + 64;
     if (cap > 16384) cap = 16384;
@@ -316,7 +319,7 @@ cx_status run_search(cx_index* h, Workspace* ws, const FilterHost& fh, const Sea
       }
       if (h->profile) CU(cudaEventRecord(ws->ev0, s));
       const std::vector<uint32_t> phases =
-          tensor_phases(tensor_tiles(st.n_rows), pl.n_slots, h->tensor_phase_growth, nullptr);
+          tensor_phases(tensor_tiles(st.n_rows), pl.n_slots, pl.growth, nullptr);
       for (uint64_t q0 = 0; q0 < B; q0 += pl.q_per_launch) {
         const uint32_t nq = (uint32_t)(B - q0 < pl.q_per_launch ? B - q0 : pl.q_per_launch);
         uint32_t tile0 = 0;
@@ -470,13 +473,19 @@ cx_status search_host(cx_index* h, const float* queries, uint64_t B, uint32_t ql
   float* hQ = (float*)hp;
   char* h_block = hp + hq;
 
-  // stage queries, zero padded to ldq
-  for (uint64_t b = 0; b < B; ++b) {
-    memcpy(hQ + b * ldq, queries + b * qlen, (size_t)qlen * 4);
-    for (uint32_t d = qlen; d < ldq; ++d) hQ[b * ldq + d] = 0.0f;
-  }
   cudaStream_t s = ws->stream;
-  CU(cudaMemcpyAsync(sb.dQ, hQ, B * ldq * 4, cudaMemcpyHostToDevice, s));
+  if (qlen == ldq) {
+    // rows need no padding: copy straight from the caller's buffer (a true async DMA when it is
+    // pinned; staged by the driver when it is pageable) -- no intermediate host copy
+    CU(cudaMemcpyAsync(sb.dQ, queries, B * ldq * 4, cudaMemcpyHostToDevice, s));
+  } else {
+    // stage queries, zero padded to ldq
+    for (uint64_t b = 0; b < B; ++b) {
+      memcpy(hQ + b * ldq, queries + b * qlen, (size_t)qlen * 4);
+      for (uint32_t d = qlen; d < ldq; ++d) hQ[b * ldq + d] = 0.0f;
+    }
+    CU(cudaMemcpyAsync(sb.dQ, hQ, B * ldq * 4, cudaMemcpyHostToDevice, s));
+  }
   h->h2d += B * ldq * 4;
 
   std::vector<uint64_t> totals;

@@ -32,6 +32,7 @@
 // Algorithmic work: 2*D flops per scored pair; DESIGN.md §4.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdio.h>
 
 #include "cx_kernels.h"
 
@@ -41,7 +42,8 @@ constexpr uint32_t TC_BM = 128;       // queries per CTA (UMMA M, TMEM lanes)
 constexpr uint32_t TC_BN = 256;       // corpus rows per tile (UMMA N, TMEM columns)
 constexpr uint32_t TC_BK = 64;        // bf16 per K chunk = one 128 B swizzle atom
 constexpr uint32_t TC_UK = 16;        // K of one tcgen05.mma for 16-bit inputs
-constexpr uint32_t TC_THREADS = 384;      // 4 control warps + 8 epilogue warps
+constexpr uint32_t TC_CTRL_WARPS = 4;     // TMA producer, MMA issuer, TMEM allocator, (idle)
+constexpr uint32_t TC_LIST_POOL = 256 * 512;  // private-list entries per CTA, split among its epilogue threads
 constexpr uint32_t TC_QCHUNK_BYTES = TC_BM * TC_BK * 2;  // 16 KB
 constexpr uint32_t TC_MAX_STAGES = 8;
 // bytes of one ring stage per CTA: the whole [256 x 64] bf16 box, or -- for a CTA pair, where
@@ -49,8 +51,9 @@ constexpr uint32_t TC_MAX_STAGES = 8;
 __host__ __device__ constexpr uint32_t tc_stage_bytes(bool pair) { return (pair ? TC_BN / 2 : TC_BN) * TC_BK * 2; }
 constexpr uint32_t TC_SMEM_LIMIT = 227 * 1024;
 constexpr uint32_t TC_TMEM_COLS = 512;
-constexpr uint32_t TC_NPL = 16;                 // list entries per lane in a cooperative sort
-constexpr uint32_t TC_LIST_CAP = TC_NPL * 32;   // private list entries per (CTA, query) = 512
+// EW epilogue warps (8 or 16): four per TMEM lane quarter share the 256 columns of a tile;
+// private list entries per epilogue thread and per lane in a cooperative sort
+__host__ __device__ constexpr uint32_t tc_list_cap(uint32_t EW) { return TC_LIST_POOL / (EW * 32); }
 
 enum { TC_MODE_SCAN = 0, TC_MODE_DUMP = 1 };
 
@@ -69,7 +72,7 @@ struct TensorParams {
   const uint32_t* meta;
   const uint32_t* agent;
   DevFilter flt;
-  uint64_t* lists;  // [grid][128][TC_LIST_CAP] private candidate lists (scratch)
+  uint64_t* lists;  // [grid][TC_LIST_POOL] private candidate lists (scratch), one slice per epilogue thread
   uint64_t* keys;   // merged list per query [nq][cap]
   uint32_t* cnt;
   uint64_t* gtau;
@@ -203,10 +206,10 @@ __device__ __forceinline__ float pick32(const float (&v)[32], uint32_t j) {
 }
 
 // ---- warp-cooperative reduction of one private list --------------------------------
-// Sort (descending) the n <= 512 keys at L across the warp's registers, write the best KP
+// Sort (descending) the n <= 32 * NPL keys at L across the warp's registers, write the best KP
 // back in order, return the KP-th key (0 if n < KP).  All lanes call it.
+template <int NPL>
 __device__ __noinline__ uint64_t warp_compact(uint64_t* L, uint32_t n, uint32_t KP, uint32_t lane) {
-  constexpr int NPL = TC_NPL;
   uint64_t k[NPL];
 #pragma unroll
   for (int i = 0; i < NPL; ++i) {
@@ -258,14 +261,17 @@ __device__ __noinline__ uint64_t warp_compact(uint64_t* L, uint32_t n, uint32_t 
   return n >= KP ? kth : 0ull;
 }
 
+// measurement hook: SM cycles and nanoseconds block 0 spent in its last launch (-> effective clock)
+__device__ unsigned long long g_tensor_clock[2];
+
 // PAIR = two CTAs of a cluster (one TPC) work as one tcgen05 cta_group::2 unit: each holds
 // its own 128-query tile (the pair's M = 256) and stages HALF of every [256 x 64] box of E;
 // the leader CTA issues the MMAs, which read both halves.  Per SM that halves the L2->SM
 // traffic and the shared-memory reads of the E operand (the binding limits of the
 // single-CTA form: 64 B/clk of TMA writes + 96 B/clk of MMA operand reads against
 // 128 B/clk of shared-memory bandwidth).
-template <bool PAIR>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <bool PAIR, int EW>
+__global__ void __launch_bounds__((TC_CTRL_WARPS + EW) * 32, 1)
 tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmE,
                    const TensorParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -283,6 +289,11 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;   // 0 = leader
+  unsigned long long dbg_c0 = 0, dbg_t0 = 0;
+  if (p.debug && blockIdx.x == 0 && tid == 0) {
+    dbg_c0 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
+  }
   const uint32_t unit = PAIR ? blockIdx.x >> 1 : blockIdx.x;  // CTA or CTA pair
 
   if (tid == 0) {
@@ -293,7 +304,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
     for (uint32_t a = 0; a < 2; ++a) {
       mbar_init(bar_tfull + 8 * a, 1);
-      mbar_init(bar_tempty + 8 * a, PAIR ? 16 : 8);  // epilogue warps (of both CTAs) that drain an accumulator
+      mbar_init(bar_tempty + 8 * a, PAIR ? 2 * EW : EW);  // epilogue warps (of both CTAs) that drain an accumulator
     }
     fence_mbar_init();
   }
@@ -331,6 +342,10 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           for (uint32_t kc = 0; kc < p.n_kc; ++kc, ++it) {
             const uint32_t stage = it % S;
             if (it >= S) mbar_wait(bar_empty + 8 * stage, ((it / S) - 1) & 1);
+            if (p.debug & 4) {  // measurement: no E traffic at all, the MMAs reuse whatever the stage holds
+              mbar_arrive(bar_full + 8 * stage);
+              continue;
+            }
             mbar_arrive_expect_tx(bar_full + 8 * stage, STAGE_BYTES);
             tma_load_2d(smem_u32(sE + (size_t)stage * STAGE_BYTES), &tmE, (int)(kc * TC_BK), row0,
                         bar_full + 8 * stage);
@@ -351,6 +366,10 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           for (uint32_t kc = 0; kc < p.n_kc; ++kc, ++it) {
             const uint32_t stage = it % S;
             if (it >= S) mbar_wait(bar_empty + 8 * stage, ((it / S) - 1) & 1);
+            if (p.debug & 4) {
+              if (rank == 0) mbar_arrive(bar_full + 8 * stage);
+              continue;
+            }
             if (rank == 0) mbar_arrive_expect_tx(bar_full + 8 * stage, 2 * STAGE_BYTES);
             tma_load_2d_pair(smem_u32(sE + (size_t)stage * STAGE_BYTES), &tmE, (int)(kc * TC_BK), row0,
                              mapa_u32(bar_full + 8 * stage, 0));
@@ -390,15 +409,18 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         else umma_commit(bar_tfull + 8 * acc);
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= TC_CTRL_WARPS) {
     // ------------------------------ epilogue ----------------------------------
-    // two warps per TMEM lane quarter: warp w may read lanes 32*(w%4)..; each takes half the columns
-    const uint32_t ew = warp & 3, half = (warp - 4) >> 2;
+    // EW / 4 warps per TMEM lane quarter (warp w may read lanes 32 * (w % 4) ..); each takes an
+    // equal share of the tile's 256 columns, 32 at a time
+    constexpr uint32_t LIST_CAP = tc_list_cap(EW);
+    constexpr uint32_t CH_PER_WARP = (TC_BN / 32) / (EW / 4);
+    const uint32_t ew = warp & 3, part = (warp - TC_CTRL_WARPS) >> 2;
     const uint32_t q = qt * TC_BM + ew * 32 + lane;
     const bool valid = q < p.nq_valid;
-    const uint32_t list_slot = blockIdx.x * (2 * TC_BM) + (warp - 4) * 32;
+    const uint32_t list_slot = blockIdx.x * (EW * 32) + (warp - TC_CTRL_WARPS) * 32;
     const uint32_t l_bar_tempty = PAIR ? mapa_u32(bar_tempty, 0) : bar_tempty;  // the MMA issuer's barrier
-    uint64_t* myL = p.lists + ((size_t)list_slot + lane) * TC_LIST_CAP;
+    uint64_t* myL = p.lists + ((size_t)list_slot + lane) * LIST_CAP;
     uint32_t cnt = 0;
     uint64_t tau_key = 0ull;
     float tau = valid ? -INFINITY : INFINITY;
@@ -406,7 +428,6 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       tau_key = *((volatile uint64_t*)(p.gtau + q));
       if (tau_key != 0ull) tau = float_from_ord(key_ord(tau_key));
     }
-    constexpr uint32_t CH_PER_WARP = TC_BN / 32 / 2;
 
     for (uint32_t ti = 0; ti < n_my; ++ti) {
       const uint32_t acc = ti & 1, use = ti >> 1;
@@ -414,7 +435,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       mbar_wait(bar_tfull + 8 * acc, use & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((ew * 32u) << 16) + acc * TC_BN;
-      if (p.debug == 1) {
+      if (p.debug & 1) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
@@ -425,7 +446,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       }
 #pragma unroll 1
       for (uint32_t c = 0; c < CH_PER_WARP; ++c) {
-        const uint32_t ch = half * CH_PER_WARP + c;
+        const uint32_t ch = part * CH_PER_WARP + c;
         float v[32];
         tmem_ld32(taddr + ch * 32, v);
         if (c == CH_PER_WARP - 1) {  // this warp's share of the accumulator is drained
@@ -456,20 +477,27 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           }
           continue;
         }
-        // branch-free hit mask: bit j set when v[j] >= tau (never for padded lanes or NaN)
-        uint32_t m = 0;
+        // common path: the largest of the 32 scores against the cut-off (group maxima of 8 are
+        // kept so that a hit is located without a per-score test; fmaxf drops NaN, padded
+        // lanes have tau = +inf)
+        float g8[4];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) m |= (v[j] >= tau ? 1u : 0u) << j;
-        if (p.debug == 2) m = 0;
-        if (__any_sync(0xffffffffu, m != 0)) {
+        for (int i = 0; i < 4; ++i) {
+          const float a = fmaxf(fmaxf(v[8 * i], v[8 * i + 1]), v[8 * i + 2]);
+          const float b = fmaxf(fmaxf(v[8 * i + 3], v[8 * i + 4]), v[8 * i + 5]);
+          g8[i] = fmaxf(fmaxf(a, b), fmaxf(v[8 * i + 6], v[8 * i + 7]));
+        }
+        const bool hit = fmaxf(fmaxf(g8[0], g8[1]), fmaxf(g8[2], g8[3])) >= tau && !(p.debug & 2);
+        if (__any_sync(0xffffffffu, hit)) {
           // make room first: a chunk can append up to 32 keys
-          uint32_t full = __ballot_sync(0xffffffffu, cnt + 32 > TC_LIST_CAP);
+          uint32_t full = __ballot_sync(0xffffffffu, cnt + 32 > LIST_CAP);
           while (full) {
             const uint32_t l = __ffs(full) - 1;
             full &= full - 1;
             __syncwarp();  // lane l's appended keys must be visible to the whole warp
             const uint32_t n_l = __shfl_sync(0xffffffffu, cnt, l);
-            uint64_t kth = warp_compact(p.lists + ((size_t)list_slot + l) * TC_LIST_CAP, n_l, p.KP, lane);
+            uint64_t kth =
+                warp_compact<(int)(LIST_CAP / 32)>(p.lists + ((size_t)list_slot + l) * LIST_CAP, n_l, p.KP, lane);
             if (lane == l) {
               cnt = n_l < p.KP ? n_l : p.KP;
               if (kth > tau_key) {
@@ -479,14 +507,19 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
               }
             }
           }
-          // per-hit loop; v[j] for a run-time j comes from a 5-level select tree (registers only)
+          // hit mask (bit j: v[j] >= tau), then one loop iteration per hit; v[j] for a run-time j
+          // comes from a 5-level select tree so v never leaves the registers
+          uint32_t m = 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) m |= (v[j] >= tau ? 1u : 0u) << j;
+          if (!hit) m = 0;
           while (m) {
             const uint32_t j = __ffs(m) - 1;
             m &= m - 1;
-            const float s = pick32(v, j);
+            const float sc = pick32(v, j);
             const uint32_t row = r0 + j;
-            if (s >= tau && row < p.n_rows) {
-              const uint64_t key = make_key(ord_from_float(s), row);
+            if (sc >= tau && row < p.n_rows) {
+              const uint64_t key = make_key(ord_from_float(sc), row);
               if (key >= tau_key && (!p.check_rows || row_passes(p.flt, p.meta, p.agent, row))) myL[cnt++] = key;
             }
           }
@@ -516,6 +549,12 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_before();
   if (PAIR) cluster_sync_all();  // neither CTA may leave (or free TMEM) while the other still uses it
   else __syncthreads();
+  if (p.debug && blockIdx.x == 0 && tid == 0) {
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    g_tensor_clock[0] = clock64() - dbg_c0;
+    g_tensor_clock[1] = t1 - dbg_t0;
+  }
   if (warp == 2) {
     tc_fence_after();
     if (PAIR) tmem_dealloc_pair(tmem_base, TC_TMEM_COLS);
@@ -623,7 +662,7 @@ bool tensor_scan_eligible(uint32_t ld16, uint32_t k) {
   return get_encode() != nullptr && tensor_keep(k) != 0 && tensor_stages(ld16 / TC_BK, false, &t) != 0;
 }
 
-size_t tensor_scratch_bytes(int sm_count) { return (size_t)sm_count * 2 * TC_BM * TC_LIST_CAP * 8; }
+size_t tensor_scratch_bytes(int sm_count) { return (size_t)sm_count * TC_LIST_POOL * 8; }
 
 // sampled row tiles for the cut-off bootstrap: more when few queries share the cost
 uint32_t tensor_sample_tiles(uint32_t n_rows, uint32_t nq) {
@@ -632,10 +671,52 @@ uint32_t tensor_sample_tiles(uint32_t n_rows, uint32_t nq) {
   return want < n_tiles ? want : n_tiles;
 }
 
+static int g_tensor_epi_warps = 8;  // epilogue warps per CTA (8 or 16; measured equal within noise)
+void tensor_set_epi_warps(int n) { g_tensor_epi_warps = n == 8 ? 8 : 16; }
+
+template <int EW>
+static cudaError_t launch_kernel(bool pair, uint32_t units, size_t smem, cudaStream_t s, const CUtensorMap& tmQ,
+                                 const CUtensorMap& tmE, const TensorParams& p) {
+  constexpr uint32_t threads = (TC_CTRL_WARPS + EW) * 32;
+  if (!pair) {
+    cudaError_t e = cudaFuncSetAttribute(tensor_scan_kernel<false, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) return e;
+    tensor_scan_kernel<false, EW><<<units, threads, smem, s>>>(tmQ, tmE, p);
+    return cudaGetLastError();
+  }
+  cudaError_t e =
+      cudaFuncSetAttribute(tensor_scan_kernel<true, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2 * units, 1, 1);
+  cfg.blockDim = dim3(threads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, tensor_scan_kernel<true, EW>, tmQ, tmE, p);
+}
+
 static int g_tensor_pair = 0;  // 1 = two or more query tiles run as CTA pairs (cta_group::2); measured slower so far
 static int g_tensor_debug = 0; // measurement hook, see TensorParams::debug
 void tensor_set_pair(int on) { g_tensor_pair = on; }
-void tensor_set_debug(int mode) { g_tensor_debug = mode; }
+void tensor_set_debug(int mode) {
+  if (mode == -1) {  // report the effective SM clock of block 0 in the last debug-mode launch
+    unsigned long long c[2] = {0, 0};
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(c, g_tensor_clock, sizeof c) == cudaSuccess && c[1])
+      fprintf(stderr, "[cortex_gpu] tensor_scan block 0: %llu cycles in %llu ns = %.0f MHz\n", c[0], c[1],
+              1e3 * (double)c[0] / (double)c[1]);
+    return;
+  }
+  g_tensor_debug = mode;
+}
 
 static cudaError_t launch_mode(const StoreView& st, const void* Q16, uint32_t q0, uint32_t nq, const DevFilter& flt,
                                bool check_rows, const CandView& cv, uint64_t* lists, float* dump, uint32_t n_slots,
@@ -686,29 +767,8 @@ static cudaError_t launch_mode(const StoreView& st, const void* Q16, uint32_t q0
   // bounds for the map and reads as zeros
   if (!encode_2d(&tmQ, qbase, st.ld16, (uint64_t)n_tiles_q * TC_BM, TC_BM)) return cudaErrorInvalidValue;
   if (!encode_2d(&tmE, st.E16, st.ld16, st.n_rows, pair ? TC_BN / 2 : TC_BN)) return cudaErrorInvalidValue;
-  if (!pair) {
-    cudaError_t e =
-        cudaFuncSetAttribute(tensor_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    tensor_scan_kernel<false><<<n_qt * n_es, TC_THREADS, smem, s>>>(tmQ, tmE, p);
-    return cudaGetLastError();
-  }
-  cudaError_t e =
-      cudaFuncSetAttribute(tensor_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(2 * n_qt * n_es, 1, 1);
-  cfg.blockDim = dim3(TC_THREADS, 1, 1);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, tensor_scan_kernel<true>, tmQ, tmE, p);
+  return g_tensor_epi_warps == 8 ? launch_kernel<8>(pair, n_qt * n_es, smem, s, tmQ, tmE, p)
+                                 : launch_kernel<16>(pair, n_qt * n_es, smem, s, tmQ, tmE, p);
 }
 
 // Bootstrap: sample scores -> per-query cut-off in cv.gtau[q0 .. q0+nq).  dump holds
