@@ -61,9 +61,11 @@ void launch_prepare_queries(const float* Q, float* qnorm, float* rqnorm, uint32_
 uint32_t stream_scan_groups(uint32_t n_rows, int sm_count);
 size_t stream_scan_smem(uint32_t ld, uint32_t nq_pass, uint32_t KP);
 // qmap (device, optional, q0 must be 0): pass-local query b is query qmap[b]; its candidate list is slot b
+// thr_cos (optional): threshold mode -- every row whose approximate cosine reaches *thr_cos is nominated
+// (no top-KP cut-off; qv.qnorm must already hold the query norms); cv.gtau is not used.
 cudaError_t launch_stream_scan(const StoreView& st, const QueryView& qv, uint32_t q0, uint32_t nq_pass,
                                const DevFilter& flt, const CandView& cv, int sm_count, cudaStream_t s,
-                               const uint32_t* qmap = nullptr);
+                               const uint32_t* qmap = nullptr, const float* thr_cos = nullptr);
 
 // K5 + K3: merge candidate lists, exact rescore, verify, emit results.
 // eps_cos: bound on |approx - reference| cosine for the pass that produced the candidates.
@@ -73,6 +75,16 @@ size_t select_smem(uint32_t cap, uint32_t ld);
 cudaError_t launch_select_rescore(const StoreView& st, const QueryView& qv, uint32_t q0, uint32_t nq,
                                   const CandView& cv, const ResultView& rv, float eps_cos, int scale_by_rqn,
                                   cudaStream_t s, const uint32_t* qmap = nullptr);
+
+// Threshold scans: rescore ALL nominees of each query exactly, keep `score >= threshold`
+// (index.rs:385), order by (score desc, row asc), write up to rv.k of them; total[q] = how many
+// qualify; rv.ok[q] = 0 if the nominee list overflowed or more than 2048 rows qualify.
+// qv.qnorm must hold the query norms.  self_rows (optional): skip that row; upper_only: keep
+// only rows above it (the dedup scanner's unordered pairs, linker/dedup.rs:96-105).
+size_t threshold_rescore_smem(uint32_t ld);
+cudaError_t launch_threshold_rescore(const StoreView& st, const QueryView& qv, uint32_t q0, uint32_t nq,
+                                     const CandView& cv, const ResultView& rv, uint32_t* total, float threshold,
+                                     const uint32_t* self_rows, bool upper_only, cudaStream_t s);
 
 // K2: tcgen05 bf16 pass over the normalised shadow matrix.  Q16 = normalised bf16 queries
 // [round_up(nq_total,128)][ld16] made by launch_query_bf16.  One launch serves at most
@@ -96,7 +108,10 @@ cudaError_t launch_tensor_bootstrap(const StoreView& st, const void* Q16, uint32
 // check_rows: a filter is active or rows were removed -> test metadata before nominating a row
 cudaError_t launch_tensor_scan(const StoreView& st, const void* Q16, uint32_t q0, uint32_t nq,
                                const DevFilter& flt, bool check_rows, const CandView& cv, uint64_t* lists,
-                               uint32_t tile0, uint32_t n_tiles, int sm_count, cudaStream_t s);
+                               uint32_t tile0, uint32_t n_tiles, int sm_count, cudaStream_t s,
+                               bool static_tau = false);
+// Threshold scans: fix every query's cut-off at the approximate cosine thr_cos (then scan with static_tau).
+void launch_fill_tau(const CandView& cv, uint32_t q0, uint32_t nq, float thr_cos, cudaStream_t s);
 uint32_t tensor_tiles(uint32_t n_rows);
 // Between phases: raise each query's cut-off to the cv.KP-th best key nominated so far.
 cudaError_t launch_tau_refine(const CandView& cv, uint32_t q0, uint32_t nq, cudaStream_t s);

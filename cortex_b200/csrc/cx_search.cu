@@ -125,6 +125,7 @@ struct SearchBufs {
   void* sort_tmp = nullptr;
   size_t sort_tmp_bytes = 0;
   uint32_t* n_total = nullptr;
+  uint32_t* totals = nullptr;     // threshold scans: rows that qualify, per query
 };
 
 // bound on |approximate - reference| cosine for the bf16 tensor pass: both operands are
@@ -166,9 +167,17 @@ struct Plan {
   uint32_t q_per_launch;  // tensor pass: queries per launch
   bool fast;          // a nominate + rescore pass is usable for this call
   bool tensor;        // ... and it is the tcgen05 pass (else the streaming pass)
+  bool thr_fast;      // threshold scan served by nominate-all + rescore-all (else the exact path)
+  uint32_t thr_cap;   // ... nominee capacity per query
 };
 
-Plan make_plan(const cx_index* h, uint64_t B, uint32_t qlen, uint32_t ldq, uint32_t kd, bool threshold_mode) {
+// Threshold scans take the fast path when the threshold is far enough above the noise floor
+// of random directions that the nominee lists stay short (lower thresholds qualify a large
+// part of the corpus: sort-everything on the exact path is the right tool there).
+constexpr float THR_FAST_MIN = 0.2f;
+
+Plan make_plan(const cx_index* h, uint64_t B, uint32_t qlen, uint32_t ldq, uint32_t kd, bool threshold_mode,
+               float threshold = 0.0f) {
   Plan p;
   p.B = B;
   p.qlen = qlen;
@@ -188,6 +197,22 @@ Plan make_plan(const cx_index* h, uint64_t B, uint32_t qlen, uint32_t ldq, uint3
   p.n_slots = 0;
   p.KP_wide = 0;
   p.growth = 0;
+  p.thr_fast = false;
+  p.thr_cap = 0;
+  if (threshold_mode) {
+    p.thr_fast = threshold == threshold && threshold >= THR_FAST_MIN && qlen == h->dim && n_rows >= 256 &&
+                 h->force_path != PATH_EXACT && stream_scan_smem(h->ld, 8, 64) != 0 &&
+                 threshold_rescore_smem(h->ld) <= 200 * 1024;
+    if (p.thr_fast) {
+      p.KP = 64;  // sizes the streaming pass's shared-memory lists (2 * KP + 128 entries)
+      p.thr_cap = B <= 64 ? 8192u : 2048u;
+      p.cap = p.thr_cap;
+      p.q_per_launch = (uint32_t)h->sm_count * 128u;
+      p.tensor = h->dE16 && h->force_path != PATH_STREAM &&
+                 (B >= h->tensor_min_batch || h->force_path == PATH_TENSOR) && tensor_scan_eligible(h->ld16, 16);
+    }
+    return p;
+  }
   if (p.fast) {
     uint32_t w = 4 * p.KP;
     if (w > 256) w = 256;  // the select kernel rescans at most 256 rows
@@ -223,13 +248,18 @@ size_t carve_bufs(void* base, const cx_index* h, const Plan& pl, uint32_t n_excl
   sb->qnorm = c.take<float>(pl.B);
   sb->rqnorm = c.take<float>(pl.B);
   sb->excl = c.take<uint32_t>(n_excl + 1);
-  sb->cand_keys = pl.fast ? c.take<uint64_t>((size_t)pl.B * pl.cap) : nullptr;
+  sb->cand_keys = (pl.fast || pl.thr_fast) ? c.take<uint64_t>((size_t)pl.B * pl.cap) : nullptr;
+  sb->totals = c.take<uint32_t>(pl.B);
+  if (pl.thr_fast && pl.tensor) {
+    sb->q16 = c.take<uint16_t>(align_up(pl.B, 128) * h->ld16);
+    sb->lists = (uint64_t*)c.take<char>(tensor_scratch_bytes(h->sm_count));
+  }
   if (pl.fast) {
     const uint64_t chunk = pl.B < RETRY_CHUNK ? pl.B : RETRY_CHUNK;
     sb->retry_keys = c.take<uint64_t>((size_t)chunk * pl.cap_retry);
     sb->qmap = c.take<uint32_t>(RETRY_CHUNK);
   }
-  if (pl.tensor) {
+  if (pl.tensor && pl.fast) {
     sb->q16 = c.take<uint16_t>(align_up(pl.B, 128) * h->ld16);
     sb->lists = (uint64_t*)c.take<char>(tensor_scratch_bytes(h->sm_count));
     const uint64_t nq_launch = pl.B < pl.q_per_launch ? pl.B : pl.q_per_launch;
@@ -260,9 +290,16 @@ size_t carve_bufs(void* base, const cx_index* h, const Plan& pl, uint32_t n_excl
 // Core.  Queries are on the device at sb.dQ [B][ldq]; results land in sb.rows/score/
 // dist/ids/n (device).  If h_block != nullptr the whole ResultBlock is also copied to
 // it (pinned host).  h_ok: pinned host scratch of B words.  Returns with the stream idle.
+// Extras of a pair scan (the dedup self-join): queries are rows of the index itself.
+struct PairScan {
+  const uint32_t* self_rows;  // device [B]: the row each query is
+  bool upper_only;            // keep only partners above the query's own row
+  uint32_t tile0;             // first row tile worth scanning (rows below it cannot qualify)
+};
+
 cx_status run_search(cx_index* h, Workspace* ws, const FilterHost& fh, const SearchBufs& sb, const Plan& pl,
                      bool threshold_mode, float threshold, char* h_block, uint32_t* h_ok,
-                     uint64_t* h_total /* threshold mode: per-query totals */) {
+                     uint64_t* h_total /* threshold mode: per-query totals */, const PairScan* tp = nullptr) {
   cudaStream_t s = ws->stream;
   const uint64_t B = pl.B;
   StoreView st = h->view();
@@ -292,7 +329,75 @@ cx_status run_search(cx_index* h, Workspace* ws, const FilterHost& fh, const Sea
     return fail(CX_ERR_VALIDATION, "force_path=stream but the call shape is not eligible");
 
   std::vector<uint32_t> redo;
-  if (pl.fast) {
+  if (pl.thr_fast) {
+    // threshold scan: nominate every row within the pass's error bound of the threshold,
+    // rescore all nominees exactly, keep `score >= threshold` (index.rs:385)
+    CU(ws->ensure_state(B));
+    ws->state_dirty = true;
+    CandView cv;
+    cv.keys = sb.cand_keys;
+    cv.cnt = ws->d_cnt;
+    cv.gtau = ws->d_gtau;
+    cv.cap = pl.cap;
+    cv.G = pl.G;
+    cv.KP = pl.KP;
+    launch_prepare_queries(sb.dQ, sb.qnorm, sb.rqnorm, (uint32_t)B, pl.qlen, pl.ldq, s);
+    h->launches += 1;
+    // score >= thr implies reference cosine >= thr - 2^-23 (the 1-(1-x) round trip, index.rs:177,255)
+    const float slack = 1e-6f;
+    uint32_t n_pass = 0;
+    if (h->profile) CU(cudaEventRecord(ws->ev0, s));
+    if (pl.tensor) {
+      const bool check_rows = flt.has_kinds || flt.has_agent || flt.n_excl || h->n_live != h->n_rows;
+      launch_query_bf16(sb.dQ, pl.ldq, h->dim, (uint32_t)B, (uint32_t)align_up(B, 128), sb.q16, h->ld16, s);
+      cv.KP = 32;
+      launch_fill_tau(cv, 0, (uint32_t)B, threshold - eps_tensor(h->dim) - slack, s);
+      h->launches += 2;
+      const uint32_t t0 = tp ? tp->tile0 : 0, nt = tensor_tiles(st.n_rows) - t0;
+      for (uint64_t q0 = 0; q0 < B; q0 += pl.q_per_launch) {
+        const uint32_t nq = (uint32_t)(B - q0 < pl.q_per_launch ? B - q0 : pl.q_per_launch);
+        CU(launch_tensor_scan(st, sb.q16, (uint32_t)q0, nq, flt, check_rows, cv, sb.lists, t0, nt, h->sm_count, s,
+                              /*static_tau=*/true));
+        ++n_pass;
+      }
+    } else {
+      const float thr_cos = threshold - eps_stream(h->dim) - slack;
+      for (uint64_t q0 = 0; q0 < B; q0 += 8) {
+        const uint32_t nq = (uint32_t)(B - q0 < 8 ? B - q0 : 8);
+        CU(launch_stream_scan(st, qv, (uint32_t)q0, nq, flt, cv, h->sm_count, s, nullptr, &thr_cos));
+        ++n_pass;
+      }
+    }
+    if (h->profile) CU(cudaEventRecord(ws->ev1, s));
+    CU(launch_threshold_rescore(st, qv, 0, (uint32_t)B, cv, rv, sb.totals, threshold, tp ? tp->self_rows : nullptr,
+                                tp ? tp->upper_only : false, s));
+    h->launches += n_pass + 1;
+    std::vector<uint32_t> tot32;
+    if (h_total) tot32.resize(B);
+    if (h_block) {
+      CU(cudaMemcpyAsync(h_block, sb.res, rb.total, cudaMemcpyDeviceToHost, s));
+      h_ok = (uint32_t*)(h_block + rb.ok);
+    } else {
+      CU(cudaMemcpyAsync(h_ok, sb.ok, B * 4, cudaMemcpyDeviceToHost, s));
+    }
+    if (h_total) CU(cudaMemcpyAsync(tot32.data(), sb.totals, B * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    if (h->profile) {
+      float ms = 0.f;
+      CU(cudaEventElapsedTime(&ms, ws->ev0, ws->ev1));
+      h->pass_ns += (uint64_t)(ms * 1e6);
+      h->pass_launches += n_pass;
+    }
+    ws->state_dirty = false;
+    for (uint64_t b = 0; b < B; ++b) {
+      if (!h_ok[b]) redo.push_back((uint32_t)b);
+      else if (h_total) h_total[b] = tot32[b];
+    }
+    (pl.tensor ? h->q_tensor : h->q_stream) += B - redo.size();
+    h->fallbacks += redo.size();
+    if (redo.empty()) return CX_OK;
+    if (tp) return fail(CX_ERR_VALIDATION, "threshold scan overflow");  // pair scans have no per-query exact fallback
+  } else if (pl.fast) {
     CU(ws->ensure_state(B));
     ws->state_dirty = true;  // until the select kernel has re-zeroed it and the stream drained cleanly
     CandView cv;
@@ -458,7 +563,7 @@ cx_status search_host(cx_index* h, const float* queries, uint64_t B, uint32_t ql
 
   FilterHost fh;
   build_filter(h, filter, &fh);
-  const Plan pl = make_plan(h, B, qlen, ldq, kd, threshold_mode);
+  const Plan pl = make_plan(h, B, qlen, ldq, kd, threshold_mode, threshold);
 
   WsLease lease(h);
   CU(lease.init());
@@ -534,6 +639,84 @@ extern "C" cx_status cx_search_threshold(cx_index* h, const float* query, uint32
                              out_n, &total);
   if (out_total) *out_total = total;
   return st;
+}
+
+extern "C" cx_status cx_search_threshold_batch(cx_index* h, const float* queries, uint64_t B, uint32_t qlen,
+                                               float threshold, const cx_filter* filter, uint64_t cap,
+                                               uint8_t* out_ids, float* out_score, float* out_distance,
+                                               uint64_t* out_n, uint64_t* out_total) {
+  return search_host(h, queries, B, qlen, cap, filter, true, threshold, out_ids, out_score, out_distance, out_n,
+                     out_total);
+}
+
+// ------------------------------------------------------------------------------
+// DedupScanner::scan (linker/dedup.rs:65-127) restricted to what the similarity scan decides:
+// every live row searches the index with search_threshold(embedding, threshold) (:84-86),
+// skips itself (:91-93) and reports each unordered pair once (:96-105).  Here the rows of the
+// index are their own query batch (device resident, no copy), the tcgen05 pass scans only the
+// row tiles at or above the batch (a pair is reported from its lower row), and the exact
+// rescoring keeps `score >= threshold` among partners above the query's own row.
+// Pairs come out ordered by (row of a asc, score desc, row of b asc) -- the order the reference
+// produces when storage lists nodes in insertion order.
+extern "C" cx_status cx_dedup_scan(cx_index* h, float threshold, uint32_t per_node_cap, uint64_t max_pairs,
+                                   uint8_t* out_a_ids, uint8_t* out_b_ids, float* out_score, uint64_t* out_n,
+                                   uint64_t* out_total) {
+  if (!h) return fail(CX_ERR_VALIDATION, "null index");
+  if (!out_n) return fail(CX_ERR_VALIDATION, "null out_n");
+  *out_n = 0;
+  if (out_total) *out_total = 0;
+  if (h->n_live < 2 || !per_node_cap || threshold != threshold) return CX_OK;
+  if (max_pairs && (!out_a_ids || !out_b_ids || !out_score)) return fail(CX_ERR_VALIDATION, "null output buffer");
+  CU(cudaSetDevice(h->device));
+  const uint32_t n_rows = (uint32_t)h->n_rows;
+  const uint32_t kd = per_node_cap < n_rows ? per_node_cap : n_rows;
+  FilterHost fh;
+  build_filter(h, nullptr, &fh);
+  const uint64_t QB = (uint64_t)h->sm_count * 128u;  // one tensor-pass launch group
+  uint64_t n_out = 0, n_tot = 0;
+  std::vector<uint32_t> self(QB);
+  for (uint64_t r0 = 0; r0 < n_rows; r0 += QB) {
+    const uint64_t B = n_rows - r0 < QB ? n_rows - r0 : QB;
+    Plan pl = make_plan(h, B, h->dim, h->ld, kd, true, threshold);
+    if (!pl.thr_fast)
+      return fail(CX_ERR_VALIDATION, "dedup scan needs a threshold >= %.2f and at least 256 rows", THR_FAST_MIN);
+    WsLease lease(h);
+    CU(lease.init());
+    Workspace* ws = lease.ws;
+    SearchBufs sb;
+    const size_t dbytes = carve_bufs(nullptr, h, pl, 0, false, true, &sb) + align_up(B * 4, 256);
+    const ResultBlock rb = ResultBlock::make(B, kd);
+    CU(ws->ensure(dbytes, rb.total + align_up(B * 8, 256)));
+    const size_t used = carve_bufs(ws->d, h, pl, 0, false, true, &sb);
+    uint32_t* d_self = (uint32_t*)((char*)ws->d + used);
+    sb.dQ = h->dE + (size_t)r0 * h->ld;  // the rows are the queries
+    for (uint64_t i = 0; i < B; ++i) self[i] = (uint32_t)(r0 + i);
+    CU(cudaMemcpyAsync(d_self, self.data(), B * 4, cudaMemcpyHostToDevice, ws->stream));
+    PairScan tp;
+    tp.self_rows = d_self;
+    tp.upper_only = true;
+    tp.tile0 = (uint32_t)(r0 / 256);
+    char* h_block = (char*)ws->hp;
+    std::vector<uint64_t> totals(B, 0);
+    cx_status stt = run_search(h, ws, fh, sb, pl, true, threshold, h_block, nullptr, totals.data(), &tp);
+    if (stt != CX_OK) return stt;
+    h->d2h += rb.total;
+    const uint32_t* h_n = (const uint32_t*)(h_block + rb.n);
+    const uint32_t* h_rows = (const uint32_t*)(h_block + rb.rows);
+    const float* h_score = (const float*)(h_block + rb.score);
+    for (uint64_t i = 0; i < B; ++i) {
+      if (h->h_meta[r0 + i] & META_DEAD) continue;  // removed nodes search for nothing (dedup.rs:73-76)
+      n_tot += totals[i];
+      for (uint32_t j = 0; j < h_n[i] && n_out < max_pairs; ++j, ++n_out) {
+        memcpy(out_a_ids + 16 * n_out, h->h_ids.data() + 16 * (r0 + i), 16);
+        memcpy(out_b_ids + 16 * n_out, h->h_ids.data() + 16 * (size_t)h_rows[i * kd + j], 16);
+        out_score[n_out] = h_score[i * kd + j];
+      }
+    }
+  }
+  *out_n = n_out;
+  if (out_total) *out_total = n_tot;
+  return CX_OK;
 }
 
 extern "C" cx_status cx_search_batch_device(cx_index* h, const float* d_queries, uint64_t B, uint64_t k,

@@ -266,6 +266,220 @@ __global__ void __launch_bounds__(SEL_THREADS) select_rescore_kernel(const Selec
   }
 }
 
+// ---------------------------------------------------------------------------------
+// Threshold scans (search_threshold, index.rs:376-388; the dedup scanner's per-node search,
+// linker/dedup.rs:84-86): the pass nominated every row whose approximate cosine reaches
+// threshold - eps.  Here ALL nominees are rescored with reference arithmetic, the exact test
+// `score >= threshold` (index.rs:385) is applied, and the survivors come out ordered by
+// (score desc, row asc).  Because the nominees are a superset of the qualifying rows, the
+// result is exact with no verification step; the only failure is a list that overflowed
+// (ok = 0 -> the host reruns that query on the exact path).
+constexpr int THR_THREADS = 512;
+constexpr int THR_BATCH = 16;
+constexpr uint32_t THR_MAX = 2048;  // survivors that can be ordered in shared memory
+
+struct ThresholdParams {
+  StoreView st;
+  const float* Q;
+  const float* qnorm;    // reference-order norms (launch_prepare_queries)
+  uint32_t ldq, qlen;
+  const uint64_t* keys;  // [nq][cap] nominees (approximate keys; only the row is used)
+  uint32_t* cnt;         // [nq] (re-zeroed on exit)
+  uint64_t* gtau;        // [nq] (re-zeroed on exit)
+  uint32_t cap;
+  float threshold;
+  const uint32_t* self_rows;  // optional [nq]: row to skip (the query's own row), 0xFFFFFFFF = none
+  uint32_t upper_only;        // 1: keep only rows above self_rows[q] (unordered pairs, each once)
+  ResultView rv;         // k = output capacity per query; n = written; ok
+  uint32_t* total;       // [nq] how many qualify
+};
+
+struct ThresholdLayout {
+  size_t q, stage, ekey, edist, escore, idx, total;
+};
+__host__ __device__ inline ThresholdLayout threshold_layout(uint32_t ld) {
+  ThresholdLayout L;
+  size_t o = 0;
+  L.q = o;
+  o += (size_t)ld * 4;
+  L.stage = o;
+  o += (size_t)THR_BATCH * (ld + 1) * 4;
+  o = (o + 7) & ~(size_t)7;
+  L.ekey = o;
+  o += (size_t)THR_MAX * 8;
+  L.edist = o;
+  o += (size_t)THR_MAX * 4;
+  L.escore = o;
+  o += (size_t)THR_MAX * 4;
+  L.idx = o;
+  o += (size_t)THR_MAX * 2;
+  L.total = o;
+  return L;
+}
+
+__global__ void __launch_bounds__(THR_THREADS) threshold_rescore_kernel(const ThresholdParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const ThresholdLayout L = threshold_layout(p.st.ld);
+  float* q_s = reinterpret_cast<float*>(smem_raw + L.q);
+  float* stage = reinterpret_cast<float*>(smem_raw + L.stage);
+  uint64_t* ekey = reinterpret_cast<uint64_t*>(smem_raw + L.ekey);
+  float* edist = reinterpret_cast<float*>(smem_raw + L.edist);
+  float* escore = reinterpret_cast<float*>(smem_raw + L.escore);
+  uint16_t* eidx = reinterpret_cast<uint16_t*>(smem_raw + L.idx);
+  __shared__ uint32_t s_m;
+
+  const uint32_t tid = threadIdx.x, q = blockIdx.x;
+  const uint32_t ld = p.st.ld, dim = p.st.dim;
+  const uint32_t n_app = p.cnt[q];
+  const uint32_t n_src = min(n_app, p.cap);
+  const uint64_t* src = p.keys + (size_t)q * p.cap;
+  const uint32_t self = p.self_rows ? p.self_rows[q] : 0xFFFFFFFFu;
+  if (tid == 0) s_m = 0;
+  for (uint32_t d = tid; d < ld; d += THR_THREADS) q_s[d] = d < p.qlen ? p.Q[(size_t)q * p.ldq + d] : 0.0f;
+  __syncthreads();
+  const float na = p.qnorm[q];
+  const uint32_t warp = tid >> 5, lane = tid & 31, nwarps = THR_THREADS / 32;
+  const uint32_t sstride = ld + 1;
+
+  for (uint32_t base = 0; base < n_src; base += THR_BATCH) {
+    const uint32_t nb = min((uint32_t)THR_BATCH, n_src - base);
+    for (uint32_t j = warp; j < nb; j += nwarps) {
+      const uint32_t row = key_row(src[base + j]);
+      const float* g = p.st.E + (size_t)row * ld;
+      uint32_t d = lane;
+      for (; d + 7 * 32 < ld; d += 8 * 32) {
+        float x[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) x[u] = __ldg(g + d + u * 32);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) stage[j * sstride + d + u * 32] = x[u];
+      }
+      for (; d < ld; d += 32) stage[j * sstride + d] = __ldg(g + d);
+    }
+    __syncthreads();
+    if (tid < nb) {
+      const uint32_t row = key_row(src[base + tid]);
+      const bool wanted = row != self && !(p.upper_only && row < self);
+      if (wanted) {
+        const float* r = stage + tid * sstride;
+        const uint32_t n = p.qlen < dim ? p.qlen : dim;
+        float dot = 0.0f;
+        uint32_t d = 0;
+        for (; d + 8 <= n; d += 8) {
+          float a[8], b[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            a[j] = q_s[d + j];
+            b[j] = r[d + j];
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dot = ref_fold(dot, a[j], b[j]);
+        }
+        for (; d < n; ++d) dot = ref_fold(dot, q_s[d], r[d]);
+        const float nbm = __ldg(p.st.norm + row);
+        const float sim = __fdiv_rn(dot, __fmul_rn(na, nbm));
+        const float dist = __fsub_rn(1.0f, sim);
+        const float sc = ref_score_from_distance(dist);
+        if (sc >= p.threshold) {  // index.rs:385 (false for NaN)
+          const uint32_t pos = atomicAdd(&s_m, 1u);
+          if (pos < THR_MAX) {
+            ekey[pos] = make_key(ord_from_score(sc), row);
+            edist[pos] = dist;
+            escore[pos] = sc;
+            eidx[pos] = (uint16_t)pos;
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  const uint32_t M = s_m;
+  const bool ok = n_app <= p.cap && M <= THR_MAX;
+  if (ok && M) {
+    // order (key, idx) by key descending: bitonic network over a power of two, padded with 0
+    uint32_t NK = 2;
+    while (NK < M) NK <<= 1;
+    for (uint32_t i = M + tid; i < NK; i += THR_THREADS) {
+      ekey[i] = 0ull;
+      eidx[i] = 0;
+    }
+    __syncthreads();
+    for (uint32_t k = 2; k <= NK; k <<= 1) {
+      for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+        for (uint32_t i = tid; i < NK; i += THR_THREADS) {
+          const uint32_t l = i ^ j;
+          if (l > i) {
+            const uint64_t x = ekey[i], y = ekey[l];
+            const bool desc_block = (i & k) == 0;
+            if (desc_block ? (x < y) : (x > y)) {
+              ekey[i] = y;
+              ekey[l] = x;
+              const uint16_t t = eidx[i];
+              eidx[i] = eidx[l];
+              eidx[l] = t;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    }
+    const uint32_t n_out = min(M, p.rv.k);
+    for (uint32_t i = tid; i < n_out; i += THR_THREADS) {
+      const size_t o = (size_t)q * p.rv.k + i;
+      const uint32_t row = key_row(ekey[i]);
+      const uint32_t e = eidx[i];
+      p.rv.rows[o] = row;
+      p.rv.score[o] = escore[e];
+      p.rv.dist[o] = edist[e];
+      if (p.rv.ids)
+        *reinterpret_cast<uint4*>(p.rv.ids + o * 16) = *reinterpret_cast<const uint4*>(p.st.ids + (size_t)row * 16);
+    }
+  }
+  if (tid == 0) {
+    p.rv.n[q] = ok ? min(M, p.rv.k) : 0u;
+    p.rv.ok[q] = ok ? 1u : 0u;
+    if (p.total) p.total[q] = ok ? M : 0u;
+    p.cnt[q] = 0;
+    p.gtau[q] = 0ull;
+  }
+}
+
+cudaError_t launch_threshold_rescore(const StoreView& st, const QueryView& qv, uint32_t q0, uint32_t nq,
+                                     const CandView& cv, const ResultView& rv, uint32_t* total, float threshold,
+                                     const uint32_t* self_rows, bool upper_only, cudaStream_t s) {
+  if (!nq) return cudaSuccess;
+  ThresholdParams p;
+  p.st = st;
+  p.Q = qv.Q + (size_t)q0 * qv.ldq;
+  p.qnorm = qv.qnorm + q0;
+  p.ldq = qv.ldq;
+  p.qlen = qv.qlen;
+  p.keys = cv.keys + (size_t)(q0 - cv.q_base) * cv.cap;
+  p.cnt = cv.cnt + q0;
+  p.gtau = cv.gtau + q0;
+  p.cap = cv.cap;
+  p.threshold = threshold;
+  p.self_rows = self_rows ? self_rows + q0 : nullptr;
+  p.upper_only = upper_only ? 1u : 0u;
+  p.rv = rv;
+  p.rv.rows += (size_t)q0 * rv.k;
+  p.rv.score += (size_t)q0 * rv.k;
+  p.rv.dist += (size_t)q0 * rv.k;
+  if (p.rv.ids) p.rv.ids += (size_t)q0 * rv.k * 16;
+  p.rv.n += q0;
+  p.rv.ok += q0;
+  p.total = total ? total + q0 : nullptr;
+  const size_t smem = threshold_layout(st.ld).total;
+  if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
+  cudaError_t e =
+      cudaFuncSetAttribute(threshold_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  threshold_rescore_kernel<<<nq, THR_THREADS, smem, s>>>(p);
+  return cudaGetLastError();
+}
+size_t threshold_rescore_smem(uint32_t ld) { return threshold_layout(ld).total; }
+
 size_t select_smem(uint32_t cap, uint32_t ld) {
   (void)cap;
   return select_layout(ld).total + 2048;

@@ -46,6 +46,11 @@ struct StreamParams {
   uint32_t cap;
   const uint32_t* qmap;  // optional: pass-local query b is query qmap[b] (Q row, cnt, gtau); its list slot stays b
   uint32_t G, KP, C, n_tiles, stages, kslice, n_slices;
+  // threshold mode (search_threshold, index.rs:376-388): instead of a running top-KP cut-off every
+  // row whose approximate cosine reaches thr_cos is nominated; full lists are flushed, not compacted
+  uint32_t thr_mode;
+  float thr_cos;         // threshold minus the pass's error bound, in cosine units
+  const float* qnorm;    // |q| per query (keys are cosine * |q|)
 };
 
 template <int NV>
@@ -142,7 +147,13 @@ __global__ void __launch_bounds__(SC_THREADS, 1) stream_scan_kernel(const Stream
     q_s[i] = (b < p.nq_valid) ? p.Q[(size_t)(p.qmap ? p.qmap[b] : b) * p.ldq + d] : 0.0f;
   }
   for (uint32_t i = tid; i < NQ; i += SC_THREADS) {
-    tau_s[i] = 0;
+    uint64_t t0 = 0;
+    if (p.thr_mode && i < p.nq_valid) {
+      // fixed cut-off: the largest key BELOW every key whose score is thr_cos * |q| or more
+      const float t = p.thr_cos * p.qnorm[p.qmap ? p.qmap[i] : i];
+      t0 = t == t ? ((uint64_t)ord_from_float(t) << 32) - 1ull : ~0ull;  // NaN norm: nominate nothing
+    }
+    tau_s[i] = t0;
     cnt_s[i] = 0;
     cur_s[i] = 0;
   }
@@ -227,6 +238,24 @@ __global__ void __launch_bounds__(SC_THREADS, 1) stream_scan_kernel(const Stream
         if (t > tau_s[b]) tau_s[b] = t;
       }
     }
+    csync();
+  };
+
+  // threshold mode: move list[b] to the query's merged list and start over
+  auto flush = [&](uint32_t b) {
+    csync();
+    const uint32_t raw = cnt_s[b], n = min(raw, C);
+    // a list that overran between two checkpoints lost keys: poison the count so that the
+    // rescoring kernel reports an overflow (cannot happen while C >= 2 * SC_QUAD * SC_TILE_ROWS)
+    if (ctid == 0) flag_s[2] = n ? atomicAdd(p.cnt + gq(b), n + (raw > C ? 0x40000000u : 0u)) : 0;
+    csync();
+    const uint32_t base = flag_s[2];
+    const uint64_t* src = list_s + ((size_t)b * 2 + cur_s[b]) * C;
+    uint64_t* out = p.keys + (size_t)b * p.cap;
+    for (uint32_t j = ctid; j < n; j += SC_CT)
+      if (base + j < p.cap) out[base + j] = src[j];  // excess is dropped; cnt > cap tells the rescoring kernel
+    csync();
+    if (ctid == 0) cnt_s[b] = 0;
     csync();
   };
 
@@ -318,21 +347,29 @@ __global__ void __launch_bounds__(SC_THREADS, 1) stream_scan_kernel(const Stream
     // checkpoint after the last tile of every full quad (tile i%4 == 2 for group 0, 3 for group 1)
     if ((i % SC_QUAD) == (SC_QUAD - SC_GROUPS + grp) && (i / SC_QUAD) < n_quads) {
       csync();
-      if (ctid < NQ) {
+      if (ctid < NQ && !p.thr_mode) {
         const uint64_t g = *((volatile uint64_t*)(p.gtau + gq(ctid)));
         if (g > tau_s[ctid]) tau_s[ctid] = g;
       }
       if (ctid == 0) {
         uint32_t m = 0;
         for (uint32_t b = 0; b < NQ; ++b)
-          if (cnt_s[b] >= 2 * KP || cnt_s[b] + SC_QUAD * SC_TILE_ROWS > C) m |= 1u << b;
+          if ((!p.thr_mode && cnt_s[b] >= 2 * KP) || cnt_s[b] + SC_QUAD * SC_TILE_ROWS > C) m |= 1u << b;
         *flag_s = m;
       }
       csync();
       const uint32_t m = *flag_s;
       for (uint32_t b = 0; b < NQ; ++b)
-        if (m & (1u << b)) compact(b);
+        if (m & (1u << b)) {
+          if (p.thr_mode) flush(b);
+          else compact(b);
+        }
     }
+  }
+
+  if (p.thr_mode) {
+    for (uint32_t b = 0; b < p.nq_valid; ++b) flush(b);
+    return;
   }
 
   // final: rank every list and append the part that can still matter -- keys at or
@@ -425,7 +462,7 @@ static cudaError_t launch_nq(const StreamParams& p, size_t smem, cudaStream_t s)
 
 cudaError_t launch_stream_scan(const StoreView& st, const QueryView& qv, uint32_t q0, uint32_t nq_pass,
                                const DevFilter& flt, const CandView& cv, int sm_count, cudaStream_t s,
-                               const uint32_t* qmap) {
+                               const uint32_t* qmap, const float* thr_cos) {
   if (!st.n_rows || !nq_pass) return cudaSuccess;
   if (qmap && q0 != 0) return cudaErrorInvalidValue;
   if (nq_pass > 8) return cudaErrorInvalidValue;
@@ -440,6 +477,9 @@ cudaError_t launch_stream_scan(const StoreView& st, const QueryView& qv, uint32_
   p.KP = cv.KP;
   p.cap = cv.cap;
   p.qmap = qmap;
+  p.thr_mode = thr_cos ? 1u : 0u;
+  p.thr_cos = thr_cos ? *thr_cos : 0.0f;
+  p.qnorm = qmap ? qv.qnorm : qv.qnorm + q0;
   p.keys = cv.keys + (size_t)(q0 - cv.q_base) * cv.cap;
   p.cnt = cv.cnt + q0;
   p.gtau = cv.gtau + q0;

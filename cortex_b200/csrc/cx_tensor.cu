@@ -66,6 +66,8 @@ struct TensorParams {
   uint32_t stages;
   uint32_t mode;
   uint32_t check_rows;  // 0: no filter and no removed rows -> skip the per-row metadata test
+  uint32_t static_tau;  // threshold scans: the cut-off in gtau is fixed; a full private list is flushed to the
+                        // query's merged list instead of being cut to its best KP
   uint32_t debug;       // measurement hook (results become wrong): 1 = epilogue only releases the
                         // accumulator, 2 = epilogue loads and masks but never handles a hit
   uint32_t KP;
@@ -491,6 +493,16 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         if (__any_sync(0xffffffffu, hit)) {
           // make room first: a chunk can append up to 32 keys
           uint32_t full = __ballot_sync(0xffffffffu, cnt + 32 > LIST_CAP);
+          if (p.static_tau) {
+            if (cnt + 32 > LIST_CAP) {
+              const uint32_t pos = atomicAdd(p.cnt + q, cnt);
+              uint64_t* out = p.keys + (size_t)q * p.cap;
+              for (uint32_t i = 0; i < cnt; ++i)
+                if (pos + i < p.cap) out[pos + i] = myL[i];
+              cnt = 0;
+            }
+            full = 0;
+          }
           while (full) {
             const uint32_t l = __ffs(full) - 1;
             full &= full - 1;
@@ -720,7 +732,7 @@ void tensor_set_debug(int mode) {
 
 static cudaError_t launch_mode(const StoreView& st, const void* Q16, uint32_t q0, uint32_t nq, const DevFilter& flt,
                                bool check_rows, const CandView& cv, uint64_t* lists, float* dump, uint32_t n_slots,
-                               uint32_t tile0, uint32_t mode, int sm_count, cudaStream_t s) {
+                               uint32_t tile0, uint32_t mode, int sm_count, cudaStream_t s, bool static_tau = false) {
   const uint32_t n_tiles_q = (nq + TC_BM - 1) / TC_BM;
   if (n_tiles_q > (uint32_t)sm_count) return cudaErrorInvalidValue;  // caller splits larger batches
   // two or more query tiles: CTA pairs (each pair = two query tiles walking the same rows)
@@ -751,6 +763,7 @@ static cudaError_t launch_mode(const StoreView& st, const void* Q16, uint32_t q0
   p.mode = mode;
   p.check_rows = check_rows ? 1u : 0u;
   p.debug = mode == TC_MODE_SCAN ? (uint32_t)g_tensor_debug : 0u;
+  p.static_tau = static_tau ? 1u : 0u;
   p.KP = cv.KP;
   p.meta = st.meta;
   p.agent = st.agent;
@@ -786,9 +799,19 @@ cudaError_t launch_tensor_bootstrap(const StoreView& st, const void* Q16, uint32
 
 cudaError_t launch_tensor_scan(const StoreView& st, const void* Q16, uint32_t q0, uint32_t nq,
                                const DevFilter& flt, bool check_rows, const CandView& cv, uint64_t* lists,
-                               uint32_t tile0, uint32_t n_tiles, int sm_count, cudaStream_t s) {
+                               uint32_t tile0, uint32_t n_tiles, int sm_count, cudaStream_t s, bool static_tau) {
   if (!nq || !st.n_rows || !n_tiles) return cudaSuccess;
-  return launch_mode(st, Q16, q0, nq, flt, check_rows, cv, lists, nullptr, n_tiles, tile0, TC_MODE_SCAN, sm_count, s);
+  return launch_mode(st, Q16, q0, nq, flt, check_rows, cv, lists, nullptr, n_tiles, tile0, TC_MODE_SCAN, sm_count, s,
+                     static_tau);
+}
+
+// gtau[q] = the largest key below every key whose approximate cosine is thr_cos or more
+__global__ void fill_tau_kernel(uint64_t* __restrict__ gtau, uint32_t nq, float thr_cos) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nq) gtau[i] = ((uint64_t)ord_from_float(thr_cos) << 32);
+}
+void launch_fill_tau(const CandView& cv, uint32_t q0, uint32_t nq, float thr_cos, cudaStream_t s) {
+  if (nq) fill_tau_kernel<<<(nq + 255) / 256, 256, 0, s>>>(cv.gtau + q0, nq, thr_cos);
 }
 
 uint32_t tensor_tiles(uint32_t n_rows) { return (n_rows + TC_BN - 1) / TC_BN; }

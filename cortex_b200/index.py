@@ -216,6 +216,38 @@ class GpuVectorIndex:
             cap = int(total.value)
         return [SimilarityResult(ids[i].tobytes(), float(sc[i]), float(di[i])) for i in range(n.value)]
 
+    def search_threshold_batch_arrays(self, queries: np.ndarray, threshold: float, cap: int,
+                                      filter: Optional[VectorFilter] = None):
+        """search_threshold for B queries at once.  Returns ids [B,cap,16], score [B,cap],
+        distance [B,cap], n [B] (entries written), total [B] (rows that qualify)."""
+        Q = np.ascontiguousarray(queries, dtype=np.float32)
+        if Q.ndim != 2:
+            raise CortexError("queries must be [B, dim]")
+        B, qlen = Q.shape
+        cap = max(1, int(cap))
+        ids = np.zeros((B, cap, 16), np.uint8)
+        sc = np.zeros((B, cap), np.float32)
+        di = np.zeros((B, cap), np.float32)
+        n = np.zeros(B, np.uint64)
+        total = np.zeros(B, np.uint64)
+        cf = _c_filter(filter)
+        _check(self._L.cx_search_threshold_batch(self._h, Q.ctypes.data, B, qlen, C.c_float(threshold),
+                                                 cf.ptr if cf else None, cap, ids.ctypes.data, sc.ctypes.data,
+                                                 di.ctypes.data, n.ctypes.data, total.ctypes.data))
+        return ids, sc, di, n, total
+
+    def dedup_scan(self, threshold: float, per_node_cap: int = 64, max_pairs: int = 1 << 20):
+        """DedupScanner::scan's similarity step (linker/dedup.rs:65-127) as one self-join.
+        Returns (a_ids [P,16], b_ids [P,16], score [P], total) -- every unordered pair once,
+        a inserted before b, ordered by (a, score desc, b)."""
+        a = np.zeros((max_pairs, 16), np.uint8)
+        b = np.zeros((max_pairs, 16), np.uint8)
+        sc = np.zeros(max_pairs, np.float32)
+        n, total = C.c_uint64(0), C.c_uint64(0)
+        _check(self._L.cx_dedup_scan(self._h, C.c_float(threshold), int(per_node_cap), int(max_pairs), a.ctypes.data,
+                                     b.ctypes.data, sc.ctypes.data, C.byref(n), C.byref(total)))
+        return a[:n.value], b[:n.value], sc[:n.value], int(total.value)
+
     def search_batch_arrays(self, queries: np.ndarray, k: int, filter: Optional[VectorFilter] = None
                             ) -> Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]:
         """Array form: ids [B,k,16], score [B,k], distance [B,k], n [B]."""

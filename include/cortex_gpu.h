@@ -103,6 +103,21 @@ cx_status cx_search(cx_index* h, const float* query, uint32_t qlen, uint64_t k, 
 cx_status cx_search_threshold(cx_index* h, const float* query, uint32_t qlen, float threshold,
                               const cx_filter* filter, uint64_t cap, uint8_t* out_ids, float* out_score,
                               float* out_distance, uint64_t* out_n, uint64_t* out_total);
+/* search_threshold for B queries at once (the call the dedup scanner and the link rules make
+ * once per node, linker/dedup.rs:84-86): outputs are [B][cap], out_n[b] entries written,
+ * out_total[b] rows qualify. */
+cx_status cx_search_threshold_batch(cx_index* h, const float* queries, uint64_t B, uint32_t qlen, float threshold,
+                                    const cx_filter* filter, uint64_t cap, uint8_t* out_ids, float* out_score,
+                                    float* out_distance, uint64_t* out_n, uint64_t* out_total);
+/* DedupScanner::scan, linker/dedup.rs:65-127, as one self-join: every live node runs
+ * search_threshold(own embedding, threshold), skips itself and reports each unordered pair
+ * once.  At most per_node_cap partners per node and max_pairs pairs are written (a-id, b-id,
+ * score), ordered by (insertion order of a, score desc, insertion order of b) with a inserted
+ * before b; *out_total = pairs that qualify.  Choosing merge / supersede / link for a pair
+ * (determine_action, :130-171) needs graph degrees and stays with the caller. */
+cx_status cx_dedup_scan(cx_index* h, float threshold, uint32_t per_node_cap, uint64_t max_pairs,
+                        uint8_t* out_a_ids, uint8_t* out_b_ids, float* out_score, uint64_t* out_n,
+                        uint64_t* out_total);
 /* VectorIndex::search_batch, index.rs:390-410.  queries is [B][qlen] row-major;
  * outputs are [B][k] (ids [B][k][16]); out_n[b] = results of query b.  The caller
  * keys the result map by its own query ids. */
