@@ -5,6 +5,8 @@ Writes one JSON document (default profiles/results_r1.json) with a section per c
   cfg1  10k x 384, 100 queries, top-10: GPU vs CPU oracle, ids/score bits compared
   cfg2  1M x 384, query batch sweep 1..1024, top-10: queries/s, kernel roofline per batch
   cfg3  auto-link cycle: B new nodes x N-row corpus, k=100 (+ threshold 0.75): scored pairs/s
+  dedup the dedup scanner's self-join over 1M rows at threshold 0.92
+  hnsw  recall@10 / @100 of the reference's approximate path (restated on the CPU) against the exact result
   cfg5  streaming ingest: 256-node batches searched (k=100) then appended to a growing corpus,
         p50/p99 latency per batch
 cfg4 (50M x 1024 bf16 on 8 GPUs) is not run: see DESIGN.md §8.
@@ -223,6 +225,63 @@ def cfg5(torch, out, final_rows):
                                                     "n": len(v)} for m, v in lat.items() if v}}
 
 
+def dedup(torch, out, rows):
+    """dedup self-join (linker/dedup.rs:65-127): every node's search_threshold(0.92) as one scan of the
+    upper triangle of E.E^T; unit of work = unordered (node, node) pair scored."""
+    from cortex_b200 import GpuVectorIndex
+
+    dev = torch.device("cuda", 0)
+    ix = GpuVectorIndex(384)
+    ix.reserve(rows)
+    c = bench.make_corpus_torch(rows, 384, bench.SEED + 77, dev)
+    ix.insert_batch_device(ids_for(rows), c)
+    del c
+    torch.cuda.empty_cache()
+    ix.dedup_scan(0.92, per_node_cap=64, max_pairs=4 << 20)  # warm-up (workspace allocation)
+    t0 = time.perf_counter()
+    a, b, sc, total = ix.dedup_scan(0.92, per_node_cap=64, max_pairs=4 << 20)
+    dt = time.perf_counter() - t0
+    pairs = rows * (rows - 1) / 2.0
+    pk = bench.peaks()
+    tf = 2.0 * 384 * pairs / dt / 1e12
+    out["dedup"] = {"workload": f"dedup self-join over {rows} x 384 rows, threshold 0.92, host call (ids out)",
+                    "seconds": dt, "unordered_pairs_scored_per_s": pairs / dt, "tflops_upper_triangle": tf,
+                    "frac_of_sustained_bf16": tf / pk["bf16_tflops_sustained"], "duplicate_pairs": int(total),
+                    "pairs_returned": int(len(a)), "paths": ix.stats()}
+
+
+def hnsw(torch, out, rows, n_queries):
+    """The reference's approximate path (HnswIndex::search after rebuild, index.rs:342-373) restated on the
+    CPU (oracle/hnsw_oracle.c -- parity unpinned, parameters unverified): recall@k against the exact
+    result, which is what this library returns."""
+    from cortex_b200 import GpuVectorIndex
+    from oracle.binding import OracleHnsw
+
+    corpus = bench.make_corpus_torch(rows, 384, bench.SEED + 9, "cpu").numpy()
+    Q = bench.make_queries_torch(torch.from_numpy(corpus), n_queries, bench.SEED + 9).numpy()
+    g = GpuVectorIndex(384)
+    g.insert_batch(ids_for(rows), corpus)
+    t0 = time.perf_counter()
+    hn = OracleHnsw(corpus)
+    t_build = time.perf_counter() - t0
+    res = {"workload": f"{rows} x 384, {n_queries} queries; HNSW restated with M=32, ef_construction=100, "
+                       f"ef_search=100 (instant-distance defaults from memory, unverified)",
+           "build_s_single_thread": t_build}
+    for k in (10, 100):
+        ids, sc, di, n = g.search_batch_arrays(Q, k)
+        exact_rows = ids[:, :, 8:].copy().view(">u8").reshape(n_queries, k).astype(np.int64)
+        hit = 0
+        t0 = time.perf_counter()
+        got = [hn.search(q, k)[0] for q in Q]
+        dt = time.perf_counter() - t0
+        for b in range(n_queries):
+            hit += len(set(int(x) for x in got[b]) & set(int(x) for x in exact_rows[b, :int(n[b])]))
+        res[f"recall@{k}"] = hit / float(n.sum())
+        res[f"cpu_hnsw_queries_per_s_k{k}"] = n_queries / dt
+        res[f"results_returned_per_query_k{k}"] = float(np.mean([len(x) for x in got]))
+    out["hnsw"] = res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "results_r1.json"))
@@ -231,6 +290,8 @@ def main():
     ap.add_argument("--cfg3-rows", type=int, default=10_000_000)
     ap.add_argument("--cfg3-new", type=int, default=100_000)
     ap.add_argument("--cfg5-rows", type=int, default=5_000_000)
+    ap.add_argument("--dedup-rows", type=int, default=1_000_000)
+    ap.add_argument("--hnsw-rows", type=int, default=10_000)
     a = ap.parse_args()
     import torch
 
@@ -253,6 +314,13 @@ def main():
     if "5" in only:
         cfg5(torch, out, a.cfg5_rows)
         print("cfg5", json.dumps(out["cfg5"]), file=sys.stderr)
+    if "dedup" in only:
+        dedup(torch, out, a.dedup_rows)
+        print("dedup", json.dumps(out["dedup"]), file=sys.stderr)
+        torch.cuda.empty_cache()
+    if "hnsw" in only:
+        hnsw(torch, out, a.hnsw_rows, 200)
+        print("hnsw", json.dumps(out["hnsw"]), file=sys.stderr)
     os.makedirs(os.path.dirname(a.out), exist_ok=True)
     with open(a.out, "w") as fp:
         json.dump(out, fp, indent=1)

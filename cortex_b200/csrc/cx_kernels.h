@@ -113,8 +113,8 @@ cudaError_t launch_tensor_scan(const StoreView& st, const void* Q16, uint32_t q0
 // Threshold scans: fix every query's cut-off at the approximate cosine thr_cos (then scan with static_tau).
 void launch_fill_tau(const CandView& cv, uint32_t q0, uint32_t nq, float thr_cos, cudaStream_t s);
 uint32_t tensor_tiles(uint32_t n_rows);
-// Between phases: raise each query's cut-off to the cv.KP-th best key nominated so far.
-cudaError_t launch_tau_refine(const CandView& cv, uint32_t q0, uint32_t nq, cudaStream_t s);
+// Between phases: raise each query's cut-off to the cv.KP-th best score nominated so far minus `margin`.
+cudaError_t launch_tau_refine(const CandView& cv, uint32_t q0, uint32_t nq, float margin, cudaStream_t s);
 
 // Exact path: every row scored with reference arithmetic -> keys[n_rows] for one query
 void launch_exact_keys(const StoreView& st, const QueryView& qv, uint32_t q, const DevFilter& flt,

@@ -430,7 +430,7 @@ cx_status run_search(cx_index* h, Workspace* ws, const FilterHost& fh, const Sea
         uint32_t tile0 = 0;
         for (size_t ph = 0; ph < phases.size(); ++ph) {
           if (ph) {  // tighten the cut-off with what the earlier phases found
-            CU(launch_tau_refine(cv, (uint32_t)q0, nq, s));
+            CU(launch_tau_refine(cv, (uint32_t)q0, nq, 2.0f * eps_tensor(h->dim), s));
             h->launches += 1;
           }
           CU(launch_tensor_scan(st, sb.q16, (uint32_t)q0, nq, flt, check_rows, cv, sb.lists, tile0, phases[ph],

@@ -126,7 +126,10 @@ __global__ void __launch_bounds__(SEL_THREADS) select_rescore_kernel(const Selec
       const uint64_t key = src[i];
       return key >= gt ? key_ord(key) : 0u;
     };
-    cut = block_kth_largest(get, n_src, min(p.KP, n_src), scratch, rstage, SEL_STAGE, tid, SEL_THREADS);
+    // keep twice the rescore count (at most what can be rescored at all): the +-eps band around
+    // the k-th result may have to be rescored too (step 3), and it lies below the KP-th key
+    const uint32_t n_keep = min(min(2 * p.KP, (uint32_t)SEL_MAX_KS), n_src);
+    cut = block_kth_largest(get, n_src, n_keep, scratch, rstage, SEL_STAGE, tid, SEL_THREADS);
     const unsigned long long left = (unsigned long long)cut << 32;  // what is left behind scores below `cut`
     if (left > U) U = left;
   }

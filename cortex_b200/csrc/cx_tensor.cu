@@ -820,9 +820,11 @@ uint32_t tensor_tiles(uint32_t n_rows) { return (n_rows + TC_BN - 1) / TC_BN; }
 // The merged list of a query holds every row scanned so far whose score cleared the cut-off in
 // force when it was seen; the KP-th best of them is a (much tighter) lower bound of the KP-th
 // best over the whole corpus, so the next phase nominates far fewer rows.
+// `margin` (cosine units, twice the pass's error bound) is subtracted so that the list keeps every row
+// inside the +-eps band around the k-th result, which the select kernel may have to rescore.
 __global__ void __launch_bounds__(256) tau_refine_kernel(const uint64_t* __restrict__ keys,
                                                          const uint32_t* __restrict__ cnt, uint32_t cap, uint32_t KP,
-                                                         uint64_t* __restrict__ gtau) {
+                                                         float margin, uint64_t* __restrict__ gtau) {
   __shared__ uint32_t scratch[260];
   __shared__ uint32_t stage[4096];
   const uint32_t q = blockIdx.x, tid = threadIdx.x;
@@ -832,15 +834,15 @@ __global__ void __launch_bounds__(256) tau_refine_kernel(const uint64_t* __restr
   auto get = [&](uint32_t i) { return key_ord(k[i]); };
   const uint32_t t = block_kth_largest(get, n, KP, scratch, stage, 4096u, tid, 256);
   if (tid == 0) {
-    const uint64_t nt = (uint64_t)t << 32;  // the lowest key with that score
+    const uint64_t nt = (uint64_t)ord_from_float(float_from_ord(t) - margin) << 32;  // the lowest key with that score
     if (nt > gtau[q]) gtau[q] = nt;
   }
 }
 
-cudaError_t launch_tau_refine(const CandView& cv, uint32_t q0, uint32_t nq, cudaStream_t s) {
+cudaError_t launch_tau_refine(const CandView& cv, uint32_t q0, uint32_t nq, float margin, cudaStream_t s) {
   if (!nq) return cudaSuccess;
   tau_refine_kernel<<<nq, 256, 0, s>>>(cv.keys + (size_t)(q0 - cv.q_base) * cv.cap, cv.cnt + q0, cv.cap, cv.KP,
-                                       cv.gtau + q0);
+                                       margin, cv.gtau + q0);
   return cudaGetLastError();
 }
 
