@@ -9,7 +9,7 @@ Writes one JSON document (default profiles/results_r1.json) with a section per c
   hnsw  recall@10 / @100 of the reference's approximate path (restated on the CPU) against the exact result
   cfg5  streaming ingest: 256-node batches searched (k=100) then appended to a growing corpus,
         p50/p99 latency per batch
-cfg4 (50M x 1024 bf16 on 8 GPUs) is not run: see DESIGN.md §8.
+  cfg4  one GPU's shard (6.25M rows) of the 50M x 1024-d corpus, batch 256, top-100
 All timing is CUDA events on the caller's stream around the public device API.
 """
 from __future__ import annotations
@@ -225,6 +225,49 @@ def cfg5(torch, out, final_rows):
                                                     "n": len(v)} for m, v in lat.items() if v}}
 
 
+def cfg4(torch, out, rows, batch):
+    """large-embedding search: one GPU's shard of the 50M x 1024-d corpus (50M / 8 = 6.25M rows), top-100,
+    batch 256.  The tensor pass scans the bf16 copy (rows x 1024 x 2 bytes per batch); the fp32 rows stay
+    resident for the exact rescoring.  At B=256 this sits at the HBM / tensor ridge."""
+    from cortex_b200 import GpuVectorIndex
+
+    dev = torch.device("cuda", 0)
+    ix = GpuVectorIndex(1024)
+    ix.reserve(rows)
+    chunk = 500_000
+    q = None
+    for s0 in range(0, rows, chunk):
+        n = min(chunk, rows - s0)
+        c = bench.make_corpus_torch(n, 1024, bench.SEED + 41 * (s0 // chunk), dev)
+        ix.insert_batch_device(ids_for(n, s0), c)
+        if q is None:
+            q = bench.make_queries_torch(c, batch, bench.SEED + 4)
+        del c
+    torch.cuda.empty_cache()
+    ix.set_option("profile", 1)
+    s = torch.cuda.current_stream().cuda_stream
+    buf = [None]
+
+    def step():
+        buf[0] = ix.search_batch_device(q, 100, stream=s, out=buf[0])
+
+    step()
+    st0 = ix.stats()
+    ms = timed(step, 10, 2, torch)
+    st1 = ix.stats()
+    pk = bench.peaks()
+    us = (st1["pass_kernel_ns"] - st0["pass_kernel_ns"]) * 1e-3 / max(1, st1["pass_kernel_launches"] - st0["pass_kernel_launches"])
+    shadow_bytes = rows * 1024 * 2
+    tf = 2.0 * 1024 * batch * rows / (us * 1e-6) / 1e12
+    out["cfg4"] = {"workload": f"one shard of cfg4: {rows} x 1024-d (bf16 copy scanned, fp32 kept for rescoring), "
+                               f"batch {batch}, top-100", "ms_per_batch": ms, "queries_per_s": batch / (ms * 1e-3),
+                   "scan_us": us, "shadow_stream_gbs": shadow_bytes / (us * 1e-6) / 1e9,
+                   "frac_of_measured_hbm": shadow_bytes / (us * 1e-6) / 1e9 / pk["hbm_gbs"], "tflops": tf,
+                   "frac_of_sustained_bf16": tf / pk["bf16_tflops_sustained"],
+                   "fallbacks": st1["fallbacks"] - st0["fallbacks"],
+                   "tensor_queries": st1["queries_tensor"] - st0["queries_tensor"]}
+
+
 def dedup(torch, out, rows):
     """dedup self-join (linker/dedup.rs:65-127): every node's search_threshold(0.92) as one scan of the
     upper triangle of E.E^T; unit of work = unordered (node, node) pair scored."""
@@ -285,11 +328,12 @@ def hnsw(torch, out, rows, n_queries):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "profiles", "results_r1.json"))
-    ap.add_argument("--only", default="1,2,3,5")
+    ap.add_argument("--only", default="1,2,3,4,dedup,hnsw,5")
     ap.add_argument("--cfg2-rows", type=int, default=1_000_000)
     ap.add_argument("--cfg3-rows", type=int, default=10_000_000)
     ap.add_argument("--cfg3-new", type=int, default=100_000)
     ap.add_argument("--cfg5-rows", type=int, default=5_000_000)
+    ap.add_argument("--cfg4-rows", type=int, default=6_250_000)
     ap.add_argument("--dedup-rows", type=int, default=1_000_000)
     ap.add_argument("--hnsw-rows", type=int, default=10_000)
     a = ap.parse_args()
@@ -314,6 +358,10 @@ def main():
     if "5" in only:
         cfg5(torch, out, a.cfg5_rows)
         print("cfg5", json.dumps(out["cfg5"]), file=sys.stderr)
+    if "4" in only:
+        cfg4(torch, out, a.cfg4_rows, 256)
+        print("cfg4", json.dumps(out["cfg4"]), file=sys.stderr)
+        torch.cuda.empty_cache()
     if "dedup" in only:
         dedup(torch, out, a.dedup_rows)
         print("dedup", json.dumps(out["dedup"]), file=sys.stderr)

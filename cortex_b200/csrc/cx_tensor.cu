@@ -272,15 +272,19 @@ __device__ unsigned long long g_tensor_clock[2];
 // traffic and the shared-memory reads of the E operand (the binding limits of the
 // single-CTA form: 64 B/clk of TMA writes + 96 B/clk of MMA operand reads against
 // 128 B/clk of shared-memory bandwidth).
-template <bool PAIR, int EW>
+// QRES = the CTA's query tile stays resident in shared memory for the whole pass (dimensions up to
+// 640); otherwise (large embeddings, e.g. 1024-d) every ring stage carries the matching [128 x 64]
+// chunk of the query tile next to the chunk of E, re-read from L2 for every row tile.
+template <bool PAIR, int EW, bool QRES>
 __global__ void __launch_bounds__((TC_CTRL_WARPS + EW) * 32, 1)
 tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmE,
                    const TensorParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  constexpr uint32_t STAGE_BYTES = tc_stage_bytes(PAIR);
+  constexpr uint32_t E_BYTES = tc_stage_bytes(PAIR);                           // E part of a stage
+  constexpr uint32_t STAGE_BYTES = E_BYTES + (QRES ? 0u : TC_QCHUNK_BYTES);  // [E chunk][Q chunk]
   const uint32_t S = p.stages;
   unsigned char* sQ = smem;
-  unsigned char* sE = smem + (size_t)p.n_kc * TC_QCHUNK_BYTES;
+  unsigned char* sE = smem + (QRES ? (size_t)p.n_kc * TC_QCHUNK_BYTES : 0);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sE + (size_t)S * STAGE_BYTES);
   const uint32_t bar_q = smem_u32(bars);
   const uint32_t bar_full = smem_u32(bars + 1);
@@ -335,9 +339,12 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0 && n_my) {
       if (!PAIR) {
-        mbar_arrive_expect_tx(bar_q, p.n_kc * TC_QCHUNK_BYTES);
-        for (uint32_t kc = 0; kc < p.n_kc; ++kc)
-          tma_load_2d(smem_u32(sQ + (size_t)kc * TC_QCHUNK_BYTES), &tmQ, (int)(kc * TC_BK), (int)(qt * TC_BM), bar_q);
+        if (QRES) {
+          mbar_arrive_expect_tx(bar_q, p.n_kc * TC_QCHUNK_BYTES);
+          for (uint32_t kc = 0; kc < p.n_kc; ++kc)
+            tma_load_2d(smem_u32(sQ + (size_t)kc * TC_QCHUNK_BYTES), &tmQ, (int)(kc * TC_BK), (int)(qt * TC_BM),
+                        bar_q);
+        }
         uint32_t it = 0;
         for (uint32_t ti = 0; ti < n_my; ++ti) {
           const int row0 = (int)(tile_of(s_begin + ti) * TC_BN);
@@ -351,17 +358,22 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             mbar_arrive_expect_tx(bar_full + 8 * stage, STAGE_BYTES);
             tma_load_2d(smem_u32(sE + (size_t)stage * STAGE_BYTES), &tmE, (int)(kc * TC_BK), row0,
                         bar_full + 8 * stage);
+            if (!QRES)
+              tma_load_2d(smem_u32(sE + (size_t)stage * STAGE_BYTES + E_BYTES), &tmQ, (int)(kc * TC_BK),
+                          (int)(qt * TC_BM), bar_full + 8 * stage);
           }
         }
       } else {
         // both CTAs load; every transfer completes on the LEADER's barrier, which the leader
         // arms with the bytes of both halves.  A CTA reuses a stage when its own empty barrier
         // (signalled in both CTAs by the leader's commit) says the MMAs that read it retired.
-        const uint32_t l_bar_q = mapa_u32(bar_q, 0);
-        if (rank == 0) mbar_arrive_expect_tx(bar_q, 2 * p.n_kc * TC_QCHUNK_BYTES);
-        for (uint32_t kc = 0; kc < p.n_kc; ++kc)
-          tma_load_2d_pair(smem_u32(sQ + (size_t)kc * TC_QCHUNK_BYTES), &tmQ, (int)(kc * TC_BK), (int)(qt * TC_BM),
-                           l_bar_q);
+        if (QRES) {
+          const uint32_t l_bar_q = mapa_u32(bar_q, 0);
+          if (rank == 0) mbar_arrive_expect_tx(bar_q, 2 * p.n_kc * TC_QCHUNK_BYTES);
+          for (uint32_t kc = 0; kc < p.n_kc; ++kc)
+            tma_load_2d_pair(smem_u32(sQ + (size_t)kc * TC_QCHUNK_BYTES), &tmQ, (int)(kc * TC_BK),
+                             (int)(qt * TC_BM), l_bar_q);
+        }
         uint32_t it = 0;
         for (uint32_t ti = 0; ti < n_my; ++ti) {
           const int row0 = (int)(tile_of(s_begin + ti) * TC_BN + rank * (TC_BN / 2));
@@ -375,6 +387,9 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             if (rank == 0) mbar_arrive_expect_tx(bar_full + 8 * stage, 2 * STAGE_BYTES);
             tma_load_2d_pair(smem_u32(sE + (size_t)stage * STAGE_BYTES), &tmE, (int)(kc * TC_BK), row0,
                              mapa_u32(bar_full + 8 * stage, 0));
+            if (!QRES)
+              tma_load_2d_pair(smem_u32(sE + (size_t)stage * STAGE_BYTES + E_BYTES), &tmQ, (int)(kc * TC_BK),
+                               (int)(qt * TC_BM), mapa_u32(bar_full + 8 * stage, 0));
           }
         }
       }
@@ -382,8 +397,10 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   } else if (warp == 1) {
     // ------------------------------ MMA issuer (leader CTA of a pair) ----------
     if (lane == 0 && n_my && rank == 0) {
-      mbar_wait(bar_q, 0);
-      tc_fence_after();
+      if (QRES) {
+        mbar_wait(bar_q, 0);
+        tc_fence_after();
+      }
       uint32_t it = 0;
       for (uint32_t ti = 0; ti < n_my; ++ti) {
         const uint32_t acc = ti & 1, use = ti >> 1;
@@ -394,7 +411,8 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           const uint32_t stage = it % S;
           mbar_wait(bar_full + 8 * stage, (it / S) & 1);
           tc_fence_after();
-          const uint64_t adesc = make_sw128_desc(smem_u32(sQ + (size_t)kc * TC_QCHUNK_BYTES));
+          const uint64_t adesc = make_sw128_desc(
+              smem_u32(QRES ? sQ + (size_t)kc * TC_QCHUNK_BYTES : sE + (size_t)stage * STAGE_BYTES + E_BYTES));
           const uint64_t bdesc = make_sw128_desc(smem_u32(sE + (size_t)stage * STAGE_BYTES));
 #pragma unroll
           for (uint32_t k = 0; k < TC_BK / TC_UK; ++k) {
@@ -648,10 +666,16 @@ static bool encode_2d(CUtensorMap* m, const void* base, uint64_t inner, uint64_t
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// the query tile stays resident when that leaves room for at least three ring stages
+static bool tensor_q_resident(uint32_t n_kc) {
+  return (size_t)n_kc * TC_QCHUNK_BYTES + 3 * tc_stage_bytes(false) + 1024 <= TC_SMEM_LIMIT;
+}
+
 static uint32_t tensor_stages(uint32_t n_kc, bool pair, size_t* total) {
-  const size_t fixed = (size_t)n_kc * TC_QCHUNK_BYTES + (6 + 2 * TC_MAX_STAGES) * 8 + 64;
+  const bool qres = tensor_q_resident(n_kc);
+  const size_t fixed = (qres ? (size_t)n_kc * TC_QCHUNK_BYTES : 0) + (6 + 2 * TC_MAX_STAGES) * 8 + 64;
   for (uint32_t s = TC_MAX_STAGES; s >= 2; --s) {
-    size_t t = fixed + (size_t)s * tc_stage_bytes(pair);
+    size_t t = fixed + (size_t)s * (tc_stage_bytes(pair) + (qres ? 0 : TC_QCHUNK_BYTES));
     if (t <= TC_SMEM_LIMIT) {
       *total = t;
       return s;
@@ -686,19 +710,19 @@ uint32_t tensor_sample_tiles(uint32_t n_rows, uint32_t nq) {
 static int g_tensor_epi_warps = 8;  // epilogue warps per CTA (8 or 16; measured equal within noise)
 void tensor_set_epi_warps(int n) { g_tensor_epi_warps = n == 8 ? 8 : 16; }
 
-template <int EW>
+template <int EW, bool QRES>
 static cudaError_t launch_kernel(bool pair, uint32_t units, size_t smem, cudaStream_t s, const CUtensorMap& tmQ,
                                  const CUtensorMap& tmE, const TensorParams& p) {
   constexpr uint32_t threads = (TC_CTRL_WARPS + EW) * 32;
   if (!pair) {
-    cudaError_t e = cudaFuncSetAttribute(tensor_scan_kernel<false, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(tensor_scan_kernel<false, EW, QRES>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    tensor_scan_kernel<false, EW><<<units, threads, smem, s>>>(tmQ, tmE, p);
+    tensor_scan_kernel<false, EW, QRES><<<units, threads, smem, s>>>(tmQ, tmE, p);
     return cudaGetLastError();
   }
-  cudaError_t e =
-      cudaFuncSetAttribute(tensor_scan_kernel<true, EW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(tensor_scan_kernel<true, EW, QRES>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * units, 1, 1);
@@ -712,7 +736,7 @@ static cudaError_t launch_kernel(bool pair, uint32_t units, size_t smem, cudaStr
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, tensor_scan_kernel<true, EW>, tmQ, tmE, p);
+  return cudaLaunchKernelEx(&cfg, tensor_scan_kernel<true, EW, QRES>, tmQ, tmE, p);
 }
 
 static int g_tensor_pair = 0;  // 1 = two or more query tiles run as CTA pairs (cta_group::2); measured slower so far
@@ -780,8 +804,9 @@ static cudaError_t launch_mode(const StoreView& st, const void* Q16, uint32_t q0
   // bounds for the map and reads as zeros
   if (!encode_2d(&tmQ, qbase, st.ld16, (uint64_t)n_tiles_q * TC_BM, TC_BM)) return cudaErrorInvalidValue;
   if (!encode_2d(&tmE, st.E16, st.ld16, st.n_rows, pair ? TC_BN / 2 : TC_BN)) return cudaErrorInvalidValue;
-  return g_tensor_epi_warps == 8 ? launch_kernel<8>(pair, n_qt * n_es, smem, s, tmQ, tmE, p)
-                                 : launch_kernel<16>(pair, n_qt * n_es, smem, s, tmQ, tmE, p);
+  if (!tensor_q_resident(p.n_kc)) return launch_kernel<8, false>(pair, n_qt * n_es, smem, s, tmQ, tmE, p);
+  return g_tensor_epi_warps == 8 ? launch_kernel<8, true>(pair, n_qt * n_es, smem, s, tmQ, tmE, p)
+                                 : launch_kernel<16, true>(pair, n_qt * n_es, smem, s, tmQ, tmE, p);
 }
 
 // Bootstrap: sample scores -> per-query cut-off in cv.gtau[q0 .. q0+nq).  dump holds

@@ -94,6 +94,8 @@ def test_shapes(n, d, b, k):
     (5000, 384, 16, 10), (20_000, 384, 200, 10), (3000, 128, 33, 5), (8000, 384, 130, 30),
     (50_000, 384, 1024, 10), (4000, 100, 40, 10), (6000, 640, 17, 10), (700, 384, 129, 3),
     (30_000, 384, 300, 10), (40_000, 256, 640, 100),
+    # large embeddings: the query tile no longer fits next to the ring and is streamed with E
+    (6000, 1024, 40, 10), (9000, 768, 260, 100), (5000, 1536, 130, 10),
 ])
 @pytest.mark.parametrize("pair", [1, 0])
 def test_tensor_pass_parity(n, d, b, k, pair):
