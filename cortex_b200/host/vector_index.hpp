@@ -138,6 +138,27 @@ class GpuVectorIndex final : public VectorIndex {
       out[queries[b].first] = collect(ids.data() + 16 * b * k, sc.data() + b * k, di.data() + b * k, n[b]);
     return out;
   }
+  // The similarity step of DedupScanner::scan (linker/dedup.rs:65-127) as one self-join: every unordered
+  // pair of live nodes with score >= threshold, once, a inserted before b.
+  struct DuplicatePair {
+    NodeId node_a, node_b;
+    float similarity;
+  };
+  std::vector<DuplicatePair> dedup_scan(float threshold, uint32_t per_node_cap = 64, size_t max_pairs = 1 << 20,
+                                        uint64_t* total = nullptr) const {
+    std::vector<uint8_t> a(16 * max_pairs), b(16 * max_pairs);
+    std::vector<float> sc(max_pairs);
+    uint64_t n = 0, tot = 0;
+    check(cx_dedup_scan(h_, threshold, per_node_cap, max_pairs, a.data(), b.data(), sc.data(), &n, &tot));
+    if (total) *total = tot;
+    std::vector<DuplicatePair> out(n);
+    for (uint64_t i = 0; i < n; ++i) {
+      __builtin_memcpy(out[i].node_a.data(), a.data() + 16 * i, 16);
+      __builtin_memcpy(out[i].node_b.data(), b.data() + 16 * i, 16);
+      out[i].similarity = sc[i];
+    }
+    return out;
+  }
   cx_index* handle() const { return h_; }
 
  private:

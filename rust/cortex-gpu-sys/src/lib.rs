@@ -50,6 +50,19 @@ extern "C" {
     pub fn cx_search_threshold(h: *mut cx_index, query: *const f32, qlen: u32, threshold: f32,
                                filter: *const cx_filter, cap: u64, out_ids: *mut u8, out_score: *mut f32,
                                out_distance: *mut f32, out_n: *mut u64, out_total: *mut u64) -> c_int;
+    pub fn cx_search_threshold_batch(h: *mut cx_index, queries: *const f32, b: u64, qlen: u32, threshold: f32,
+                                     filter: *const cx_filter, cap: u64, out_ids: *mut u8, out_score: *mut f32,
+                                     out_distance: *mut f32, out_n: *mut u64, out_total: *mut u64) -> c_int;
+    pub fn cx_dedup_scan(h: *mut cx_index, threshold: f32, per_node_cap: u32, max_pairs: u64, out_a_ids: *mut u8,
+                         out_b_ids: *mut u8, out_score: *mut f32, out_n: *mut u64, out_total: *mut u64) -> c_int;
+    pub fn cx_autolink_batch(h: *mut cx_index, new_ids: *const u8, embeddings: *const f32, b: u64, len: u32, k: u64,
+                             threshold: f32, max_edges_per_node: u32, out_to_ids: *mut u8, out_score: *mut f32,
+                             out_n: *mut u32) -> c_int;
+    pub fn cx_autolink_batch_device(h: *mut cx_index, d_embeddings: *const f32, b: u64, k: u64, threshold: f32,
+                                    max_edges_per_node: u32, d_self_rows: *const u32, d_scratch_rows: *mut u32,
+                                    d_scratch_score: *mut f32, d_scratch_distance: *mut f32, d_scratch_n: *mut u32,
+                                    d_out_rows: *mut u32, d_out_score: *mut f32, d_out_ids: *mut u8,
+                                    d_out_n: *mut u32, stream: *mut c_void) -> c_int;
     pub fn cx_search_batch(h: *mut cx_index, queries: *const f32, b: u64, qlen: u32, k: u64,
                            filter: *const cx_filter, out_ids: *mut u8, out_score: *mut f32,
                            out_distance: *mut f32, out_n: *mut u64) -> c_int;

@@ -54,6 +54,45 @@ fn c_filter(f: &VectorFilter) -> CFilter {
 }
 
 impl GpuVectorIndex {
+    /// The similarity step of DedupScanner::scan (linker/dedup.rs:65-127) as one self-join on the
+    /// device: every unordered pair of live nodes with score >= threshold, once, as
+    /// (node_a, node_b, similarity) with a inserted before b.  The scanner keeps its
+    /// determine_action() loop (dedup.rs:130-171) and feeds it these pairs instead of calling
+    /// search_threshold once per node.
+    pub fn dedup_scan(&self, threshold: f32, per_node_cap: u32, max_pairs: usize)
+        -> Result<(Vec<(NodeId, NodeId, f32)>, u64)> {
+        let (mut a, mut b, mut sc) = (vec![0u8; 16 * max_pairs], vec![0u8; 16 * max_pairs], vec![0f32; max_pairs]);
+        let (mut n, mut total) = (0u64, 0u64);
+        check(unsafe {
+            sys::cx_dedup_scan(self.h, threshold, per_node_cap, max_pairs as u64, a.as_mut_ptr(), b.as_mut_ptr(),
+                               sc.as_mut_ptr(), &mut n, &mut total)
+        })?;
+        let id = |buf: &[u8], i: usize| NodeId::from_bytes(buf[16 * i..16 * i + 16].try_into().unwrap());
+        Ok(((0..n as usize).map(|i| (id(&a, i), id(&b, i), sc[i])).collect(), total))
+    }
+
+    /// The scan step of AutoLinker::run_cycle (linker/auto_linker.rs:215-264) for a batch of new
+    /// nodes: search(embedding, k), skip self, keep score >= threshold, at most max_edges per node.
+    /// Returns, per node, the (neighbour, score) list in best-first order.
+    pub fn autolink_batch(&self, nodes: &[(NodeId, Embedding)], k: usize, threshold: f32, max_edges: u32)
+        -> Result<Vec<Vec<(NodeId, f32)>>> {
+        if nodes.is_empty() {
+            return Ok(Vec::new());
+        }
+        let (b, dim, me) = (nodes.len(), nodes[0].1.len(), max_edges as usize);
+        let ids: Vec<u8> = nodes.iter().flat_map(|(id, _)| id.as_bytes().to_vec()).collect();
+        let flat: Vec<f32> = nodes.iter().flat_map(|(_, e)| e.iter().copied()).collect();
+        let (mut to, mut sc, mut n) = (vec![0u8; 16 * b * me], vec![0f32; b * me], vec![0u32; b]);
+        check(unsafe {
+            sys::cx_autolink_batch(self.h, ids.as_ptr(), flat.as_ptr(), b as u64, dim as u32, k as u64, threshold,
+                                   max_edges, to.as_mut_ptr(), sc.as_mut_ptr(), n.as_mut_ptr())
+        })?;
+        Ok((0..b).map(|i| (0..n[i] as usize).map(|j| {
+            let o = i * me + j;
+            (NodeId::from_bytes(to[16 * o..16 * o + 16].try_into().unwrap()), sc[o])
+        }).collect()).collect())
+    }
+
     /// HnswIndex::new(dimension), index.rs:204-211
     pub fn new(dimension: usize) -> Result<Self> {
         Self::on_device(dimension, 0)
