@@ -26,11 +26,18 @@
 namespace cx {
 
 constexpr int SEL_THREADS = 512;
-constexpr int SEL_BATCH = 16;             // rows rescored per staging round
+constexpr int SEL_MAX_BATCH = 32;         // rows rescored per staging round (fewer for long rows)
 constexpr int SEL_MAX_KS = 256;
-constexpr uint32_t SEL_DIRECT_MAX = 1024; // lists up to this long skip the radix select
-constexpr uint32_t SEL_K2 = 2048;         // survivors that can be sorted
-constexpr uint32_t SEL_STAGE = 4096;      // radix-select staging words
+constexpr uint32_t SEL_K2 = 1024;         // survivors that can be ordered
+constexpr uint32_t SEL_STAGE = 2048;      // radix-select staging words
+constexpr uint32_t SEL_RANK_MAX = 256;    // up to this many survivors are ordered by rank counting (no barriers)
+
+// rows per staging round: as many as fit 64 KB of shared memory, a power of two <= 32
+__host__ __device__ inline uint32_t select_batch(uint32_t ld) {
+  uint32_t b = SEL_MAX_BATCH;
+  while (b > 4 && (size_t)b * (ld + 1) * 4 > 64 * 1024) b >>= 1;
+  return b;
+}
 
 struct SelectParams {
   StoreView st;
@@ -62,7 +69,7 @@ __host__ __device__ inline SelectLayout select_layout(uint32_t ld) {
   L.q = o;
   o += (size_t)ld * 4;
   L.stage = o;
-  o += (size_t)SEL_BATCH * (ld + 1) * 4;
+  o += (size_t)select_batch(ld) * (ld + 1) * 4;
   o = (o + 7) & ~(size_t)7;
   L.e = o;
   o += (size_t)SEL_MAX_KS * (8 + 4 + 4 + 4);
@@ -118,17 +125,18 @@ __global__ void __launch_bounds__(SEL_THREADS) select_rescore_kernel(const Selec
     p.rqnorm[q] = __frcp_rn(na);
   }
 
-  // ---- 1. survivors -> keys[0..M) ---------------------------------------------------
+  // ---- 1. survivors -> keys[0..M), ordered ---------------------------------------------
+  // Only the best n_keep candidates can matter: the KS = KP that are rescored plus as many
+  // again for the +-eps band around the k-th result (step 3).  A radix select finds that cut;
+  // what it leaves behind is bounded by `cut` and enters U.
   unsigned long long U = gt;
   uint32_t cut = 0;  // radix cut (score ord); 0 = none
-  if (n_src > SEL_DIRECT_MAX) {
+  const uint32_t n_keep = min(min(2 * p.KP, (uint32_t)SEL_MAX_KS), n_src);
+  if (n_src > n_keep) {
     auto get = [&](uint32_t i) {
       const uint64_t key = src[i];
       return key >= gt ? key_ord(key) : 0u;
     };
-    // keep twice the rescore count (at most what can be rescored at all): the +-eps band around
-    // the k-th result may have to be rescored too (step 3), and it lies below the KP-th key
-    const uint32_t n_keep = min(min(2 * p.KP, (uint32_t)SEL_MAX_KS), n_src);
     cut = block_kth_largest(get, n_src, n_keep, scratch, rstage, SEL_STAGE, tid, SEL_THREADS);
     const unsigned long long left = (unsigned long long)cut << 32;  // what is left behind scores below `cut`
     if (left > U) U = left;
@@ -143,12 +151,25 @@ __global__ void __launch_bounds__(SEL_THREADS) select_rescore_kernel(const Selec
   __syncthreads();
   const uint32_t M = min(s_m, SEL_K2);
   const bool truncated = s_m > SEL_K2;
-  uint32_t NK = 32;
-  while (NK < M) NK <<= 1;
-  for (uint32_t i = M + tid; i < NK; i += SEL_THREADS) keys[i] = 0ull;
-  __syncthreads();
-  bitonic_sort_desc(keys, NK, tid, SEL_THREADS, [] { __syncthreads(); });
-  __syncthreads();
+  if (M <= SEL_RANK_MAX) {
+    // rank counting (keys are distinct): no barriers inside, every thread reads the same key at a time
+    uint64_t mine = 0ull;
+    uint32_t rank = 0;
+    if (tid < M) {
+      mine = keys[tid];
+      for (uint32_t j = 0; j < M; ++j) rank += keys[j] > mine;
+    }
+    __syncthreads();
+    if (tid < M) keys[rank] = mine;
+    __syncthreads();
+  } else {
+    uint32_t NK = 32;
+    while (NK < M) NK <<= 1;
+    for (uint32_t i = M + tid; i < NK; i += SEL_THREADS) keys[i] = 0ull;
+    __syncthreads();
+    bitonic_sort_desc(keys, NK, tid, SEL_THREADS, [] { __syncthreads(); });
+    __syncthreads();
+  }
   const float na = s_na;
   uint32_t KS = min(min(M, p.KP), (uint32_t)SEL_MAX_KS);
 
@@ -156,8 +177,9 @@ __global__ void __launch_bounds__(SEL_THREADS) select_rescore_kernel(const Selec
   const uint32_t warp = tid >> 5, lane = tid & 31, nwarps = SEL_THREADS / 32;
   const uint32_t sstride = ld + 1;
   auto rescore = [&](uint32_t lo, uint32_t hi) {
-    for (uint32_t base = lo; base < hi; base += SEL_BATCH) {
-      const uint32_t nb = min((uint32_t)SEL_BATCH, hi - base);
+    const uint32_t batch = select_batch(ld);
+    for (uint32_t base = lo; base < hi; base += batch) {
+      const uint32_t nb = min(batch, hi - base);
       for (uint32_t j = warp; j < nb; j += nwarps) {
         const uint32_t row = key_row(keys[base + j]);
         const float* g = p.st.E + (size_t)row * ld;
