@@ -579,9 +579,15 @@ cx_status search_host(cx_index* h, const float* queries, uint64_t B, uint32_t ql
   char* h_block = hp + hq;
 
   cudaStream_t s = ws->stream;
+  bool direct = false;
   if (qlen == ldq) {
-    // rows need no padding: copy straight from the caller's buffer (a true async DMA when it is
-    // pinned; staged by the driver when it is pageable) -- no intermediate host copy
+    // rows need no padding: if the caller's buffer is pinned, DMA straight from it (pageable
+    // memory goes through the staging copy: the driver's own pageable path serialises badly)
+    cudaPointerAttributes pa;
+    if (cudaPointerGetAttributes(&pa, queries) == cudaSuccess) direct = pa.type == cudaMemoryTypeHost;
+    else (void)cudaGetLastError();
+  }
+  if (direct) {
     CU(cudaMemcpyAsync(sb.dQ, queries, B * ldq * 4, cudaMemcpyHostToDevice, s));
   } else {
     // stage queries, zero padded to ldq
