@@ -113,7 +113,7 @@ struct cx_index {
   int force_path = 0;
   uint32_t tensor_min_batch = 5;   // query groups at least this large go to the tensor pass
   uint32_t tensor_phase_growth = 0xFFFFFFFFu; // tensor pass: each scan phase covers this many times the rows seen before
-                                              // (0/1 = one phase; 0xFFFFFFFF = auto: 8 for k <= 16, 4 above)
+                                              // (0/1 = one phase; 0xFFFFFFFF = auto: one phase for B <= 256 and k <= 16, else 8 for k <= 16, 4 above)
   int profile = 0;
   // stats
   std::atomic<uint64_t> launches{0}, q_stream{0}, q_tensor{0}, q_exact{0}, fallbacks{0}, h2d{0}, d2h{0};

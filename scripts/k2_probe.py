@@ -46,9 +46,12 @@ for pair, growth, epi in [(int(p), int(g), int(e)) for p in a.pairs.split(",") f
         out = ix.search_batch_device(q, a.k, out=out)
         torch.cuda.synchronize()
         s0 = ix.stats()
+        import time
+        t0 = time.perf_counter()
         for _ in range(reps):
             out = ix.search_batch_device(q, a.k, out=out)
         torch.cuda.synchronize()
+        call_us = (time.perf_counter() - t0) / reps * 1e6
         s1 = ix.stats()
         ns = s1["pass_kernel_ns"] - s0["pass_kernel_ns"]
         n = s1["pass_kernel_launches"] - s0["pass_kernel_launches"]
@@ -56,7 +59,7 @@ for pair, growth, epi in [(int(p), int(g), int(e)) for p in a.pairs.split(",") f
         tf = 2.0 * 384 * a.batch * a.rows / (us * 1e-6) / 1e12
         if dbg:
             ix.set_option("tensor_debug", -1)  # prints the effective SM clock of the last launch to stderr
-        print(json.dumps({"epi": epi, "pair": pair, "growth": growth, "debug": dbg, "fallbacks": s1["fallbacks"] - s0["fallbacks"], "us_per_launch": us, "tflops": tf, "launches": n,
+        print(json.dumps({"call_us": call_us, "epi": epi, "pair": pair, "growth": growth, "debug": dbg, "fallbacks": s1["fallbacks"] - s0["fallbacks"], "us_per_launch": us, "tflops": tf, "launches": n,
                           "batch": a.batch, "k": a.k}), flush=True)
 ix.set_option("tensor_debug", 0)
 ix.set_option("tensor_pair", 0)
