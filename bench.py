@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--k", type=int, default=10)
     ap.add_argument("--cpu-queries", type=int, default=0, help="queries per CPU-baseline step (0 = one per thread)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--autolink-new", type=int, default=16384,
+                    help="new nodes per auto-link cycle in the extra 'autolink' measurement (0 = skip)")
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=INT",
                     help="cx_set_option before the run (A/B measurements), e.g. --opt tensor_pair=0")
     return ap.parse_args()
@@ -62,6 +64,21 @@ def peaks():
                 "bf16_tflops_sustained": float(j.get("bf16_tflops_sustained", j["bf16_tflops"])),
                 "source": "measured"}
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def ncu_traffic(kernel, batch):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, from the committed ncu
+    --set full capture of this same command (profiles/ncu_traffic.json, written by
+    scripts/ncu_summary.py --traffic); None if there is no capture for this kernel / batch."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        j = json.load(open(p))
+        e = j.get(kernel)
+        if e and int(e.get("batch", batch)) == int(batch):
+            return float(e["dram_bytes_per_launch"])
+    except Exception:
+        pass
+    return None
 
 
 # ----------------------------------------------------------------------------------
@@ -241,6 +258,8 @@ def main():
     if world > 1:
         dist.broadcast(q_all, src=0)
     d_q = q_all[:a.batch].contiguous()
+    # new nodes of the auto-link measurement: perturbed copies of rows of rank 0's shard
+    q_al = make_queries_torch(corpus, a.autolink_new, SEED + 5) if a.autolink_new > 0 else None
     corpus_np = corpus.cpu().numpy()
     ids = np.zeros((a.rows, 16), np.uint8)
     ids[:, 8:] = (np.arange(a.rows, dtype=np.uint64) + rank * a.rows).astype(">u8").view(np.uint8).reshape(-1, 8)
@@ -363,7 +382,53 @@ def main():
                      "roofline": {"bound": "hbm", "kernel": "stream_scan_kernel", "achieved": gbs,
                                   "peak": pk1["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk1["hbm_gbs"],
                                   "frac_of_nominal_8TBs": gbs / 8000.0, "us_per_launch": ns1 * 1e-3 / l1,
+                                  "traffic": ncu_traffic("stream_scan_kernel", 1),
                                   "algorithmic_bytes_per_launch": bytes1, "peak_source": pk1["source"]}}
+
+    # ---- auto-link cycle (BASELINE.json metric "auto-link pairs/s at 1/2/4/8 B200", configs[2] shape at a
+    # bounded size): every new node searches the row-sharded corpus for its 100 nearest neighbours
+    # (linker/auto_linker.rs:215-222), local lists are merged with one all_gather, candidates with
+    # score >= 0.75 become links (linker/rules.rs:50).  Unit = scored (new node, corpus row) pair.
+    autolink = None
+    if a.autolink_new > 0:
+        nq = a.autolink_new
+        if world > 1:
+            dist.broadcast(q_al, src=0)
+        q_al = q_al.contiguous()
+        out_al = None
+
+        def local_al(q, k):
+            nonlocal out_al
+            out_al = ix.search_batch_device(q, k, stream=stream.cuda_stream, out=out_al)
+            return out_al
+
+        sh_al = ShardedSearch(local_al, row_offset=rank * a.rows)
+        res = None
+        for _ in range(2):
+            res = sh_al.search(q_al, 100)
+        barrier()
+        sa0 = ix.stats()
+        ea0, ea1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_cyc = 3
+        ea0.record()
+        for _ in range(n_cyc):
+            res = sh_al.search(q_al, 100)
+            links = (res[1] >= 0.75).sum()
+        ea1.record()
+        barrier()
+        sa1 = ix.stats()
+        tt = torch.tensor([ea0.elapsed_time(ea1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_cyc = float(tt.item()) / n_cyc
+        pairs = float(nq) * a.rows * world
+        pk_a = peaks()
+        tf = 2.0 * a.dim * float(nq) * a.rows / (ms_cyc * 1e-3) / 1e12  # per GPU
+        autolink = {"metric": "scored pairs/s", "value": pairs / (ms_cyc * 1e-3), "unit": "pairs/s",
+                    "new_nodes_per_cycle": nq, "rows_per_gpu": a.rows, "k": 100, "threshold": 0.75,
+                    "ms_per_cycle": ms_cyc, "link_candidates": int(links.item()),
+                    "tflops_per_gpu_whole_cycle": tf, "frac_of_sustained_bf16_whole_cycle": tf / pk_a["bf16_tflops_sustained"],
+                    "fallbacks": sa1["fallbacks"] - sa0["fallbacks"]}
 
     if rank != 0:
         if world > 1:
@@ -382,7 +447,7 @@ def main():
         sec = ns * 1e-9 / launches
         achieved = alg_bytes / sec / 1e9
         roof = {"bound": "hbm", "kernel": "stream_scan_kernel", "achieved": achieved, "peak": pk["hbm_gbs"],
-                "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": None,
+                "unit": "GB/s", "frac": achieved / pk["hbm_gbs"], "traffic": ncu_traffic("stream_scan_kernel", a.batch),
                 "peak_source": pk["source"], "us_per_launch": sec * 1e6, "launches": launches,
                 "algorithmic_bytes_per_launch": alg_bytes,
                 "kernel_share_of_step": (ns * 1e-6) / ms_total}
@@ -397,8 +462,11 @@ def main():
         roof = {"bound": "tensor", "kernel": "tensor_scan_kernel", "achieved": achieved,
                 "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / pk["bf16_tflops_sustained"], "frac_of_burst": achieved / pk["bf16_tflops"],
-                "traffic": None, "peak_source": pk["source"], "us_per_launch": sec * 1e6, "launches": launches,
+                "traffic": ncu_traffic("tensor_scan_kernel", a.batch), "peak_source": pk["source"],
+                "us_per_launch": sec * 1e6, "launches": launches,
                 "algorithmic_flops_per_launch": flops,
+                "launch_note": "one launch = one scan of the shard: its phase launches of tensor_scan_kernel plus "
+                               "the tau_refine kernels between them (CUDA events bracket all of it)",
                 "hbm_floor_us": hbm_bytes / (pk["hbm_gbs"] * 1e9) * 1e6,
                 "hbm_gbs_of_shadow_stream": hbm_bytes / sec / 1e9,
                 "kernel_share_of_step": (ns * 1e-6) / ms_total}
@@ -417,7 +485,7 @@ def main():
                    "seed": SEED, "parallelism": f"row-shard x{world}",
                    "cache": "inputs larger than L2: the 1.5 GB corpus shard is streamed from HBM every step",
                    "value_counts": "per-shard query scans (batch x n_gpus per step)"},
-        "roofline": roof, "small_batch": small, "cpu_baseline": cpu,
+        "roofline": roof, "small_batch": small, "autolink": autolink, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": st1["kernel_launches"] - st0["kernel_launches"],
         "clocks": clk,

@@ -44,7 +44,37 @@ WANT = [
 ]
 
 
+def traffic(argv):
+    """--traffic kernel_regex batch rep [rep...]: dram bytes (read + write) per launch, summed over the
+    launches of one scan (all captured launches of that kernel are taken as one scan's phases)."""
+    import json
+    import re
+    out = {}
+    for spec in argv:
+        name, batch, rep, how = spec.split(":")  # how = sum (launches are the phases of one scan) | mean
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(io.StringIO(raw)))
+        head, units, data = rows[0], rows[1], rows[2:]
+        col = {k: i for i, k in enumerate(head)}
+        tot, n, us = 0.0, 0, 0.0
+        for r in data:
+            if not re.search(name, r[col["Kernel Name"]]):
+                continue
+            for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                v, u = float(r[col[k]]), units[col[k]].lower()
+                tot += v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[u]
+            n += 1
+        out[name] = {"batch": int(batch), "dram_bytes_per_launch": tot if how == "sum" else tot / max(n, 1),
+                     "captured_kernel_launches": n,
+                     "source": rep + " (ncu --set full --clock-control none; " +
+                               ("the captured launches are the bootstrap + phases of one scan, summed)" if how == "sum"
+                                else "mean over the captured launches)")}
+    print(json.dumps(out, indent=1))
+
+
 def main():
+    if sys.argv[1] == "--traffic":
+        return traffic(sys.argv[2:])
     rep = sys.argv[1]
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
