@@ -154,6 +154,52 @@ std::vector<uint32_t> tensor_phases(uint32_t n_tiles, uint32_t sample_tiles, uin
   return ph;
 }
 
+// Launch groups of the tensor pass, in query tiles of 128.  A group of g tiles runs as
+// g x floor(SMs / g) CTAs, each scanning 1 / floor(SMs / g) of the rows, so some group sizes leave
+// SMs idle (128 tiles on 148 SMs: 20 idle for the whole scan).  Splitting the batch into groups of
+// SMs, SMs/2 or SMs/4 tiles keeps every SM busy; a small dynamic programme picks the cheapest split
+// (cost in units of one CTA scanning the whole shard, plus a little per extra group for its
+// bootstrap and launch overhead).
+std::vector<uint32_t> tensor_groups(uint64_t n_queries, int sm_count) {
+  const uint32_t T = (uint32_t)((n_queries + 127) / 128);
+  const uint32_t S = (uint32_t)sm_count;
+  std::vector<uint32_t> groups;
+  uint32_t left = T;
+  while (left >= S) {
+    groups.push_back(S);
+    left -= S;
+  }
+  if (left) {
+    const uint32_t cand[3] = {S, S / 2, S / 4};
+    std::vector<double> cost(left + 1, 0.0);
+    std::vector<uint32_t> pick(left + 1, 0);
+    for (uint32_t r = 1; r <= left; ++r) {
+      cost[r] = 1e30;
+      for (int c = -1; c < 3; ++c) {
+        const uint32_t g = c < 0 ? r : (cand[c] < r ? cand[c] : r);
+        if (!g) continue;
+        const double t = 1.0 / (double)(S / g) + 0.02 + cost[r - g];
+        if (t < cost[r] - 1e-12) {
+          cost[r] = t;
+          pick[r] = g;
+        }
+      }
+    }
+    for (uint32_t r = left; r;) {
+      groups.push_back(pick[r]);
+      r -= pick[r];
+    }
+  }
+  // tiles -> queries (the last group takes what is left)
+  uint64_t q = n_queries;
+  for (auto& g : groups) {
+    const uint64_t nq = (uint64_t)g * 128 < q ? (uint64_t)g * 128 : q;
+    g = (uint32_t)nq;
+    q -= nq;
+  }
+  return groups;
+}
+
 struct Plan {
   uint64_t B;
   uint32_t qlen, ldq, kd;
@@ -164,7 +210,8 @@ struct Plan {
   uint32_t growth;    // tensor pass: phase growth factor (tensor_phases)
   uint32_t cap;       // merged-list capacity per query for the primary pass
   uint32_t cap_retry; // ... and for the streaming retries of unverified queries (widest tier)
-  uint32_t q_per_launch;  // tensor pass: queries per launch
+  uint32_t q_per_launch;  // tensor pass: queries in the largest launch group
+  std::vector<uint32_t> groups;  // tensor pass: queries per launch group (tensor_groups)
   bool fast;          // a nominate + rescore pass is usable for this call
   bool tensor;        // ... and it is the tcgen05 pass (else the streaming pass)
   bool thr_fast;      // threshold scan served by nominate-all + rescore-all (else the exact path)
@@ -207,7 +254,8 @@ Plan make_plan(const cx_index* h, uint64_t B, uint32_t qlen, uint32_t ldq, uint3
       p.KP = 64;  // sizes the streaming pass's shared-memory lists (2 * KP + 128 entries)
       p.thr_cap = B <= 64 ? 8192u : 2048u;
       p.cap = p.thr_cap;
-      p.q_per_launch = (uint32_t)h->sm_count * 128u;
+      p.groups = tensor_groups(B, h->sm_count);
+      p.q_per_launch = *std::max_element(p.groups.begin(), p.groups.end());
       p.tensor = h->dE16 && h->force_path != PATH_STREAM &&
                  (B >= h->tensor_min_batch || h->force_path == PATH_TENSOR) && tensor_scan_eligible(h->ld16, 16);
     }
@@ -224,7 +272,8 @@ Plan make_plan(const cx_index* h, uint64_t B, uint32_t qlen, uint32_t ldq, uint3
       (B >= h->tensor_min_batch || h->force_path == PATH_TENSOR) && tensor_scan_eligible(h->ld16, kd)) {
     p.tensor = true;
     p.KPt = tensor_keep(kd);
-    p.q_per_launch = (uint32_t)h->sm_count * 128u;
+    p.groups = tensor_groups(B, h->sm_count);
+    p.q_per_launch = *std::max_element(p.groups.begin(), p.groups.end());
     // the cut-off comes from a sample of S rows, so about KPt * rows / S keys per query clear it;
     // twice that plus slack (excess is detected by the select kernel and sent to a fallback,
     // never lost silently)
@@ -358,11 +407,12 @@ cx_status run_search(cx_index* h, Workspace* ws, const FilterHost& fh, const Sea
       launch_fill_tau(cv, 0, (uint32_t)B, threshold - eps_tensor(h->dim) - slack, s);
       h->launches += 2;
       const uint32_t t0 = tp ? tp->tile0 : 0, nt = tensor_tiles(st.n_rows) - t0;
-      for (uint64_t q0 = 0; q0 < B; q0 += pl.q_per_launch) {
-        const uint32_t nq = (uint32_t)(B - q0 < pl.q_per_launch ? B - q0 : pl.q_per_launch);
+      uint64_t q0 = 0;
+      for (const uint32_t nq : pl.groups) {
         CU(launch_tensor_scan(st, sb.q16, (uint32_t)q0, nq, flt, check_rows, cv, sb.lists, t0, nt, h->sm_count, s,
                               /*static_tau=*/true));
         ++n_pass;
+        q0 += nq;
       }
     } else {
       const float thr_cos = threshold - eps_stream(h->dim) - slack;
@@ -420,17 +470,18 @@ cx_status run_search(cx_index* h, Workspace* ws, const FilterHost& fh, const Sea
       cv.KP = pl.KPt;
       const bool check_rows = flt.has_kinds || flt.has_agent || flt.n_excl || h->n_live != h->n_rows;
       // cut-off bootstrap for every launch group first (the sample buffer is reused in stream order)
-      for (uint64_t q0 = 0; q0 < B; q0 += pl.q_per_launch) {
-        const uint32_t nq = (uint32_t)(B - q0 < pl.q_per_launch ? B - q0 : pl.q_per_launch);
+      uint64_t q0 = 0;
+      for (const uint32_t nq : pl.groups) {
         CU(launch_tensor_bootstrap(st, sb.q16, (uint32_t)q0, nq, flt, check_rows, cv, sb.dump, pl.n_slots,
                                    h->sm_count, s));
         h->launches += 2;
+        q0 += nq;
       }
       if (h->profile) CU(cudaEventRecord(ws->ev0, s));
       const std::vector<uint32_t> phases =
           tensor_phases(tensor_tiles(st.n_rows), pl.n_slots, pl.growth, nullptr);
-      for (uint64_t q0 = 0; q0 < B; q0 += pl.q_per_launch) {
-        const uint32_t nq = (uint32_t)(B - q0 < pl.q_per_launch ? B - q0 : pl.q_per_launch);
+      q0 = 0;
+      for (const uint32_t nq : pl.groups) {
         uint32_t tile0 = 0;
         for (size_t ph = 0; ph < phases.size(); ++ph) {
           if (ph) {  // tighten the cut-off with what the earlier phases found
@@ -443,6 +494,7 @@ cx_status run_search(cx_index* h, Workspace* ws, const FilterHost& fh, const Sea
           h->launches += 1;
         }
         ++n_pass;  // one scan of the whole shard (all of its phases)
+        q0 += nq;
       }
     } else {
       if (h->profile) CU(cudaEventRecord(ws->ev0, s));

@@ -96,6 +96,8 @@ def test_shapes(n, d, b, k):
     (30_000, 384, 300, 10), (40_000, 256, 640, 100),
     # large embeddings: the query tile no longer fits next to the ring and is streamed with E
     (6000, 1024, 40, 10), (9000, 768, 260, 100), (5000, 1536, 130, 10),
+    # 40 query tiles: split into launch groups of 37 + 3 tiles so that no SM idles
+    (8000, 128, 5000, 10),
 ])
 @pytest.mark.parametrize("pair", [1, 0])
 def test_tensor_pass_parity(n, d, b, k, pair):
