@@ -337,6 +337,23 @@ def main():
     ms_step = ms_total / a.steps
     value = a.batch * world * a.steps / (ms_total * 1e-3)
 
+    # ---- N > 1: the same steps without the exchange (every rank scans, nobody gathers) -- tells the
+    # all_gather + merge apart from the local scan when reading the scaling numbers
+    local_only_ms = None
+    if world > 1:
+        for _ in range(3):
+            local_search(d_q, a.k)
+        barrier()
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0.record()
+        for _ in range(a.steps):
+            local_search(d_q, a.k)
+        l1.record()
+        barrier()
+        tl = torch.tensor([l0.elapsed_time(l1)], device=dev, dtype=torch.float64)
+        dist.all_reduce(tl, op=dist.ReduceOp.MAX)
+        local_only_ms = float(tl.item()) / a.steps
+
     # ---- e2e: host buffers in and out ---------------------------------------------
     for _ in range(max(3, a.warmup)):
         step_e2e()
@@ -488,6 +505,7 @@ def main():
         "roofline": roof, "small_batch": small, "autolink": autolink, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
         "gpu_launches": st1["kernel_launches"] - st0["kernel_launches"],
+        "local_scan_only_ms_per_step": local_only_ms, "host_cpus": os.cpu_count(),
         "clocks": clk,
         "paths": {"stream": st1["queries_stream"] - st0["queries_stream"],
                   "tensor": st1["queries_tensor"] - st0["queries_tensor"],
