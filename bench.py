@@ -51,6 +51,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--autolink-new", type=int, default=16384,
                     help="new nodes per auto-link cycle in the extra 'autolink' measurement (0 = skip)")
+    ap.add_argument("--pin", action="store_true",
+                    help="N > 1: give every rank its own contiguous block of the host's CPUs (sched_setaffinity)")
     ap.add_argument("--opt", action="append", default=[], metavar="KEY=INT",
                     help="cx_set_option before the run (A/B measurements), e.g. --opt tensor_pair=0")
     return ap.parse_args()
@@ -241,6 +243,11 @@ def main():
         })
         return
 
+    if a.pin and world > 1 and hasattr(os, "sched_setaffinity"):
+        cpus = sorted(os.sched_getaffinity(0))
+        per = max(1, len(cpus) // world)
+        os.sched_setaffinity(0, set(cpus[local_rank * per:(local_rank + 1) * per]))
+
     import torch
     import torch.distributed as dist
 
@@ -350,9 +357,10 @@ def main():
             local_search(d_q, a.k)
         l1.record()
         barrier()
-        tl = torch.tensor([l0.elapsed_time(l1)], device=dev, dtype=torch.float64)
-        dist.all_reduce(tl, op=dist.ReduceOp.MAX)
-        local_only_ms = float(tl.item()) / a.steps
+        tl = torch.tensor([l0.elapsed_time(l1) / a.steps], device=dev, dtype=torch.float64)
+        tl_all = torch.empty((world,), device=dev, dtype=torch.float64)
+        dist.all_gather_into_tensor(tl_all, tl)
+        local_only_ms = [round(float(x), 4) for x in tl_all.tolist()]  # per rank
 
     # ---- e2e: host buffers in and out ---------------------------------------------
     for _ in range(max(3, a.warmup)):

@@ -83,6 +83,7 @@ Workspace::~Workspace() {
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
   if (ev_sync) cudaEventDestroy(ev_sync);
+  if (ev_block) cudaEventDestroy(ev_block);
   if (stream) cudaStreamDestroy(stream);
 }
 
@@ -95,7 +96,18 @@ cudaError_t WsLease::init() {
   if (e != cudaSuccess) return e;
   e = cudaEventCreate(&ws->ev1);
   if (e != cudaSuccess) return e;
+  e = cudaEventCreateWithFlags(&ws->ev_block, cudaEventDisableTiming | cudaEventBlockingSync);
+  if (e != cudaSuccess) return e;
   return cudaEventCreateWithFlags(&ws->ev_sync, cudaEventDisableTiming);
+}
+
+// Wait for the workspace's stream.  blocking: sleep on an event instead of spinning, which leaves
+// the core to other threads (one process per GPU on a host with few cores per GPU).
+cudaError_t Workspace::wait(bool blocking) {
+  if (!blocking) return cudaStreamSynchronize(stream);
+  cudaError_t e = cudaEventRecord(ev_block, stream);
+  if (e != cudaSuccess) return e;
+  return cudaEventSynchronize(ev_block);
 }
 
 // ------------------------------------------------------------------------------
@@ -584,6 +596,10 @@ extern "C" cx_status cx_set_option(cx_index* h, const char* key, int64_t value) 
   if (!strcmp(key, "tensor_phase_growth")) {
     if (value < 0 || value > 1024) return fail(CX_ERR_VALIDATION, "tensor_phase_growth must be 0..1024");
     h->tensor_phase_growth = (uint32_t)value;
+    return CX_OK;
+  }
+  if (!strcmp(key, "blocking_sync")) {
+    h->blocking_sync = value != 0;
     return CX_OK;
   }
   if (!strcmp(key, "tensor_epi_warps")) {

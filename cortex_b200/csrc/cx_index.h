@@ -70,7 +70,7 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // concurrent searches (read-guard holders in the reference) never share state.
 struct Workspace {
   cudaStream_t stream = nullptr;
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_sync = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_sync = nullptr, ev_block = nullptr;
   void* d = nullptr;
   size_t d_bytes = 0;
   void* hp = nullptr;  // pinned
@@ -83,6 +83,7 @@ struct Workspace {
 
   cudaError_t ensure(size_t db, size_t hb);
   cudaError_t ensure_state(size_t nq);
+  cudaError_t wait(bool blocking);
   ~Workspace();
 };
 
@@ -115,6 +116,7 @@ struct cx_index {
   uint32_t tensor_phase_growth = 0xFFFFFFFFu; // tensor pass: each scan phase covers this many times the rows seen before
                                               // (0/1 = one phase; 0xFFFFFFFF = auto: one phase for B <= 256 and k <= 16, else 8 for k <= 16, 4 above)
   int profile = 0;
+  bool blocking_sync = false;      // search calls sleep on an event instead of spinning while the GPU works
   // stats
   std::atomic<uint64_t> launches{0}, q_stream{0}, q_tensor{0}, q_exact{0}, fallbacks{0}, h2d{0}, d2h{0};
   std::atomic<uint64_t> pass_ns{0}, pass_launches{0};

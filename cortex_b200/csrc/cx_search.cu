@@ -435,7 +435,7 @@ cx_status run_search(cx_index* h, Workspace* ws, const FilterHost& fh, const Sea
       CU(cudaMemcpyAsync(h_ok, sb.ok, B * 4, cudaMemcpyDeviceToHost, s));
     }
     if (h_total) CU(cudaMemcpyAsync(tot32.data(), sb.totals, B * 4, cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
+    CU(ws->wait(h->blocking_sync));
     if (h->profile) {
       float ms = 0.f;
       CU(cudaEventElapsedTime(&ms, ws->ev0, ws->ev1));
@@ -514,7 +514,7 @@ cx_status run_search(cx_index* h, Workspace* ws, const FilterHost& fh, const Sea
     } else {
       CU(cudaMemcpyAsync(h_ok, sb.ok, B * 4, cudaMemcpyDeviceToHost, s));
     }
-    CU(cudaStreamSynchronize(s));
+    CU(ws->wait(h->blocking_sync));
     if (h->profile) {
       float ms = 0.f;
       CU(cudaEventElapsedTime(&ms, ws->ev0, ws->ev1));
@@ -554,7 +554,7 @@ cx_status run_search(cx_index* h, Workspace* ws, const FilterHost& fh, const Sea
         h->launches += 1;
       }
       CU(cudaMemcpyAsync(h_ok, sb.ok, B * 4, cudaMemcpyDeviceToHost, s));
-      CU(cudaStreamSynchronize(s));
+      CU(ws->wait(h->blocking_sync));
       std::vector<uint32_t> still;
       for (uint32_t b : redo)
         if (!h_ok[b]) still.push_back(b);
@@ -563,7 +563,7 @@ cx_status run_search(cx_index* h, Workspace* ws, const FilterHost& fh, const Sea
     }
     if (retried && redo.empty()) {
       if (h_block) CU(cudaMemcpyAsync(h_block, sb.res, rb.total, cudaMemcpyDeviceToHost, s));
-      CU(cudaStreamSynchronize(s));
+      CU(ws->wait(h->blocking_sync));
     }
     ws->state_dirty = false;
     if (redo.empty()) return CX_OK;
@@ -590,14 +590,14 @@ cx_status run_search(cx_index* h, Workspace* ws, const FilterHost& fh, const Sea
     if (h_total) {
       uint32_t t32 = 0;
       CU(cudaMemcpyAsync(&t32, sb.n_total, 4, cudaMemcpyDeviceToHost, s));
-      CU(cudaStreamSynchronize(s));
+      CU(ws->wait(h->blocking_sync));
       h_total[b] = t32;
     }
   }
   h->q_exact += redo.size();
   CU(cudaGetLastError());
   if (h_block) CU(cudaMemcpyAsync(h_block, sb.res, rb.total, cudaMemcpyDeviceToHost, s));
-  CU(cudaStreamSynchronize(s));
+  CU(ws->wait(h->blocking_sync));
   return CX_OK;
 }
 

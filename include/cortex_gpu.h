@@ -178,7 +178,8 @@ cx_status cx_row_id(const cx_index* h, uint32_t row, uint8_t out_id[16]);
 cx_status cx_get_stats(const cx_index* h, cx_stats* out);
 /* Tuning / test hooks: "force_path" 0 auto, 1 stream (K1), 2 tensor (K2), 3 exact;
  * "stream_max_batch" largest query group K1 serves before K2 takes over;
- * "profile" 1 = bracket the scan-pass kernels with CUDA events on their stream. */
+ * "profile" 1 = bracket the scan-pass kernels with CUDA events on their stream;
+ * "blocking_sync" 1 = search calls sleep on an event instead of spinning while the GPU works. */
 cx_status cx_set_option(cx_index* h, const char* key, int64_t value);
 
 const char* cx_last_error(void);
