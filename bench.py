@@ -126,19 +126,21 @@ def make_queries_torch(corpus, b, seed):
 
 # ----------------------------------------------------------------------------------
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi sampled every 100 ms during the timed region, for the first `n_gpus` GPUs of the box."""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index=0):
-        self.index = index
+    def __init__(self, n_gpus=1):
+        self.n_gpus = n_gpus
         self.rows = []
         self.proc = None
 
     def start(self):
         try:
+            ids = ",".join(str(i) for i in range(self.n_gpus))
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                ["nvidia-smi", f"--id={ids}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
                  "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -157,22 +159,33 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        per = {}
         for r in self.rows:
             f = [x.strip() for x in r.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0]))
-                mx.append(float(f[1]))
+                g = per.setdefault(int(f[0]), {"sm": [], "mx": [], "w": [], "reasons": set()})
+                g["sm"].append(float(f[1]))
+                g["mx"].append(float(f[2]))
+                g["w"].append(float(f[3]))
             except ValueError:
                 continue
-            for nm, v in zip(names, f[3:7]):
+            for nm, v in zip(names, f[4:8]):
                 if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                    g["reasons"].add(nm)
+        if not per:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        gpus = [{"gpu": i, "sm_mhz": float(np.median(g["sm"])), "power_w": float(np.median(g["w"])),
+                 "reasons": sorted(g["reasons"])} for i, g in sorted(per.items())]
+        all_sm = [x["sm_mhz"] for x in gpus]
+        out = {"sm_mhz": float(np.median(all_sm)), "sm_max_mhz": max(max(g["mx"]) for g in per.values()),
+               "samples": len(per[min(per)]["sm"]), "reasons": sorted(set().union(*[g["reasons"] for g in per.values()]))}
+        if len(gpus) > 1:
+            out["sm_mhz_min_over_gpus"] = min(all_sm)
+            out["per_gpu"] = gpus
+        return out
 
 
 # ----------------------------------------------------------------------------------
@@ -310,7 +323,7 @@ def main():
         torch.cuda.synchronize()
 
     # ---- value: device-resident ---------------------------------------------------
-    clocks = ClockSampler(local_rank)
+    clocks = ClockSampler(world)
     if rank == 0:
         clocks.start()
     for _ in range(max(3, a.warmup)):

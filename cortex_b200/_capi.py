@@ -85,6 +85,9 @@ SYMBOLS = {
     "cx_row_id": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p]),
     "cx_get_stats": (C.c_int, [C.c_void_p, C.POINTER(CxStats)]),
     "cx_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
+    "cx_debug_tensor_plan": (C.c_int, [C.c_uint64, C.c_uint64, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p,
+                                       C.POINTER(C.c_uint32), C.c_void_p, C.POINTER(C.c_uint32),
+                                       C.POINTER(C.c_double)]),
     "cx_last_error": (C.c_char_p, []),
     "cx_version": (C.c_char_p, []),
 }

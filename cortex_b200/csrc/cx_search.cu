@@ -679,6 +679,26 @@ cx_status search_host(cx_index* h, const float* queries, uint64_t B, uint32_t ql
 
 }  // namespace
 
+// Test hook (no device needed): the launch plan of the tensor pass for a batch of n_queries against
+// n_rows rows on a GPU with sm_count SMs.  groups[] = queries per launch group (tensor_groups),
+// phases[] = row tiles per scan phase (tensor_phases with `sample_tiles` bootstrap tiles and the
+// given growth); *_n in: capacity, out: entries written.
+extern "C" cx_status cx_debug_tensor_plan(uint64_t n_queries, uint64_t n_rows, int sm_count, uint32_t sample_tiles,
+                                          uint32_t growth, uint32_t* groups, uint32_t* groups_n, uint32_t* phases,
+                                          uint32_t* phases_n, double* hits_per_kp) {
+  if (!groups || !groups_n || !phases || !phases_n || sm_count < 4) return fail(CX_ERR_VALIDATION, "bad argument");
+  const std::vector<uint32_t> g = tensor_groups(n_queries, sm_count);
+  double hk = 0.0;
+  const std::vector<uint32_t> ph = tensor_phases((uint32_t)((n_rows + 255) / 256), sample_tiles, growth, &hk);
+  if (g.size() > *groups_n || ph.size() > *phases_n) return fail(CX_ERR_VALIDATION, "output too small");
+  std::copy(g.begin(), g.end(), groups);
+  std::copy(ph.begin(), ph.end(), phases);
+  *groups_n = (uint32_t)g.size();
+  *phases_n = (uint32_t)ph.size();
+  if (hits_per_kp) *hits_per_kp = hk;
+  return CX_OK;
+}
+
 extern "C" cx_status cx_search(cx_index* h, const float* query, uint32_t qlen, uint64_t k,
                                const cx_filter* filter, uint8_t* out_ids, float* out_score, float* out_distance,
                                uint64_t* out_n) {

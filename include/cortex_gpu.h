@@ -182,6 +182,12 @@ cx_status cx_get_stats(const cx_index* h, cx_stats* out);
  * "blocking_sync" 1 = search calls sleep on an event instead of spinning while the GPU works. */
 cx_status cx_set_option(cx_index* h, const char* key, int64_t value);
 
+/* Test hook, needs no device: the tensor pass's launch plan -- queries per launch
+ * group and row tiles (256 rows) per scan phase. */
+cx_status cx_debug_tensor_plan(uint64_t n_queries, uint64_t n_rows, int sm_count, uint32_t sample_tiles,
+                               uint32_t growth, uint32_t* groups, uint32_t* groups_n, uint32_t* phases,
+                               uint32_t* phases_n, double* hits_per_kp);
+
 const char* cx_last_error(void);
 const char* cx_version(void);
 
