@@ -68,6 +68,12 @@ __device__ __forceinline__ float ref_score_from_distance(float d) {
   return s;
 }
 
+// norms outside this range come from squares that under- / overflowed fp32: the reference's
+// arithmetic is followed on the exact path only (rows: cx_exact.cu row_norm_kernel; queries: the
+// rescoring kernels report "not verified")
+constexpr float NORM_REGULAR_MIN = 1e-15f;
+constexpr float NORM_REGULAR_MAX = 1e15f;
+
 // ---- per-row metadata word ---------------------------------------------------
 constexpr uint32_t META_DEAD = 0x80000000u;
 constexpr uint32_t META_HAS = 0x40000000u;

@@ -22,6 +22,7 @@ __global__ void row_norm_kernel(float* __restrict__ E, float* __restrict__ norm,
   if (i >= n) return;
   float* row = E + (size_t)(r0 + i) * ld;
   float acc = 0.0f;
+  bool any = false;
   uint32_t d = 0;
   for (; d + 4 <= dim; d += 4) {
     float4 v = *reinterpret_cast<const float4*>(row + d);
@@ -29,12 +30,35 @@ __global__ void row_norm_kernel(float* __restrict__ E, float* __restrict__ norm,
     acc = ref_fold(acc, v.y, v.y);
     acc = ref_fold(acc, v.z, v.z);
     acc = ref_fold(acc, v.w, v.w);
+    any |= (v.x != 0.0f) | (v.y != 0.0f) | (v.z != 0.0f) | (v.w != 0.0f);
   }
-  for (; d < dim; ++d) acc = ref_fold(acc, row[d], row[d]);
+  for (; d < dim; ++d) {
+    acc = ref_fold(acc, row[d], row[d]);
+    any |= row[d] != 0.0f;
+  }
   for (d = dim; d < ld; ++d) row[d] = 0.0f;  // padding never contributes
   float nb = __fsqrt_rn(acc);
   norm[r0 + i] = nb;
-  rnorm[r0 + i] = __frcp_rn(nb);
+  // A row whose squares under- or overflow fp32 has a reference norm that is not its length, so the
+  // fast passes' error bounds do not hold for it (e.g. |x| ~ 1e-25: norm 0, sim = dot / 0 = +-inf,
+  // score 1 or 0).  Such rows get a NaN reciprocal norm -- no fast pass ever nominates them -- and are
+  // counted; an index that holds any is served by the exact path (cx_index.cu).  An all-zero row is
+  // regular: its score is NaN for every query in the reference too.
+  const bool irregular = any && !(nb >= NORM_REGULAR_MIN && nb <= NORM_REGULAR_MAX);
+  rnorm[r0 + i] = irregular ? __int_as_float(0x7fc00000) : __frcp_rn(nb);
+}
+
+__global__ void count_nan_kernel(const float* __restrict__ x, uint32_t n, uint32_t* __restrict__ out) {
+  uint32_t c = 0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) c += x[i] != x[i];
+  c = __reduce_add_sync(0xffffffffu, c);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+// rows with a NaN reciprocal norm (irregular rows, see row_norm_kernel) -> *out (zeroed here)
+void launch_count_irregular(const float* rnorm, uint32_t n, uint32_t* out, cudaStream_t s) {
+  cudaMemsetAsync(out, 0, 4, s);
+  if (n) count_nan_kernel<<<(n + 1023) / 1024 < 592 ? (n + 1023) / 1024 : 592, 256, 0, s>>>(rnorm, n, out);
 }
 
 // bf16 shadow for the tensor pass: rows are stored NORMALISED (x / |x|) so that the

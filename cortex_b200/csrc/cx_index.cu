@@ -110,6 +110,20 @@ cudaError_t Workspace::wait(bool blocking) {
   return cudaEventSynchronize(ev_block);
 }
 
+// Count the irregular rows (NaN reciprocal norm, cx_exact.cu) of the whole store into h->n_irr.
+// Enqueued on s; the value is valid after the caller's stream synchronisation.
+static cudaError_t refresh_irregular(cx_index* h, cudaStream_t s) {
+  if (!h->d_irr) {
+    cudaError_t e = cudaMalloc((void**)&h->d_irr, 4);
+    if (e != cudaSuccess) return e;
+    e = cudaMallocHost((void**)&h->h_irr, 4);
+    if (e != cudaSuccess) return e;
+    *h->h_irr = 0;
+  }
+  launch_count_irregular(h->dRnorm, (uint32_t)h->n_rows, h->d_irr, s);
+  return cudaMemcpyAsync(h->h_irr, h->d_irr, 4, cudaMemcpyDeviceToHost, s);
+}
+
 // ------------------------------------------------------------------------------
 static void free_store(cx_index* h) {
   cudaFree(h->dE);
@@ -216,6 +230,8 @@ extern "C" void cx_index_destroy(cx_index* h) {
   cudaSetDevice(h->device);
   for (Workspace* w : h->ws_free) delete w;
   free_store(h);
+  if (h->d_irr) cudaFree(h->d_irr);
+  if (h->h_irr) cudaFreeHost(h->h_irr);
   if (h->mut_stream) cudaStreamDestroy(h->mut_stream);
   delete h;
 }
@@ -291,6 +307,7 @@ extern "C" cx_status cx_insert_batch(cx_index* h, const uint8_t* ids, const floa
     launch_prepare_rows(h->dE, h->dNorm, h->dRnorm, h->dE16, h->dim, h->ld, h->ld16, r, 1, s);
     h->launches += h->dE16 ? 2 : 1;
   }
+  CU(refresh_irregular(h, s));
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(s));
   return CX_OK;
@@ -342,6 +359,7 @@ extern "C" cx_status cx_insert_batch_device(cx_index* h, const uint8_t* ids, con
   CU(cudaMemcpyAsync(h->dAgent + first_new, h->h_agent.data() + first_new, n * 4, cudaMemcpyHostToDevice, s));
   launch_prepare_rows(h->dE, h->dNorm, h->dRnorm, h->dE16, h->dim, h->ld, h->ld16, (uint32_t)first_new, (uint32_t)n, s);
   h->launches += h->dE16 ? 2 : 1;
+  CU(refresh_irregular(h, s));
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(s));
   return CX_OK;
@@ -430,6 +448,8 @@ extern "C" cx_status cx_rebuild(cx_index* h) {
   h->h_agent.swap(nagent);
   h->n_rows = nl;
   h->n_live = nl;
+  CU(refresh_irregular(h, s));  // removed rows are gone: recount
+  CU(cudaStreamSynchronize(s));
   return CX_OK;
 }
 

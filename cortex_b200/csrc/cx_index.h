@@ -101,6 +101,8 @@ struct cx_index {
   uint32_t* dAgent = nullptr;
   uint8_t* dIds = nullptr;
   void* dE16 = nullptr;
+  uint32_t* d_irr = nullptr;       // device counter + pinned host mirror: rows whose norm under/overflowed
+  uint32_t* h_irr = nullptr;       //   fp32 (cx_exact.cu); any such row sends every search to the exact path
   bool want_shadow = true;
   std::vector<uint8_t> h_ids;
   std::vector<uint32_t> h_meta, h_agent;
@@ -120,6 +122,8 @@ struct cx_index {
   // stats
   std::atomic<uint64_t> launches{0}, q_stream{0}, q_tensor{0}, q_exact{0}, fallbacks{0}, h2d{0}, d2h{0};
   std::atomic<uint64_t> pass_ns{0}, pass_launches{0};
+
+  uint32_t n_irregular() const { return h_irr ? *h_irr : 0u; }
 
   cx::StoreView view() const {
     cx::StoreView v;

@@ -52,6 +52,7 @@ struct ResultView {
 // K4: norms (reference order), reciprocal norms, bf16 shadow rows for rows [r0, r0+n)
 void launch_prepare_rows(float* E, float* norm, float* rnorm, void* E16, uint32_t dim, uint32_t ld,
                          uint32_t ld16, uint32_t r0, uint32_t n, cudaStream_t s);
+void launch_count_irregular(const float* rnorm, uint32_t n, uint32_t* out, cudaStream_t s);
 // queries: reference-order norm over qlen, reciprocal
 void launch_prepare_queries(const float* Q, float* qnorm, float* rqnorm, uint32_t nq, uint32_t qlen,
                             uint32_t ldq, cudaStream_t s);

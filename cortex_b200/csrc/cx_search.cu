@@ -236,7 +236,10 @@ Plan make_plan(const cx_index* h, uint64_t B, uint32_t qlen, uint32_t ldq, uint3
   p.cap = p.G * p.KP;
   p.cap_retry = 0;
   p.q_per_launch = 0;
-  p.fast = !threshold_mode && qlen == h->dim && n_rows >= 256 && kd <= 128 && p.KP >= kd &&
+  // rows whose norm under- / overflowed fp32 are outside the fast passes' error bounds (and are never
+  // nominated): while the index holds any, everything is served by the exact path
+  const bool regular = h->n_irregular() == 0;
+  p.fast = regular && !threshold_mode && qlen == h->dim && n_rows >= 256 && kd <= 128 && p.KP >= kd &&
            stream_scan_smem(h->ld, 8, p.KP) != 0 && select_smem(p.cap, h->ld) <= 227 * 1024 &&
            h->force_path != PATH_EXACT;
   p.tensor = false;
@@ -247,7 +250,7 @@ Plan make_plan(const cx_index* h, uint64_t B, uint32_t qlen, uint32_t ldq, uint3
   p.thr_fast = false;
   p.thr_cap = 0;
   if (threshold_mode) {
-    p.thr_fast = threshold == threshold && threshold >= THR_FAST_MIN && qlen == h->dim && n_rows >= 256 &&
+    p.thr_fast = regular && threshold == threshold && threshold >= THR_FAST_MIN && qlen == h->dim && n_rows >= 256 &&
                  h->force_path != PATH_EXACT && stream_scan_smem(h->ld, 8, 64) != 0 &&
                  threshold_rescore_smem(h->ld) <= 200 * 1024;
     if (p.thr_fast) {
@@ -761,7 +764,9 @@ extern "C" cx_status cx_dedup_scan(cx_index* h, float threshold, uint32_t per_no
     const uint64_t B = n_rows - r0 < QB ? n_rows - r0 : QB;
     Plan pl = make_plan(h, B, h->dim, h->ld, kd, true, threshold);
     if (!pl.thr_fast)
-      return fail(CX_ERR_VALIDATION, "dedup scan needs a threshold >= %.2f and at least 256 rows", THR_FAST_MIN);
+      return fail(CX_ERR_VALIDATION,
+                  "dedup scan needs a threshold >= %.2f, at least 256 rows and no row whose norm under- or "
+                  "overflows fp32 (%u such rows)", THR_FAST_MIN, h->n_irregular());
     WsLease lease(h);
     CU(lease.init());
     Workspace* ws = lease.ws;

@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(SEL_THREADS) select_rescore_kernel(const Selec
   // ---- 4. verify ---------------------------------------------------------------------
   if (tid == 0) {
     p.rv.n[q] = min(k, KS);
-    bool ok = KS >= k && !overflow && !truncated;
+    bool ok = KS >= k && !overflow && !truncated && na >= NORM_REGULAR_MIN && na <= NORM_REGULAR_MAX;
     if (ok) {
       const float sk = s_scorek, simk = s_simk;
       if (sk != sk) ok = false;
@@ -420,7 +420,11 @@ __global__ void __launch_bounds__(THR_THREADS) threshold_rescore_kernel(const Th
   }
 
   const uint32_t M = s_m;
-  const bool ok = n_app <= p.cap && M <= THR_MAX;
+  // a query whose norm under- / overflowed is not covered by the nominating pass's error bound: exact
+  // path.  (In a pair scan the queries are rows of the index, all regular or all-zero there: an all-zero
+  // row scores NaN against everything and simply has no partners.)
+  const bool q_regular = (na >= NORM_REGULAR_MIN && na <= NORM_REGULAR_MAX) || p.self_rows != nullptr;
+  const bool ok = n_app <= p.cap && M <= THR_MAX && q_regular;
   if (ok && M) {
     // order (key, idx) by key descending: bitonic network over a power of two, padded with 0
     uint32_t NK = 2;
