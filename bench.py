@@ -443,15 +443,15 @@ def main():
         sh_al = ShardedSearch(local_al, row_offset=rank * a.rows)
         res = None
         for _ in range(2):
-            res = sh_al.search(q_al, 100)
+            res = sh_al.autolink(q_al, None, 100, 0.75, 50)
         barrier()
         sa0 = ix.stats()
         ea0, ea1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         n_cyc = 3
         ea0.record()
         for _ in range(n_cyc):
-            res = sh_al.search(q_al, 100)
-            links = (res[1] >= 0.75).sum()
+            res = sh_al.autolink(q_al, None, 100, 0.75, 50)  # sharded search(k=100) + threshold + cap 50
+            links = res[2].sum()
         ea1.record()
         barrier()
         sa1 = ix.stats()

@@ -115,3 +115,24 @@ class ShardedSearch:
         keys = gathered[:, 0]
         dists = gathered[:, 1].to(torch.int32).view(torch.float32)
         return merge_gathered(keys, dists, k)
+
+    def autolink(self, new_embeddings: torch.Tensor, self_global_rows: Optional[torch.Tensor] = None, k: int = 100,
+                 threshold: float = 0.75, max_edges_per_node: int = 50):
+        """The scan step of AutoLinker::run_cycle (linker/auto_linker.rs:215-264) over the sharded corpus:
+        sharded search(embedding, k) (:221), skip the node itself (:235-237; `self_global_rows` [B] int64,
+        -1 = not in the index), keep `score >= threshold` (linker/rules.rs:50), at most
+        max_edges_per_node per node (:261).  Returns (global_rows [B,me] int64, score [B,me], n [B]);
+        identical on every rank."""
+        grow, score, _, n = self.search(new_embeddings, k)
+        B = grow.shape[0]
+        idx = torch.arange(grow.shape[1], device=grow.device)[None, :]
+        keep = (idx < n.to(torch.int64)[:, None]) & (score >= threshold)        # NaN >= t is False
+        if self_global_rows is not None:
+            keep &= grow != self_global_rows.to(grow.device).to(torch.int64)[:, None]
+        # stable compaction of the kept entries to the front (they are already best first)
+        order = torch.argsort((~keep).to(torch.int8), dim=1, stable=True)
+        me = min(int(max_edges_per_node), grow.shape[1])
+        out_rows = torch.gather(grow, 1, order)[:, :me]
+        out_score = torch.gather(score, 1, order)[:, :me]
+        out_n = keep.sum(dim=1).clamp(max=me).to(torch.int32)
+        return out_rows, out_score, out_n

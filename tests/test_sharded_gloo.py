@@ -41,8 +41,12 @@ def _worker(rank, world, port, n, d, b, k, out_dir):
 
     sh = ShardedSearch(local_search, row_offset=lo)
     grow, score, dd, nn = sh.search(torch.from_numpy(Q), k)
+    # auto-link step over the shards: the first b corpus rows play the new nodes (they are in the index)
+    self_rows = torch.arange(b, dtype=torch.int64)
+    arow, asc, an = sh.autolink(torch.from_numpy(corpus[:b].copy()), self_rows, k=20, threshold=0.75,
+                                max_edges_per_node=5)
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), grow=grow.numpy(), score=score.numpy(), dist=dd.numpy(),
-             n=nn.numpy())
+             n=nn.numpy(), arow=arow.numpy(), asc=asc.numpy(), an=an.numpy())
     dist.destroy_process_group()
 
 
@@ -61,6 +65,16 @@ def test_two_rank_merge_matches_single_index(tmp_path):
         assert np.array_equal(z["grow"], rows.astype(np.int64))
         assert np.array_equal(z["score"].view(np.uint32), sc.view(np.uint32))
         assert np.array_equal(z["dist"].view(np.uint32), di.view(np.uint32))
+    # auto-link: the reference loop (auto_linker.rs:215-264) on the single index
+    _, sc20, _, rows20, n20 = full.search_batch(corpus[:b], 20)
+    for r in range(2):
+        z = np.load(os.path.join(str(tmp_path), f"r{r}.npz"))
+        for q in range(b):
+            exp = [(int(rows20[q, j]), sc20[q, j]) for j in range(int(n20[q]))
+                   if int(rows20[q, j]) != q and sc20[q, j] >= np.float32(0.75)][:5]
+            got = [(int(z["arow"][q, j]), z["asc"][q, j]) for j in range(int(z["an"][q]))]
+            assert [g[0] for g in got] == [e[0] for e in exp], (q, got, exp)
+            assert all(np.float32(g[1]).view(np.uint32) == np.float32(e[1]).view(np.uint32) for g, e in zip(got, exp))
 
 
 def test_merge_orders_ties_nan_and_short_lists():
