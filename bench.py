@@ -364,16 +364,20 @@ def main():
         for _ in range(3):
             local_search(d_q, a.k)
         barrier()
+        sl0 = ix.stats()
         l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0.record()
         for _ in range(a.steps):
             local_search(d_q, a.k)
         l1.record()
         barrier()
-        tl = torch.tensor([l0.elapsed_time(l1) / a.steps], device=dev, dtype=torch.float64)
-        tl_all = torch.empty((world,), device=dev, dtype=torch.float64)
-        dist.all_gather_into_tensor(tl_all, tl)
-        local_only_ms = [round(float(x), 4) for x in tl_all.tolist()]  # per rank
+        sl1 = ix.stats()
+        k_us = (sl1["pass_kernel_ns"] - sl0["pass_kernel_ns"]) * 1e-3 / max(1, sl1["pass_kernel_launches"] - sl0["pass_kernel_launches"])
+        tl = torch.tensor([l0.elapsed_time(l1) / a.steps, k_us], device=dev, dtype=torch.float64)
+        tl_all = torch.empty((world, 2), device=dev, dtype=torch.float64)
+        dist.all_gather_into_tensor(tl_all.view(-1), tl)
+        local_only_ms = {"step_ms_per_rank": [round(float(x), 4) for x in tl_all[:, 0].tolist()],
+                         "scan_kernel_us_per_rank": [round(float(x), 1) for x in tl_all[:, 1].tolist()]}
 
     # ---- e2e: host buffers in and out ---------------------------------------------
     for _ in range(max(3, a.warmup)):
