@@ -301,7 +301,13 @@ def main():
         out = ix.search_batch_device(q, k, stream=stream.cuda_stream, out=out)
         return out
 
-    sh = ShardedSearch(local_search, row_offset=rank * a.rows)
+    def local_begin(q, k):
+        nonlocal out
+        out, ticket = ix.search_batch_device_begin(q, k, stream=stream.cuda_stream, out=out)
+        return out, ticket
+
+    sh = ShardedSearch(local_search, row_offset=rank * a.rows, local_begin=local_begin,
+                       local_end=ix.search_batch_device_end, ticket_ok_ptr=ix.ticket_ok_ptr)
 
     def step_device():
         return sh.search(d_q, a.k)
@@ -444,7 +450,13 @@ def main():
             out_al = ix.search_batch_device(q, k, stream=stream.cuda_stream, out=out_al)
             return out_al
 
-        sh_al = ShardedSearch(local_al, row_offset=rank * a.rows)
+        def local_al_begin(q, k):
+            nonlocal out_al
+            out_al, ticket = ix.search_batch_device_begin(q, k, stream=stream.cuda_stream, out=out_al)
+            return out_al, ticket
+
+        sh_al = ShardedSearch(local_al, row_offset=rank * a.rows, local_begin=local_al_begin,
+                              local_end=ix.search_batch_device_end, ticket_ok_ptr=ix.ticket_ok_ptr)
         res = None
         for _ in range(2):
             res = sh_al.autolink(q_al, None, 100, 0.75, 50)

@@ -9,12 +9,17 @@
 namespace cx {
 
 // payload per (query, slot): word0 = score-order key (high 32) | distance bits (low 32),
-//                            word1 = global row; word0 == 0 marks an empty slot
+//                            word1 = global row; word0 == 0 marks an empty slot.
+// Two trailer words follow the B*k slots: [0] = how many of this rank's queries are still unverified
+// (their slots may change once the rank has retried them), [1] = reserved.  The trailer lets every
+// rank learn from the gathered payloads alone whether the exchange has to be repeated.
 __global__ void pack_topk_kernel(const uint32_t* __restrict__ rows, const float* __restrict__ score,
-                                 const float* __restrict__ dist, const uint32_t* __restrict__ n, uint32_t B,
-                                 uint32_t k, uint64_t row_offset, uint64_t* __restrict__ payload) {
+                                 const float* __restrict__ dist, const uint32_t* __restrict__ n,
+                                 const uint32_t* __restrict__ ok, uint32_t B, uint32_t k, uint64_t row_offset,
+                                 uint64_t* __restrict__ payload) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * k) return;
+  if (ok && i < B && !ok[i]) atomicAdd(reinterpret_cast<unsigned long long*>(payload + 2 * (size_t)B * k), 1ull);
   const uint32_t b = i / k, j = i % k;
   uint64_t w0 = 0, w1 = 0;
   if (j < n[b]) {
@@ -28,14 +33,21 @@ __global__ void pack_topk_kernel(const uint32_t* __restrict__ rows, const float*
 // one CTA per query; W*k candidates ranked by counting (all (ord,row) pairs are distinct)
 __global__ void merge_topk_kernel(const uint64_t* __restrict__ gathered, uint32_t W, uint32_t B, uint32_t k,
                                   int64_t* __restrict__ out_rows, float* __restrict__ out_score,
-                                  float* __restrict__ out_dist, uint32_t* __restrict__ out_n) {
+                                  float* __restrict__ out_dist, uint32_t* __restrict__ out_n,
+                                  uint64_t* __restrict__ out_unverified) {
   extern __shared__ uint64_t sm[];  // [W*k][2]
   const uint32_t b = blockIdx.x, tid = threadIdx.x, n = W * k;
+  const size_t stride = 2 * (size_t)B * k + 2;  // words per rank: slots + trailer
   __shared__ uint32_t s_valid;
   if (tid == 0) s_valid = 0;
+  if (b == 0 && tid == 0 && out_unverified) {
+    uint64_t t = 0;
+    for (uint32_t w = 0; w < W; ++w) t += gathered[(size_t)w * stride + stride - 2];
+    *out_unverified = t;
+  }
   for (uint32_t i = tid; i < n; i += blockDim.x) {
     const uint32_t w = i / k, j = i % k;
-    const uint64_t* src = gathered + 2 * (((size_t)w * B + b) * k + j);
+    const uint64_t* src = gathered + (size_t)w * stride + 2 * ((size_t)b * k + j);
     sm[2 * i] = src[0];
     sm[2 * i + 1] = src[1];
   }
@@ -110,20 +122,21 @@ void launch_autolink_filter(const uint32_t* rows, const float* score, const uint
 using namespace cx;
 
 extern "C" cx_status cx_pack_topk_device(const uint32_t* d_rows, const float* d_score, const float* d_distance,
-                                         const uint32_t* d_n, uint64_t B, uint64_t k, uint64_t row_offset,
-                                         uint64_t* d_payload, void* stream) {
+                                         const uint32_t* d_n, const uint32_t* d_ok, uint64_t B, uint64_t k,
+                                         uint64_t row_offset, uint64_t* d_payload, void* stream) {
   if (!d_rows || !d_score || !d_distance || !d_n || !d_payload) return fail(CX_ERR_VALIDATION, "null device buffer");
   if (!B || !k) return CX_OK;
   const uint64_t total = B * k;
+  CU(cudaMemsetAsync(d_payload + 2 * total, 0, 16, (cudaStream_t)stream));  // trailer
   pack_topk_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      d_rows, d_score, d_distance, d_n, (uint32_t)B, (uint32_t)k, row_offset, d_payload);
+      d_rows, d_score, d_distance, d_n, d_ok, (uint32_t)B, (uint32_t)k, row_offset, d_payload);
   CU(cudaGetLastError());
   return CX_OK;
 }
 
 extern "C" cx_status cx_merge_topk_device(const uint64_t* d_gathered, uint32_t world, uint64_t B, uint64_t k,
                                           int64_t* d_out_rows, float* d_out_score, float* d_out_distance,
-                                          uint32_t* d_out_n, void* stream) {
+                                          uint32_t* d_out_n, uint64_t* d_out_unverified, void* stream) {
   if (!d_gathered || !d_out_rows || !d_out_score || !d_out_distance || !d_out_n)
     return fail(CX_ERR_VALIDATION, "null device buffer");
   if (!B || !k || !world) return CX_OK;
@@ -131,7 +144,8 @@ extern "C" cx_status cx_merge_topk_device(const uint64_t* d_gathered, uint32_t w
   if (smem > 200 * 1024) return fail(CX_ERR_VALIDATION, "world * k too large for the merge kernel");
   CU(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   merge_topk_kernel<<<(unsigned)B, 128, smem, (cudaStream_t)stream>>>(d_gathered, world, (uint32_t)B, (uint32_t)k,
-                                                                      d_out_rows, d_out_score, d_out_distance, d_out_n);
+                                                                      d_out_rows, d_out_score, d_out_distance, d_out_n,
+                                                                      d_out_unverified);
   CU(cudaGetLastError());
   return CX_OK;
 }

@@ -12,6 +12,7 @@
 // Whatever the path, emitted scores/distances come from the reference's operation
 // sequence, and ids follow (score desc, NaN last, row asc).
 #include <algorithm>
+#include <memory>
 #include <vector>
 
 #include "cx_index.h"
@@ -353,9 +354,16 @@ struct PairScan {
   uint32_t tile0;             // first row tile worth scanning (rows below it cannot qualify)
 };
 
+// phase: RUN_ALL = the whole call; RUN_ENQUEUE = everything up to (and including) the copy of the
+// verification flags to the host, no wait (returns CX_PENDING; only for plans with pl.fast);
+// RUN_FINISH = wait, then retry / fall back what could not be verified.
+enum { RUN_ALL = 0, RUN_ENQUEUE = 1, RUN_FINISH = 2 };
+constexpr cx_status CX_PENDING = (cx_status)-1;
+
 cx_status run_search(cx_index* h, Workspace* ws, const FilterHost& fh, const SearchBufs& sb, const Plan& pl,
                      bool threshold_mode, float threshold, char* h_block, uint32_t* h_ok,
-                     uint64_t* h_total /* threshold mode: per-query totals */, const PairScan* tp = nullptr) {
+                     uint64_t* h_total /* threshold mode: per-query totals */, const PairScan* tp = nullptr,
+                     int phase = RUN_ALL) {
   cudaStream_t s = ws->stream;
   const uint64_t B = pl.B;
   StoreView st = h->view();
@@ -369,7 +377,8 @@ cx_status run_search(cx_index* h, Workspace* ws, const FilterHost& fh, const Sea
   DevFilter flt = fh.dev;
   flt.excl_rows = sb.excl;
   flt.n_excl = (uint32_t)fh.excl_rows.size();
-  if (flt.n_excl) CU(cudaMemcpyAsync(sb.excl, fh.excl_rows.data(), flt.n_excl * 4, cudaMemcpyHostToDevice, s));
+  if (flt.n_excl && phase != RUN_FINISH)
+    CU(cudaMemcpyAsync(sb.excl, fh.excl_rows.data(), flt.n_excl * 4, cudaMemcpyHostToDevice, s));
 
   ResultView rv;
   rv.rows = sb.rows;
@@ -455,67 +464,66 @@ cx_status run_search(cx_index* h, Workspace* ws, const FilterHost& fh, const Sea
     if (redo.empty()) return CX_OK;
     if (tp) return fail(CX_ERR_VALIDATION, "threshold scan overflow");  // pair scans have no per-query exact fallback
   } else if (pl.fast) {
-    CU(ws->ensure_state(B));
-    ws->state_dirty = true;  // until the select kernel has re-zeroed it and the stream drained cleanly
     CandView cv;
     cv.keys = sb.cand_keys;
     cv.cnt = ws->d_cnt;
     cv.gtau = ws->d_gtau;
     cv.cap = pl.cap;
     cv.G = pl.G;
-    cv.KP = pl.KP;
-    uint32_t n_pass = 0;
-    if (pl.tensor) {
-      launch_query_bf16(sb.dQ, pl.ldq, h->dim, (uint32_t)B, (uint32_t)align_up(B, 128), sb.q16, h->ld16, s);
-      h->launches += 1;
-    }
-    if (pl.tensor) {
-      cv.KP = pl.KPt;
-      const bool check_rows = flt.has_kinds || flt.has_agent || flt.n_excl || h->n_live != h->n_rows;
-      // cut-off bootstrap for every launch group first (the sample buffer is reused in stream order)
-      uint64_t q0 = 0;
-      for (const uint32_t nq : pl.groups) {
-        CU(launch_tensor_bootstrap(st, sb.q16, (uint32_t)q0, nq, flt, check_rows, cv, sb.dump, pl.n_slots,
-                                   h->sm_count, s));
-        h->launches += 2;
-        q0 += nq;
-      }
-      if (h->profile) CU(cudaEventRecord(ws->ev0, s));
-      const std::vector<uint32_t> phases =
-          tensor_phases(tensor_tiles(st.n_rows), pl.n_slots, pl.growth, nullptr);
-      q0 = 0;
-      for (const uint32_t nq : pl.groups) {
-        uint32_t tile0 = 0;
-        for (size_t ph = 0; ph < phases.size(); ++ph) {
-          if (ph) {  // tighten the cut-off with what the earlier phases found
-            CU(launch_tau_refine(cv, (uint32_t)q0, nq, 2.0f * eps_tensor(h->dim), s));
+    cv.KP = pl.tensor ? pl.KPt : pl.KP;
+    // scans of the whole shard this call makes (what the profile events cover)
+    const uint32_t n_pass = pl.tensor ? (uint32_t)pl.groups.size() : (uint32_t)((B + 7) / 8);
+    if (h_block) h_ok = (uint32_t*)(h_block + rb.ok);
+    if (phase != RUN_FINISH) {
+      CU(ws->ensure_state(B));
+      ws->state_dirty = true;  // until the select kernel has re-zeroed it and the stream drained cleanly
+      cv.cnt = ws->d_cnt;
+      cv.gtau = ws->d_gtau;
+      if (pl.tensor) {
+        launch_query_bf16(sb.dQ, pl.ldq, h->dim, (uint32_t)B, (uint32_t)align_up(B, 128), sb.q16, h->ld16, s);
+        h->launches += 1;
+        const bool check_rows = flt.has_kinds || flt.has_agent || flt.n_excl || h->n_live != h->n_rows;
+        // cut-off bootstrap for every launch group first (the sample buffer is reused in stream order)
+        uint64_t q0 = 0;
+        for (const uint32_t nq : pl.groups) {
+          CU(launch_tensor_bootstrap(st, sb.q16, (uint32_t)q0, nq, flt, check_rows, cv, sb.dump, pl.n_slots,
+                                     h->sm_count, s));
+          h->launches += 2;
+          q0 += nq;
+        }
+        if (h->profile) CU(cudaEventRecord(ws->ev0, s));
+        const std::vector<uint32_t> phases =
+            tensor_phases(tensor_tiles(st.n_rows), pl.n_slots, pl.growth, nullptr);
+        q0 = 0;
+        for (const uint32_t nq : pl.groups) {
+          uint32_t tile0 = 0;
+          for (size_t ph = 0; ph < phases.size(); ++ph) {
+            if (ph) {  // tighten the cut-off with what the earlier phases found
+              CU(launch_tau_refine(cv, (uint32_t)q0, nq, 2.0f * eps_tensor(h->dim), s));
+              h->launches += 1;
+            }
+            CU(launch_tensor_scan(st, sb.q16, (uint32_t)q0, nq, flt, check_rows, cv, sb.lists, tile0, phases[ph],
+                                  h->sm_count, s));
+            tile0 += phases[ph];
             h->launches += 1;
           }
-          CU(launch_tensor_scan(st, sb.q16, (uint32_t)q0, nq, flt, check_rows, cv, sb.lists, tile0, phases[ph],
-                                h->sm_count, s));
-          tile0 += phases[ph];
-          h->launches += 1;
+          q0 += nq;
         }
-        ++n_pass;  // one scan of the whole shard (all of its phases)
-        q0 += nq;
+      } else {
+        if (h->profile) CU(cudaEventRecord(ws->ev0, s));
+        for (uint64_t q0 = 0; q0 < B; q0 += 8) {
+          const uint32_t nq = (uint32_t)(B - q0 < 8 ? B - q0 : 8);
+          CU(launch_stream_scan(st, qv, (uint32_t)q0, nq, flt, cv, h->sm_count, s));
+        }
+        h->launches += n_pass;
       }
-    } else {
-      if (h->profile) CU(cudaEventRecord(ws->ev0, s));
-      for (uint64_t q0 = 0; q0 < B; q0 += 8) {
-        const uint32_t nq = (uint32_t)(B - q0 < 8 ? B - q0 : 8);
-        CU(launch_stream_scan(st, qv, (uint32_t)q0, nq, flt, cv, h->sm_count, s));
-        ++n_pass;
-      }
-    }
-    if (h->profile) CU(cudaEventRecord(ws->ev1, s));
-    CU(launch_select_rescore(st, qv, 0, (uint32_t)B, cv, rv, pl.tensor ? eps_tensor(h->dim) : eps_stream(h->dim),
-                             /*scale_by_rqn=*/pl.tensor ? 0 : 1, s));
-    h->launches += (pl.tensor ? 0 : n_pass) + 1;
-    if (h_block) {
-      CU(cudaMemcpyAsync(h_block, sb.res, rb.total, cudaMemcpyDeviceToHost, s));
-      h_ok = (uint32_t*)(h_block + rb.ok);
-    } else {
-      CU(cudaMemcpyAsync(h_ok, sb.ok, B * 4, cudaMemcpyDeviceToHost, s));
+      if (h->profile) CU(cudaEventRecord(ws->ev1, s));
+      CU(launch_select_rescore(st, qv, 0, (uint32_t)B, cv, rv, pl.tensor ? eps_tensor(h->dim) : eps_stream(h->dim),
+                               /*scale_by_rqn=*/pl.tensor ? 0 : 1, s));
+      h->launches += 1;
+      if (h_block) CU(cudaMemcpyAsync(h_block, sb.res, rb.total, cudaMemcpyDeviceToHost, s));
+      else CU(cudaMemcpyAsync(h_ok, sb.ok, B * 4, cudaMemcpyDeviceToHost, s));
+      if (phase == RUN_ENQUEUE) return CX_PENDING;
     }
     CU(ws->wait(h->blocking_sync));
     if (h->profile) {
@@ -806,10 +814,20 @@ extern "C" cx_status cx_dedup_scan(cx_index* h, float threshold, uint32_t per_no
   return CX_OK;
 }
 
-extern "C" cx_status cx_search_batch_device(cx_index* h, const float* d_queries, uint64_t B, uint64_t k,
-                                            const cx_filter* filter, uint32_t* d_out_rows, float* d_out_score,
-                                            float* d_out_distance, uint8_t* d_out_ids, uint32_t* d_out_n,
-                                            void* stream) {
+// A device-resident batch search in flight (cx_search_batch_device_begin .. _end).
+struct DeviceSearch {
+  WsLease lease;
+  FilterHost fh;
+  SearchBufs sb;
+  Plan pl;
+  explicit DeviceSearch(cx_index* h) : lease(h) {}
+};
+
+// Shared by the one-call and the begin / end forms.  ticket == nullptr: run to completion.
+static cx_status device_search(cx_index* h, const float* d_queries, uint64_t B, uint64_t k, const cx_filter* filter,
+                               uint32_t* d_out_rows, float* d_out_score, float* d_out_distance, uint8_t* d_out_ids,
+                               uint32_t* d_out_n, void* stream, void** ticket) {
+  if (ticket) *ticket = nullptr;
   if (!h) return fail(CX_ERR_VALIDATION, "null index");
   if (!d_queries || !d_out_rows || !d_out_score || !d_out_distance || !d_out_n)
     return fail(CX_ERR_VALIDATION, "null device buffer");
@@ -823,17 +841,16 @@ extern "C" cx_status cx_search_batch_device(cx_index* h, const float* d_queries,
   if (k > h->n_rows) return fail(CX_ERR_VALIDATION, "device search needs k <= rows in the shard");
   const uint32_t kd = (uint32_t)k;
   const uint32_t ldq = h->ld;
-  FilterHost fh;
-  build_filter(h, filter, &fh);
-  const Plan pl = make_plan(h, B, h->dim, ldq, kd, false);
-  WsLease lease(h);
-  CU(lease.init());
-  Workspace* ws = lease.ws;
-  SearchBufs sb;
+  std::unique_ptr<DeviceSearch> t(new DeviceSearch(h));
+  build_filter(h, filter, &t->fh);
+  t->pl = make_plan(h, B, h->dim, ldq, kd, false);
+  CU(t->lease.init());
+  Workspace* ws = t->lease.ws;
   const bool own_q = h->dim != h->ld;
-  const size_t dbytes = carve_bufs(nullptr, h, pl, (uint32_t)fh.excl_rows.size(), own_q, false, &sb);
+  const size_t dbytes = carve_bufs(nullptr, h, t->pl, (uint32_t)t->fh.excl_rows.size(), own_q, false, &t->sb);
   CU(ws->ensure(dbytes, align_up(B * 4, 256)));
-  carve_bufs(ws->d, h, pl, (uint32_t)fh.excl_rows.size(), own_q, false, &sb);
+  carve_bufs(ws->d, h, t->pl, (uint32_t)t->fh.excl_rows.size(), own_q, false, &t->sb);
+  SearchBufs& sb = t->sb;
   // order after whatever produced the queries on the caller's stream
   CU(cudaEventRecord(ws->ev_sync, user));
   CU(cudaStreamWaitEvent(ws->stream, ws->ev_sync, 0));
@@ -849,8 +866,54 @@ extern "C" cx_status cx_search_batch_device(cx_index* h, const float* d_queries,
   sb.dist = d_out_distance;
   sb.ids = d_out_ids;
   sb.n = d_out_n;
-  cx_status st = run_search(h, ws, fh, sb, pl, false, 0.0f, nullptr, (uint32_t*)ws->hp, nullptr);
+  const bool split = ticket != nullptr && t->pl.fast;
+  cx_status st = run_search(h, ws, t->fh, sb, t->pl, false, 0.0f, nullptr, (uint32_t*)ws->hp, nullptr, nullptr,
+                            split ? RUN_ENQUEUE : RUN_ALL);
+  if (st == CX_PENDING) {
+    // the caller's stream continues after the results (they are final unless _end reports retries)
+    CU(cudaEventRecord(ws->ev_sync, ws->stream));
+    CU(cudaStreamWaitEvent(user, ws->ev_sync, 0));
+    *ticket = t.release();
+    return CX_OK;
+  }
   // run_search returned with its stream idle: the results are complete and visible
+  return st;
+}
+
+extern "C" cx_status cx_search_batch_device(cx_index* h, const float* d_queries, uint64_t B, uint64_t k,
+                                            const cx_filter* filter, uint32_t* d_out_rows, float* d_out_score,
+                                            float* d_out_distance, uint8_t* d_out_ids, uint32_t* d_out_n,
+                                            void* stream) {
+  return device_search(h, d_queries, B, k, filter, d_out_rows, d_out_score, d_out_distance, d_out_ids, d_out_n,
+                       stream, nullptr);
+}
+
+extern "C" cx_status cx_search_batch_device_begin(cx_index* h, const float* d_queries, uint64_t B, uint64_t k,
+                                                  const cx_filter* filter, uint32_t* d_out_rows,
+                                                  float* d_out_score, float* d_out_distance, uint8_t* d_out_ids,
+                                                  uint32_t* d_out_n, void* stream, void** ticket) {
+  if (!ticket) return fail(CX_ERR_VALIDATION, "null ticket");
+  return device_search(h, d_queries, B, k, filter, d_out_rows, d_out_score, d_out_distance, d_out_ids, d_out_n,
+                       stream, ticket);
+}
+
+extern "C" cx_status cx_search_ticket_ok(void* ticket, const uint32_t** d_ok) {
+  if (!d_ok) return fail(CX_ERR_VALIDATION, "null argument");
+  *d_ok = ticket ? ((DeviceSearch*)ticket)->sb.ok : nullptr;
+  return CX_OK;
+}
+
+extern "C" cx_status cx_search_batch_device_end(cx_index* h, void* ticket, uint64_t* n_redone) {
+  if (n_redone) *n_redone = 0;
+  if (!ticket) return CX_OK;  // _begin already ran the call to completion
+  std::unique_ptr<DeviceSearch> t((DeviceSearch*)ticket);
+  if (!h) return fail(CX_ERR_VALIDATION, "null index");
+  CU(cudaSetDevice(h->device));
+  Workspace* ws = t->lease.ws;
+  const uint64_t before = h->fallbacks.load();
+  cx_status st = run_search(h, ws, t->fh, t->sb, t->pl, false, 0.0f, nullptr, (uint32_t*)ws->hp, nullptr, nullptr,
+                            RUN_FINISH);
+  if (n_redone) *n_redone = h->fallbacks.load() - before;
   return st;
 }
 

@@ -300,6 +300,53 @@ class GpuVectorIndex:
                                               n.data_ptr(), C.c_void_p(stream)))
         return out
 
+    def search_batch_device_begin(self, d_queries, k: int, filter: Optional[VectorFilter] = None, stream: int = 0,
+                                  out=None):
+        """Enqueue a device-resident search without waiting (cx_search_batch_device_begin).  Returns
+        (out, ticket): `stream` is ordered after the results; call search_batch_device_end(ticket)
+        before the next mutation -- it reports how many queries had to be redone."""
+        import torch
+
+        assert d_queries.is_cuda and d_queries.dtype == torch.float32 and d_queries.is_contiguous()
+        B = d_queries.shape[0]
+        if out is None:
+            dev = d_queries.device
+            out = (torch.empty((B, k), dtype=torch.int32, device=dev),
+                   torch.empty((B, k), dtype=torch.float32, device=dev),
+                   torch.empty((B, k), dtype=torch.float32, device=dev),
+                   torch.empty((B,), dtype=torch.int32, device=dev))
+        rows, sc, di, n = out
+        cf = _c_filter(filter)
+        ticket = C.c_void_p()
+        _check(self._L.cx_search_batch_device_begin(self._h, d_queries.data_ptr(), B, int(k), cf.ptr if cf else None,
+                                                    rows.data_ptr(), sc.data_ptr(), di.data_ptr(), None,
+                                                    n.data_ptr(), C.c_void_p(stream), C.byref(ticket)))
+        return out, ticket
+
+    def ticket_ok_ptr(self, ticket) -> int:
+        """Device address of the verification flags of a search in flight (0 = none: all verified)."""
+        p = C.c_void_p()
+        _check(self._L.cx_search_ticket_ok(ticket, C.byref(p)))
+        return p.value or 0
+
+    def ticket_ok(self, ticket, B: int):
+        """The verification flags as a borrowed int32 CUDA tensor [B] (None if there are none)."""
+        import torch
+
+        addr = self.ticket_ok_ptr(ticket)
+        if not addr:
+            return None
+
+        class _Borrowed:
+            __cuda_array_interface__ = {"shape": (B,), "typestr": "<i4", "data": (addr, False), "version": 3}
+
+        return torch.as_tensor(_Borrowed(), device=f"cuda:{self.device}")
+
+    def search_batch_device_end(self, ticket) -> int:
+        n = C.c_uint64(0)
+        _check(self._L.cx_search_batch_device_end(self._h, ticket, C.byref(n)))
+        return int(n.value)
+
     def autolink_batch(self, new_nodes: Iterable[Tuple[bytes, Sequence[float]]], threshold: float = 0.75,
                        k: int = 100, max_edges_per_node: int = 50) -> Dict[bytes, List[Tuple[bytes, float]]]:
         """The scan step of AutoLinker::run_cycle (linker/auto_linker.rs:215-264) for a batch of new

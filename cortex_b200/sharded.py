@@ -62,15 +62,22 @@ def merge_gathered(keys: torch.Tensor, dists: torch.Tensor, k: int):
 class ShardedSearch:
     """local_search(d_queries, k) -> (rows int32 [B,k], score f32 [B,k], dist f32 [B,k], n int32 [B])"""
 
-    def __init__(self, local_search: Callable, row_offset: int, group: Optional[dist.ProcessGroup] = None):
+    def __init__(self, local_search: Callable, row_offset: int, group: Optional[dist.ProcessGroup] = None,
+                 local_begin: Optional[Callable] = None, local_end: Optional[Callable] = None,
+                 ticket_ok_ptr: Optional[Callable] = None):
+        """local_begin(d_queries, k) -> (out, ticket) / local_end(ticket) -> n_redone / ticket_ok_ptr(ticket) ->
+        device address: the two-step form of the local scan (GpuVectorIndex.search_batch_device_begin/_end).
+        With them the exchange is enqueued behind the scan with no host wait in between."""
         self.local_search = local_search
+        self.local_begin, self.local_end, self.ticket_ok_ptr = local_begin, local_end, ticket_ok_ptr
         self.row_offset = int(row_offset)
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self._bufs = {}
 
-    def _search_cuda(self, rows, score, d, n, k):
-        """GPU exchange: pack kernel -> one NCCL all_gather -> merge kernel (cx_merge.cu)."""
+    def _exchange_cuda(self, rows, score, d, n, k, ok_ptr=0):
+        """GPU exchange: pack kernel -> one NCCL all_gather -> merge kernel (cx_merge.cu), all enqueued on
+        the current stream.  Returns the merged lists and a device word = unverified queries over all ranks."""
         import ctypes as C
 
         from . import _capi
@@ -81,26 +88,51 @@ class ShardedSearch:
         key = (B, k, str(dev))
         buf = self._bufs.get(key)
         if buf is None:
-            buf = (torch.empty((B, k, 2), dtype=torch.int64, device=dev),
-                   torch.empty((self.world, B, k, 2), dtype=torch.int64, device=dev),
+            words = B * k * 2 + 2  # slots + trailer (cortex_gpu.h)
+            buf = (torch.empty((words,), dtype=torch.int64, device=dev),
+                   torch.empty((self.world * words,), dtype=torch.int64, device=dev),
                    torch.empty((B, k), dtype=torch.int64, device=dev),
                    torch.empty((B, k), dtype=torch.float32, device=dev),
                    torch.empty((B, k), dtype=torch.float32, device=dev),
-                   torch.empty((B,), dtype=torch.int32, device=dev))
+                   torch.empty((B,), dtype=torch.int32, device=dev),
+                   torch.zeros((1,), dtype=torch.int64, device=dev),
+                   torch.zeros((1,), dtype=torch.int64).pin_memory())
             self._bufs[key] = buf
-        payload, gathered, grow, gscore, gdist, gn = buf
-        st = L.cx_pack_topk_device(rows.data_ptr(), score.data_ptr(), d.data_ptr(), n.data_ptr(), B, k,
-                                   self.row_offset, payload.data_ptr(), stream)
+        payload, gathered, grow, gscore, gdist, gn, unv, unv_host = buf
+        st = L.cx_pack_topk_device(rows.data_ptr(), score.data_ptr(), d.data_ptr(), n.data_ptr(),
+                                   C.c_void_p(ok_ptr) if ok_ptr else None, B, k, self.row_offset,
+                                   payload.data_ptr(), stream)
         if st != 0:
             raise RuntimeError(L.cx_last_error().decode())
-        dist.all_gather_into_tensor(gathered.view(self.world * B, k, 2), payload, group=self.group)
+        dist.all_gather_into_tensor(gathered, payload, group=self.group)
         st = L.cx_merge_topk_device(gathered.data_ptr(), self.world, B, k, grow.data_ptr(), gscore.data_ptr(),
-                                    gdist.data_ptr(), gn.data_ptr(), stream)
+                                    gdist.data_ptr(), gn.data_ptr(), unv.data_ptr(), stream)
         if st != 0:
             raise RuntimeError(L.cx_last_error().decode())
-        return grow, gscore, gdist, gn
+        return (grow, gscore, gdist, gn), unv, unv_host
+
+    def _search_cuda(self, rows, score, d, n, k):
+        return self._exchange_cuda(rows, score, d, n, k)[0]
+
+    def _search_overlapped(self, queries, k):
+        """scan -> pack -> all_gather -> merge enqueued back to back; ONE host wait at the end.  The
+        gathered trailers tell every rank whether any rank still has unverified queries; only then (rare)
+        do all ranks repeat the exchange after the local retries."""
+        out, ticket = self.local_begin(queries, k)
+        rows, score, d, n = out
+        res, unv, unv_host = self._exchange_cuda(rows, score, d, n, k, self.ticket_ok_ptr(ticket))
+        unv_host.copy_(unv, non_blocking=True)
+        # the one host wait of the step; after it nothing reads the local lists any more, so _end may
+        # overwrite them with the retried results
+        torch.cuda.current_stream(rows.device).synchronize()
+        self.local_end(ticket)                   # retries this rank's unverified queries, if any
+        if int(unv_host.item()):                 # same value on every rank: collective decision
+            res = self._exchange_cuda(rows, score, d, n, k)[0]
+        return res
 
     def search(self, queries: torch.Tensor, k: int):
+        if self.world > 1 and queries.is_cuda and self.local_begin is not None:
+            return self._search_overlapped(queries, k)
         rows, score, d, n = self.local_search(queries, k)
         if self.world == 1:  # nothing to exchange: the local list is already the answer
             return rows.to(torch.int64) + self.row_offset, score, d, n

@@ -135,6 +135,20 @@ cx_status cx_search_batch_device(cx_index* h, const float* d_queries, uint64_t B
                                  const cx_filter* filter, uint32_t* d_out_rows, float* d_out_score,
                                  float* d_out_distance, uint8_t* d_out_ids, uint32_t* d_out_n, void* stream);
 
+/* Two-step form of cx_search_batch_device for callers that have more device work to enqueue behind
+ * the search (the sharded exchange: pack -> all_gather -> merge).  _begin enqueues the scan and
+ * returns without waiting; `stream` is ordered after the results, which are final unless _end says
+ * otherwise.  _end waits, re-runs the queries whose fast-pass result could not be verified (rare) on
+ * the tighter paths, and reports how many there were in *n_redone: if non-zero the output buffers
+ * changed after `stream` may have consumed them and the caller must redo its dependent work.
+ * *ticket may come back NULL (the call already ran to completion); _end then does nothing.  Every
+ * _begin must be matched by one _end on the same thread before the next mutation of the index. */
+cx_status cx_search_batch_device_begin(cx_index* h, const float* d_queries, uint64_t B, uint64_t k,
+                                       const cx_filter* filter, uint32_t* d_out_rows, float* d_out_score,
+                                       float* d_out_distance, uint8_t* d_out_ids, uint32_t* d_out_n, void* stream,
+                                       void** ticket);
+cx_status cx_search_batch_device_end(cx_index* h, void* ticket, uint64_t* n_redone);
+
 /* The scan step of AutoLinker::run_cycle (linker/auto_linker.rs:215-264) for a batch of B new
  * nodes: search(embedding, k) (k = 100 in the reference, :221), skip the node itself
  * (:235-237, found through new_ids; NULL = none of them is in the index), keep
@@ -155,17 +169,22 @@ cx_status cx_autolink_batch_device(cx_index* h, const float* d_embeddings, uint6
                                    uint8_t* d_out_ids, uint32_t* d_out_n, void* stream);
 
 /* Row-sharded search (one process per GPU): the exchange step around the
- * caller's all-gather.  pack: a rank's device-resident local top-k -> payload
- * [B][k][2] u64 (score-order key | distance bits, global row = row_offset + local row).
- * merge: the gathered payloads [world][B][k][2] -> global top-k per query in the
- * single-index order (score desc, NaN last, global row asc).  No reference counterpart:
- * the reference is single-process (ARCHITECTURE.md:38). */
+ * caller's all-gather.  pack: a rank's device-resident local top-k -> payload of B*k*2 + 2 u64:
+ * [B][k][2] slots (score-order key | distance bits, global row = row_offset + local row) and a
+ * two-word trailer whose first word counts this rank's still unverified queries (d_ok = the
+ * verification flags of a search in flight, cx_search_ticket_ok; NULL = all verified).
+ * merge: the gathered payloads [world][B*k*2 + 2] -> global top-k per query in the single-index
+ * order (score desc, NaN last, global row asc); *d_out_unverified (optional) = unverified queries
+ * over all ranks: non-zero means some rank will change its list and the exchange must be repeated.
+ * No reference counterpart: the reference is single-process (ARCHITECTURE.md:38). */
 cx_status cx_pack_topk_device(const uint32_t* d_rows, const float* d_score, const float* d_distance,
-                              const uint32_t* d_n, uint64_t B, uint64_t k, uint64_t row_offset,
-                              uint64_t* d_payload, void* stream);
+                              const uint32_t* d_n, const uint32_t* d_ok, uint64_t B, uint64_t k,
+                              uint64_t row_offset, uint64_t* d_payload, void* stream);
 cx_status cx_merge_topk_device(const uint64_t* d_gathered, uint32_t world, uint64_t B, uint64_t k,
                                int64_t* d_out_rows, float* d_out_score, float* d_out_distance,
-                               uint32_t* d_out_n, void* stream);
+                               uint32_t* d_out_n, uint64_t* d_out_unverified, void* stream);
+/* device pointer to the verification flags [B] of a search in flight (NULL ticket -> NULL) */
+cx_status cx_search_ticket_ok(void* ticket, const uint32_t** d_ok);
 
 /* VectorIndex::save / load, index.rs:437-472: bincode 1.3 layout of
  * (HashMap<Uuid,Vec<f32>>, HashMap<Uuid,NodeMetadata>, usize). */

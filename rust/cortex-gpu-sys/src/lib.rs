@@ -70,11 +70,21 @@ extern "C" {
                                   filter: *const cx_filter, d_out_rows: *mut u32, d_out_score: *mut f32,
                                   d_out_distance: *mut f32, d_out_ids: *mut u8, d_out_n: *mut u32,
                                   stream: *mut c_void) -> c_int;
+    pub fn cx_search_batch_device_begin(h: *mut cx_index, d_queries: *const f32, b: u64, k: u64,
+                                        filter: *const cx_filter, d_out_rows: *mut u32, d_out_score: *mut f32,
+                                        d_out_distance: *mut f32, d_out_ids: *mut u8, d_out_n: *mut u32,
+                                        stream: *mut c_void, ticket: *mut *mut c_void) -> c_int;
+    pub fn cx_search_batch_device_end(h: *mut cx_index, ticket: *mut c_void, n_redone: *mut u64) -> c_int;
+    pub fn cx_search_ticket_ok(ticket: *mut c_void, d_ok: *mut *const u32) -> c_int;
     pub fn cx_pack_topk_device(d_rows: *const u32, d_score: *const f32, d_distance: *const f32, d_n: *const u32,
-                               b: u64, k: u64, row_offset: u64, d_payload: *mut u64, stream: *mut c_void) -> c_int;
+                               d_ok: *const u32, b: u64, k: u64, row_offset: u64, d_payload: *mut u64,
+                               stream: *mut c_void) -> c_int;
     pub fn cx_merge_topk_device(d_gathered: *const u64, world: u32, b: u64, k: u64, d_out_rows: *mut i64,
                                 d_out_score: *mut f32, d_out_distance: *mut f32, d_out_n: *mut u32,
-                                stream: *mut c_void) -> c_int;
+                                d_out_unverified: *mut u64, stream: *mut c_void) -> c_int;
+    pub fn cx_debug_tensor_plan(n_queries: u64, n_rows: u64, sm_count: c_int, sample_tiles: u32, growth: u32,
+                                groups: *mut u32, groups_n: *mut u32, phases: *mut u32, phases_n: *mut u32,
+                                hits_per_kp: *mut f64) -> c_int;
     pub fn cx_save(h: *const cx_index, path: *const c_char) -> c_int;
     pub fn cx_load(path: *const c_char, device: c_int, out: *mut *mut cx_index) -> c_int;
     pub fn cx_row_id(h: *const cx_index, row: u32, out_id: *mut u8) -> c_int;

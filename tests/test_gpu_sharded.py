@@ -14,26 +14,30 @@ from oracle.binding import OracleIndex
 pytestmark = pytest.mark.gpu
 
 
-def cuda_pack(L, rows, score, dist, n, offset):
+def cuda_pack(L, rows, score, dist, n, offset, ok=None):
     B, k = rows.shape
-    payload = torch.empty((B, k, 2), dtype=torch.int64, device=rows.device)
-    st = L.cx_pack_topk_device(rows.data_ptr(), score.data_ptr(), dist.data_ptr(), n.data_ptr(), B, k, offset,
+    payload = torch.empty((B * k * 2 + 2,), dtype=torch.int64, device=rows.device)  # slots + trailer
+    st = L.cx_pack_topk_device(rows.data_ptr(), score.data_ptr(), dist.data_ptr(), n.data_ptr(),
+                               ok.data_ptr() if ok is not None else None, B, k, offset,
                                payload.data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream))
     assert st == 0, L.cx_last_error()
     return payload
 
 
-def cuda_merge(L, gathered, k):
-    W, B = gathered.shape[0], gathered.shape[1]
+def cuda_merge(L, gathered, k, B, want_unverified=False):
+    W = gathered.shape[0]
     dev = gathered.device
+    unv = torch.full((1,), -1, dtype=torch.int64, device=dev)
     grow = torch.empty((B, k), dtype=torch.int64, device=dev)
     gs = torch.empty((B, k), dtype=torch.float32, device=dev)
     gd = torch.empty((B, k), dtype=torch.float32, device=dev)
     gn = torch.empty((B,), dtype=torch.int32, device=dev)
     st = L.cx_merge_topk_device(gathered.data_ptr(), W, B, k, grow.data_ptr(), gs.data_ptr(), gd.data_ptr(),
-                                gn.data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream))
+                                gn.data_ptr(), unv.data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream))
     assert st == 0, L.cx_last_error()
     torch.cuda.synchronize()
+    if want_unverified:
+        return grow, gs, gd, gn, int(unv.item())
     return grow, gs, gd, gn
 
 
@@ -51,7 +55,7 @@ def test_four_simulated_shards_match_single_index_oracle():
         g.insert_batch(ids[w * per:(w + 1) * per], corpus[w * per:(w + 1) * per])
         rows, sc, di, nn = g.search_batch_device(dq, k, stream=torch.cuda.current_stream().cuda_stream)
         payloads.append(cuda_pack(L, rows, sc, di, nn, w * per))
-    grow, gs, gd, gn = cuda_merge(L, torch.stack(payloads).contiguous(), k)
+    grow, gs, gd, gn = cuda_merge(L, torch.stack(payloads).contiguous(), k, b)
     o = OracleIndex(d, faithful_copy=False)
     o.insert_batch(ids, corpus)
     _, osc, odi, orow, on = o.search_batch(Q, k)
@@ -79,7 +83,7 @@ def test_cuda_merge_equals_torch_merge_with_ties_nan_and_short_lists():
         payloads.append(cuda_pack(L, r, s, dd, nn, w * 1000))
         keys.append(pack_keys(rows, score, n, w * 1000))
         dists.append(dist)
-    grow, gs, gd, gn = cuda_merge(L, torch.stack(payloads).contiguous(), k)
+    grow, gs, gd, gn = cuda_merge(L, torch.stack(payloads).contiguous(), k, B)
     trow, ts, td, tn = merge_gathered(torch.stack(keys), torch.stack(dists), k)
     assert torch.equal(gn.cpu(), tn)
     for b in range(B):
@@ -87,3 +91,41 @@ def test_cuda_merge_equals_torch_merge_with_ties_nan_and_short_lists():
         assert torch.equal(grow.cpu()[b, :m], trow[b, :m])
         x, y = gs.cpu()[b, :m], ts[b, :m]
         assert torch.all((x == y) | (torch.isnan(x) & torch.isnan(y)))
+
+
+def test_begin_end_and_the_unverified_trailer():
+    """cx_search_batch_device_begin/_end: the exchange is enqueued behind the scan without a host wait;
+    the pack trailer carries each rank's count of unverified queries so that all ranks learn from the
+    gathered payloads whether the exchange must be repeated.  A zero query cannot be verified by the
+    fast passes (its norm is degenerate) and forces that path."""
+    L = _capi.load()
+    n, d, b, k = 6000, 384, 40, 10
+    corpus = synth.make_corpus(n, d, seed=12)
+    Q = synth.make_queries(corpus, b, seed=13)
+    Q[7] = 0.0   # degenerate norm: never verified by a fast pass
+    Q[21] = 0.0
+    g = GpuVectorIndex(d)
+    g.insert_batch(synth.make_ids(n), corpus)
+    o = OracleIndex(d, faithful_copy=False)
+    o.insert_batch(synth.make_ids(n), corpus)
+    dq = torch.from_numpy(Q).cuda()
+    out, ticket = g.search_batch_device_begin(dq, k, stream=torch.cuda.current_stream().cuda_stream)
+    ok = g.ticket_ok(ticket, b)
+    p = cuda_pack(L, out[0], out[1], out[2], out[3], 0, ok)
+    _, _, _, _, unv = cuda_merge(L, p[None, :].contiguous(), k, b, want_unverified=True)
+    assert unv == 2
+    redone = g.search_batch_device_end(ticket)
+    assert redone == 2
+    # after _end the buffers hold the final answer
+    _, osc, odi, orow, on = o.search_batch(Q, k)
+    assert np.array_equal(out[3].cpu().numpy(), on.astype(np.int32))
+    assert np.array_equal(out[0].cpu().numpy().astype(np.int64), orow.astype(np.int64))
+    a = out[1].cpu().numpy()
+    assert np.all((a.view(np.uint32) == osc.view(np.uint32)) | (np.isnan(a) & np.isnan(osc)))
+    # nothing unverified: the trailer is zero and _end reports nothing to redo
+    Q2 = synth.make_queries(corpus, b, seed=14)
+    dq2 = torch.from_numpy(Q2).cuda()
+    out2, t2 = g.search_batch_device_begin(dq2, k, stream=torch.cuda.current_stream().cuda_stream)
+    p2 = cuda_pack(L, out2[0], out2[1], out2[2], out2[3], 0, g.ticket_ok(t2, b))
+    _, _, _, _, unv2 = cuda_merge(L, p2[None, :].contiguous(), k, b, want_unverified=True)
+    assert unv2 == 0 and g.search_batch_device_end(t2) == 0
