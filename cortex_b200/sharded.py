@@ -65,7 +65,7 @@ class ShardedSearch:
     def __init__(self, local_search: Callable, row_offset: int, group: Optional[dist.ProcessGroup] = None,
                  local_begin: Optional[Callable] = None, local_end: Optional[Callable] = None,
                  ticket_ok_ptr: Optional[Callable] = None):
-        """local_begin(d_queries, k) -> (out, ticket) / local_end(ticket) -> n_redone / ticket_ok_ptr(ticket) ->
+        """local_begin(d_queries, k, slot) -> (out, ticket) / local_end(ticket) -> n_redone / ticket_ok_ptr(ticket) ->
         device address: the two-step form of the local scan (GpuVectorIndex.search_batch_device_begin/_end).
         With them the exchange is enqueued behind the scan with no host wait in between."""
         self.local_search = local_search
@@ -75,7 +75,7 @@ class ShardedSearch:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self._bufs = {}
 
-    def _exchange_cuda(self, rows, score, d, n, k, ok_ptr=0):
+    def _exchange_cuda(self, rows, score, d, n, k, ok_ptr=0, slot=0):
         """GPU exchange: pack kernel -> one NCCL all_gather -> merge kernel (cx_merge.cu), all enqueued on
         the current stream.  Returns the merged lists and a device word = unverified queries over all ranks."""
         import ctypes as C
@@ -85,7 +85,7 @@ class ShardedSearch:
         B = rows.shape[0]
         dev = rows.device
         stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        key = (B, k, str(dev))
+        key = (B, k, str(dev), slot)
         buf = self._bufs.get(key)
         if buf is None:
             words = B * k * 2 + 2  # slots + trailer (cortex_gpu.h)
@@ -118,7 +118,7 @@ class ShardedSearch:
         """scan -> pack -> all_gather -> merge enqueued back to back; ONE host wait at the end.  The
         gathered trailers tell every rank whether any rank still has unverified queries; only then (rare)
         do all ranks repeat the exchange after the local retries."""
-        out, ticket = self.local_begin(queries, k)
+        out, ticket = self.local_begin(queries, k, 0)
         rows, score, d, n = out
         res, unv, unv_host = self._exchange_cuda(rows, score, d, n, k, self.ticket_ok_ptr(ticket))
         unv_host.copy_(unv, non_blocking=True)
@@ -128,6 +128,35 @@ class ShardedSearch:
         self.local_end(ticket)                   # retries this rank's unverified queries, if any
         if int(unv_host.item()):                 # same value on every rank: collective decision
             res = self._exchange_cuda(rows, score, d, n, k)[0]
+        return res
+
+    # ---- pipelined form: keep the GPU fed across calls ------------------------------------------------
+    def search_begin(self, queries: torch.Tensor, k: int, slot: int = 0):
+        """Enqueue one sharded search (scan + exchange) and return without waiting.  `slot` selects the set
+        of exchange buffers (use alternating slots to keep two searches in flight); local_begin(q, k, slot)
+        must likewise write into per-slot output buffers.  Finish with search_end(pending)."""
+        assert queries.is_cuda and self.local_begin is not None
+        out, ticket = self.local_begin(queries, k, slot)
+        if self.world == 1:
+            return (out, ticket, None, None, None, k, slot)
+        rows, score, d, n = out
+        res, unv, unv_host = self._exchange_cuda(rows, score, d, n, k, self.ticket_ok_ptr(ticket), slot)
+        unv_host.copy_(unv, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(rows.device))
+        return (out, ticket, res, unv_host, ev, k, slot)
+
+    def search_end(self, pending):
+        out, ticket, res, unv_host, ev, k, slot = pending
+        if self.world == 1:
+            self.local_end(ticket)               # waits for this scan only; retries what was not verified
+            rows, score, d, n = out
+            return rows.to(torch.int64) + self.row_offset, score, d, n
+        ev.synchronize()                         # this search's exchange is done; later ones keep running
+        self.local_end(ticket)
+        if int(unv_host.item()):                 # same value on every rank: collective decision
+            rows, score, d, n = out
+            res = self._exchange_cuda(rows, score, d, n, k, 0, slot)[0]
         return res
 
     def search(self, queries: torch.Tensor, k: int):

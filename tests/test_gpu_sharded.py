@@ -129,3 +129,46 @@ def test_begin_end_and_the_unverified_trailer():
     p2 = cuda_pack(L, out2[0], out2[1], out2[2], out2[3], 0, g.ticket_ok(t2, b))
     _, _, _, _, unv2 = cuda_merge(L, p2[None, :].contiguous(), k, b, want_unverified=True)
     assert unv2 == 0 and g.search_batch_device_end(t2) == 0
+
+
+def test_pipelined_search_keeps_two_batches_in_flight():
+    """ShardedSearch.search_begin / search_end (world 1): the next batch is enqueued before the host waits
+    for the previous one; every batch still comes back exact."""
+    from cortex_b200.sharded import ShardedSearch
+
+    n, d, b, k = 9000, 384, 64, 10
+    corpus = synth.make_corpus(n, d, seed=31)
+    g = GpuVectorIndex(d)
+    g.insert_batch(synth.make_ids(n), corpus)
+    o = OracleIndex(d, faithful_copy=False)
+    o.insert_batch(synth.make_ids(n), corpus)
+    stream = torch.cuda.current_stream().cuda_stream
+    outs = {}
+
+    def local_begin(q, kk, slot=0):
+        out, ticket = g.search_batch_device_begin(q, kk, stream=stream, out=outs.get(slot))
+        outs[slot] = out
+        return out, ticket
+
+    sh = ShardedSearch(lambda q, kk: g.search_batch_device(q, kk, stream=stream), row_offset=0,
+                       local_begin=local_begin, local_end=g.search_batch_device_end, ticket_ok_ptr=g.ticket_ok_ptr)
+    batches = [synth.make_queries(corpus, b, seed=40 + i) for i in range(5)]
+    batches[2][3] = 0.0  # one query that only the exact path can answer
+    dqs = [torch.from_numpy(q).cuda() for q in batches]
+    pend, got = [], []
+    for i, dq in enumerate(dqs):
+        pend.append((i, sh.search_begin(dq, k, slot=i % 2)))
+        if len(pend) == 2:
+            j, p = pend.pop(0)
+            rows, sc, di, nn = sh.search_end(p)
+            got.append((j, rows.cpu().numpy().copy(), sc.cpu().numpy().copy(), nn.cpu().numpy().copy()))
+    while pend:
+        j, p = pend.pop(0)
+        rows, sc, di, nn = sh.search_end(p)
+        got.append((j, rows.cpu().numpy().copy(), sc.cpu().numpy().copy(), nn.cpu().numpy().copy()))
+    assert [j for j, *_ in got] == list(range(5))
+    for j, rows, sc, nn in got:
+        _, osc, _, orow, on = o.search_batch(batches[j], k)
+        assert np.array_equal(nn, on.astype(np.int32))
+        assert np.array_equal(rows, orow.astype(np.int64))
+        assert np.all((sc.view(np.uint32) == osc.view(np.uint32)) | (np.isnan(sc) & np.isnan(osc)))
