@@ -31,6 +31,14 @@ def test_every_header_symbol_is_exported_and_bound(lib):
     assert syms == set(_capi.SYMBOLS), "ctypes table and header disagree"
 
 
+def test_rust_ffi_crate_declares_exactly_the_header_symbols():
+    """rust/cortex-gpu-sys cannot be compiled here (no cargo): at least keep its extern block in step with
+    the header, symbol for symbol."""
+    src = open(os.path.join(ROOT, "rust", "cortex-gpu-sys", "src", "lib.rs")).read()
+    rust = set(re.findall(r"pub fn (cx_[a-z_0-9]+)\s*\(", src))
+    assert rust == header_symbols(), (sorted(header_symbols() - rust), sorted(rust - header_symbols()))
+
+
 def test_version_and_error_strings(lib):
     assert b"sm_100a" in lib.cx_version()
     assert isinstance(lib.cx_last_error(), bytes)
