@@ -195,10 +195,15 @@ cx_status cx_load(const char* path, int device, cx_index** out);
 cx_status cx_row_id(const cx_index* h, uint32_t row, uint8_t out_id[16]);
 
 cx_status cx_get_stats(const cx_index* h, cx_stats* out);
-/* Tuning / test hooks: "force_path" 0 auto, 1 stream (K1), 2 tensor (K2), 3 exact;
- * "stream_max_batch" largest query group K1 serves before K2 takes over;
- * "profile" 1 = bracket the scan-pass kernels with CUDA events on their stream;
- * "blocking_sync" 1 = search calls sleep on an event instead of spinning while the GPU works. */
+/* Tuning / test hooks.  Per index: "force_path" 0 auto, 1 stream (K1), 2 tensor (K2), 3 exact;
+ * "tensor_min_batch" smallest query batch the tensor pass serves (default 5); "tensor_phase_growth"
+ * growth factor of the scan phases (0/1 = one phase, default auto); "shadow" 0 = keep no bf16
+ * copy (disables the tensor pass; before the first insert); "profile" 1 = bracket the scan-pass
+ * kernels with CUDA events on their stream (cx_get_stats: pass_kernel_ns); "blocking_sync" 1 = search
+ * calls sleep on an event instead of spinning while the GPU works.  Process-wide measurement hooks of
+ * the tensor pass: "tensor_pair" 1 = CTA-pair (cta_group::2) form, "tensor_epi_warps" 8 | 16,
+ * "tensor_debug" (results become wrong: 1 no epilogue work, 2 no hit handling, 4 no E traffic,
+ * -1 print the effective SM clock of the last launch). */
 cx_status cx_set_option(cx_index* h, const char* key, int64_t value);
 
 /* Test hook, needs no device: the tensor pass's launch plan -- queries per launch
