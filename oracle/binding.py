@@ -20,9 +20,10 @@ _LIB_PATH = os.path.join(_HERE, "libcortex_oracle.so")
 
 def build(force: bool = False) -> str:
     """Compile the oracle with the committed Makefile (gcc, -ffp-contract=off)."""
-    srcs = [os.path.join(_HERE, f) for f in ("cortex_oracle.c", "hnsw_oracle.c", "Makefile")]
-    stale = not os.path.exists(_LIB_PATH) or any(
-        os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs
+    srcs = [os.path.join(_HERE, f) for f in ("cortex_oracle.c", "hnsw_oracle.c", "cpu_fast.c", "Makefile")]
+    fast = os.path.join(_HERE, "libcortex_cpufast_v3.so")
+    stale = not os.path.exists(_LIB_PATH) or not os.path.exists(fast) or any(
+        os.path.getmtime(s) > min(os.path.getmtime(_LIB_PATH), os.path.getmtime(fast)) for s in srcs
     )
     if force or stale:
         subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
@@ -276,3 +277,42 @@ class OracleHnsw:
 
     def distance_evals(self) -> int:
         return int(self._L.cxo_hnsw_distance_evals(self._h))
+
+
+class CpuFastScan:
+    """oracle/cpu_fast.c: an OPTIMISED CPU scan (hoisted norms, one corpus pass per 16 queries, vectorised
+    reassociated fp32, k-heaps, OpenMP) -- a courtesy baseline, NOT the reference and not a checker."""
+
+    def __init__(self, corpus: np.ndarray):
+        build()
+        flags = set()
+        try:
+            for line in open("/proc/cpuinfo"):
+                if line.startswith("flags"):
+                    flags = set(line.split(":", 1)[1].split())
+                    break
+        except OSError:
+            pass
+        if {"avx512f", "avx512vl", "avx512bw", "avx512dq", "avx512cd"} <= flags:
+            name = "libcortex_cpufast_v4.so"
+        elif {"avx2", "fma", "bmi2"} <= flags:
+            name = "libcortex_cpufast_v3.so"
+        else:
+            raise RuntimeError("host CPU has neither AVX-512 nor AVX2+FMA: no optimised CPU baseline")
+        self.isa = name[len("libcortex_cpufast_"):-3]
+        L = C.CDLL(os.path.join(_HERE, name))
+        L.cxf_row_rnorms.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p]
+        L.cxf_search_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t,
+                                       C.c_size_t, C.c_void_p, C.c_void_p, C.c_int]
+        self._L = L
+        self._E = np.ascontiguousarray(corpus, dtype=np.float32)
+        self._rn = np.zeros(self._E.shape[0], np.float32)
+        L.cxf_row_rnorms(self._E.ctypes.data, self._E.shape[0], self._E.shape[1], self._rn.ctypes.data)
+
+    def search_batch(self, queries: np.ndarray, k: int, n_threads: int = 0):
+        Q = np.ascontiguousarray(queries, dtype=np.float32)
+        rows = np.zeros((Q.shape[0], k), np.uint32)
+        score = np.zeros((Q.shape[0], k), np.float32)
+        self._L.cxf_search_batch(self._E.ctypes.data, self._rn.ctypes.data, self._E.shape[0], self._E.shape[1],
+                                 Q.ctypes.data, Q.shape[0], k, rows.ctypes.data, score.ctypes.data, n_threads)
+        return rows, score

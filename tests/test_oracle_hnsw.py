@@ -35,3 +35,20 @@ def test_hnsw_recall_against_exact_scan():
         hit += len(set(int(r) for r in ids) & set(int(r) for r in exact.rows))
     recall = hit / (b * k)
     assert recall >= 0.9, recall
+
+
+def test_cpu_fast_courtesy_scan_agrees_with_the_oracle():
+    """oracle/cpu_fast.c (the optimised, non-reference CPU baseline) returns the exact scan's ids on data
+    without near-ties and scores within fp32 rounding of the reference's."""
+    from oracle.binding import CpuFastScan
+
+    n, dim, b, k = 6000, 96, 33, 10
+    corpus = synth.make_corpus(n, dim, dup_frac=0.0, seed=17)
+    Q = synth.make_queries(corpus, b, seed=18)
+    o = OracleIndex(dim, faithful_copy=False)
+    o.insert_batch(synth.make_ids(n), corpus)
+    _, osc, _, orow, on = o.search_batch(Q, k)
+    rows, score = CpuFastScan(corpus).search_batch(Q, k)
+    same = sum(len(set(map(int, rows[i])) & set(map(int, orow[i]))) for i in range(b))
+    assert same >= 0.99 * b * k
+    assert np.max(np.abs(score - osc)) < 2e-6
