@@ -40,6 +40,11 @@ class CxStats(C.Structure):
         ("d2h_bytes", C.c_uint64),
         ("pass_kernel_ns", C.c_uint64),
         ("pass_kernel_launches", C.c_uint64),
+        ("graph_launches", C.c_uint64),
+        ("grow_events", C.c_uint64),
+        ("irregular_rows", C.c_uint64),
+        ("capacity_rows", C.c_uint64),
+        ("in_place_growth", C.c_uint64),
     ]
 
 
@@ -47,6 +52,8 @@ class CxStats(C.Structure):
 # symbol the header declares is exported.
 SYMBOLS = {
     "cx_index_create": (C.c_int, [C.c_uint32, C.c_int, C.POINTER(C.c_void_p)]),
+    "cx_index_create_sharded": (C.c_int, [C.c_uint32, C.POINTER(C.c_int), C.c_uint32, C.POINTER(C.c_void_p)]),
+    "cx_shard_count": (C.c_uint32, [C.c_void_p]),
     "cx_index_destroy": (None, [C.c_void_p]),
     "cx_insert": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]),
     "cx_insert_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32]),
@@ -87,6 +94,7 @@ SYMBOLS = {
     "cx_search_ticket_ok": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "cx_save": (C.c_int, [C.c_void_p, C.c_char_p]),
     "cx_load": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "cx_load_sharded": (C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.c_uint32, C.POINTER(C.c_void_p)]),
     "cx_row_id": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p]),
     "cx_get_stats": (C.c_int, [C.c_void_p, C.POINTER(CxStats)]),
     "cx_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),

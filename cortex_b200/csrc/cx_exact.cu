@@ -48,17 +48,26 @@ __global__ void row_norm_kernel(float* __restrict__ E, float* __restrict__ norm,
   rnorm[r0 + i] = irregular ? __int_as_float(0x7fc00000) : __frcp_rn(nb);
 }
 
-__global__ void count_nan_kernel(const float* __restrict__ x, uint32_t n, uint32_t* __restrict__ out) {
+__global__ void count_nan_kernel(const float* __restrict__ x, const uint32_t* __restrict__ meta, uint32_t r0,
+                                 uint32_t n, int sign, uint32_t* __restrict__ out) {
   uint32_t c = 0;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) c += x[i] != x[i];
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    c += (x[r0 + i] != x[r0 + i]) && !(meta[r0 + i] & META_DEAD);
   c = __reduce_add_sync(0xffffffffu, c);
-  if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+  if ((threadIdx.x & 31) == 0 && c) {
+    if (sign > 0) atomicAdd(out, c);
+    else atomicSub(out, c);
+  }
 }
 
-// rows with a NaN reciprocal norm (irregular rows, see row_norm_kernel) -> *out (zeroed here)
-void launch_count_irregular(const float* rnorm, uint32_t n, uint32_t* out, cudaStream_t s) {
-  cudaMemsetAsync(out, 0, 4, s);
-  if (n) count_nan_kernel<<<(n + 1023) / 1024 < 592 ? (n + 1023) / 1024 : 592, 256, 0, s>>>(rnorm, n, out);
+// live rows of [r0, r0+n) with a NaN reciprocal norm (irregular rows, see row_norm_kernel) are added to
+// (sign > 0) or taken off (sign < 0) the index's running count: the count follows inserts, overwrites
+// and removes incrementally instead of being recomputed over the whole store
+void launch_count_irregular(const float* rnorm, const uint32_t* meta, uint32_t r0, uint32_t n, int sign,
+                            uint32_t* counter, cudaStream_t s) {
+  if (!n) return;
+  const uint32_t blocks = (n + 1023) / 1024 < 592 ? (n + 1023) / 1024 : 592;
+  count_nan_kernel<<<blocks, n < 256 ? 32 : 256, 0, s>>>(rnorm, meta, r0, n, sign, counter);
 }
 
 // bf16 shadow for the tensor pass: rows are stored NORMALISED (x / |x|) so that the
@@ -123,14 +132,17 @@ __device__ __forceinline__ float ref_dot(const float* __restrict__ q, const floa
 }
 
 __global__ void exact_keys_kernel_p(StoreView st, const float* __restrict__ q, const float* __restrict__ qnorm_p,
-                                    uint32_t qlen, DevFilter flt, uint64_t* __restrict__ keys) {
+                                    uint32_t qlen, DevFilter flt, uint64_t* __restrict__ keys, uint32_t self_row,
+                                    uint32_t upper_only, const uint64_t* __restrict__ row_seq, uint64_t q_seq) {
   extern __shared__ float q_s[];
   for (uint32_t d = threadIdx.x; d < qlen; d += blockDim.x) q_s[d] = q[d];
   __syncthreads();
   uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= st.n_rows) return;
   uint64_t key = 0;
-  if (row_passes(flt, st.meta, st.agent, row)) {
+  // pair rules of the dedup scanner (linker/dedup.rs:91-105): never the node itself, each unordered pair once
+  const bool wanted = row_seq ? row_seq[row] > q_seq : (row != self_row && !(upper_only && row < self_row));
+  if (wanted && row_passes(flt, st.meta, st.agent, row)) {
     uint32_t n = qlen < st.dim ? qlen : st.dim;
     float dot = ref_dot(q_s, st.E + (size_t)row * st.ld, n);
     float dist = ref_distance_from(dot, __ldg(qnorm_p), __ldg(st.norm + row));
@@ -140,11 +152,12 @@ __global__ void exact_keys_kernel_p(StoreView st, const float* __restrict__ q, c
 }
 
 void launch_exact_keys(const StoreView& st, const QueryView& qv, uint32_t q, const DevFilter& flt,
-                       uint64_t* keys, cudaStream_t s) {
+                       uint64_t* keys, cudaStream_t s, uint32_t self_row, bool upper_only, const uint64_t* row_seq,
+                       uint64_t q_seq) {
   if (!st.n_rows) return;
   uint32_t threads = 128;
   exact_keys_kernel_p<<<(st.n_rows + threads - 1) / threads, threads, qv.qlen * sizeof(float), s>>>(
-      st, qv.Q + (size_t)q * qv.ldq, qv.qnorm + q, qv.qlen, flt, keys);
+      st, qv.Q + (size_t)q * qv.ldq, qv.qnorm + q, qv.qlen, flt, keys, self_row, upper_only ? 1u : 0u, row_seq, q_seq);
 }
 
 size_t exact_sort_tmp_bytes(uint32_t n) {
@@ -205,9 +218,9 @@ void launch_exact_emit(const StoreView& st, const QueryView& qv, uint32_t q, con
 }
 
 // ---------------------------------------------------------------------------------
-__global__ void gather_rows_kernel(StoreView src, float* E, float* norm, float* rnorm, uint32_t* meta,
-                                   uint32_t* agent, uint8_t* ids, __nv_bfloat16* E16,
-                                   const uint32_t* __restrict__ live, uint32_t n_live) {
+__global__ void gather_rows_kernel(StoreView src, const uint64_t* __restrict__ src_seq, float* E, float* norm,
+                                   float* rnorm, uint32_t* meta, uint32_t* agent, uint8_t* ids, __nv_bfloat16* E16,
+                                   uint64_t* seq, const uint32_t* __restrict__ live, uint32_t n_live) {
   // one warp per destination row
   uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (w >= n_live) return;
@@ -225,17 +238,18 @@ __global__ void gather_rows_kernel(StoreView src, float* E, float* norm, float* 
     rnorm[w] = src.rnorm[r];
     meta[w] = src.meta[r];
     agent[w] = src.agent[r];
+    if (seq && src_seq) seq[w] = src_seq[r];
     *reinterpret_cast<uint4*>(ids + (size_t)w * 16) = *reinterpret_cast<const uint4*>(src.ids + (size_t)r * 16);
   }
 }
 
-void launch_gather_rows(const StoreView& src, float* E, float* norm, float* rnorm, uint32_t* meta,
-                        uint32_t* agent, uint8_t* ids, void* E16, const uint32_t* live, uint32_t n_live,
-                        cudaStream_t s) {
+void launch_gather_rows(const StoreView& src, const uint64_t* src_seq, float* E, float* norm, float* rnorm,
+                        uint32_t* meta, uint32_t* agent, uint8_t* ids, void* E16, uint64_t* seq,
+                        const uint32_t* live, uint32_t n_live, cudaStream_t s) {
   if (!n_live) return;
   uint32_t threads = 256, warps_per_block = threads / 32;
   gather_rows_kernel<<<(n_live + warps_per_block - 1) / warps_per_block, threads, 0, s>>>(
-      src, E, norm, rnorm, meta, agent, ids, (__nv_bfloat16*)E16, live, n_live);
+      src, src_seq, E, norm, rnorm, meta, agent, ids, (__nv_bfloat16*)E16, seq, live, n_live);
 }
 
 }  // namespace cx

@@ -66,6 +66,27 @@ struct Interner {
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// A device array that grows in place.  With the driver's virtual-memory API (cuMemAddressReserve /
+// cuMemCreate / cuMemMap) a range of addresses large enough for the biggest shard the device can hold
+// is reserved once and physical chunks are mapped behind it as rows arrive: the base pointer never
+// changes, nothing is copied and growth needs no second copy of the store.  Where that API is not
+// available the array falls back to allocate-copy-free (the pointer then changes on growth).
+struct VmArray {
+  char* p = nullptr;
+  size_t reserved = 0;   // bytes of address space (vmm only)
+  size_t mapped = 0;     // bytes usable
+  bool vmm = false;
+  int device = 0;
+  struct Chunk { unsigned long long handle; size_t off, size; };
+  std::vector<Chunk> chunks;
+  cx_status init(int device, size_t reserve_bytes);
+  // make at least `bytes` usable; the fallback path preserves the first `used` bytes (copied on s, synchronised)
+  cx_status ensure(size_t bytes, size_t used, cudaStream_t s);
+  void shrink(size_t bytes);  // vmm only: give back whole chunks that lie entirely above `bytes`
+  void destroy();
+};
+bool vmm_available();
+
 // Per-call scratch: one stream + device/pinned buffers, recycled through a pool so
 // concurrent searches (read-guard holders in the reference) never share state.
 struct Workspace {
@@ -75,6 +96,21 @@ struct Workspace {
   size_t d_bytes = 0;
   void* hp = nullptr;  // pinned
   size_t h_bytes = 0;
+  // exact-path buffers (two key arrays of n_rows + radix-sort scratch): allocated the first time a
+  // query of this workspace actually takes the exact path, not per search
+  void* dx = nullptr;
+  size_t dx_bytes = 0;
+  // second device block for callers that stage their own inputs / outputs around a device search
+  void* aux = nullptr;
+  size_t aux_bytes = 0;
+  void* aux_h = nullptr;  // pinned
+  size_t aux_h_bytes = 0;
+  // replayable launch sequence of the last device-resident search shape (cx_search.cu)
+  cudaGraphExec_t graph = nullptr;
+  uint32_t graph_nlaunch = 0;   // kernels one replay launches
+  bool graph_broken = false;    // recording failed once on this workspace: plain launches from then on
+  uint64_t graph_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  uint64_t last_key[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // candidate-list state that must be zero between passes (cnt u32 + gtau u64 per query)
   uint32_t* d_cnt = nullptr;
   uint64_t* d_gtau = nullptr;
@@ -82,18 +118,25 @@ struct Workspace {
   bool state_dirty = false;
 
   cudaError_t ensure(size_t db, size_t hb);
+  cudaError_t ensure_exact(size_t bytes);
+  cudaError_t ensure_aux(size_t db, size_t hb);
   cudaError_t ensure_state(size_t nq);
+  void drop_graph();
   cudaError_t wait(bool blocking);
   ~Workspace();
 };
 
 }  // namespace cx
 
+namespace cx { struct ShardSet; }
+
 struct cx_index {
   int device = 0;
   int sm_count = 148;
   uint32_t dim = 0, ld = 0, ld16 = 0;
   uint64_t n_rows = 0, n_live = 0, cap = 0;
+  // the store: growable device arrays and the raw pointers into them
+  cx::VmArray aE, aNorm, aRnorm, aMeta, aAgent, aIds, aE16, aSeq;
   float* dE = nullptr;
   float* dNorm = nullptr;
   float* dRnorm = nullptr;
@@ -101,15 +144,25 @@ struct cx_index {
   uint32_t* dAgent = nullptr;
   uint8_t* dIds = nullptr;
   void* dE16 = nullptr;
-  uint32_t* d_irr = nullptr;       // device counter + pinned host mirror: rows whose norm under/overflowed
+  uint64_t* dSeq = nullptr;        // shards of a multi-device index only: global insertion number of every row
+  bool with_seq = false;
+  uint64_t max_rows = 0;           // rows the reserved address ranges can hold
+  size_t total_mem = 0;
+  bool store_ready = false;        // address ranges reserved (first insert / reserve)
+  void* stage_h = nullptr;         // pinned staging for the side arrays of an insert
+  size_t stage_bytes = 0;
+  uint32_t* d_irr = nullptr;       // device counter + pinned host mirror: LIVE rows whose norm under/overflowed
   uint32_t* h_irr = nullptr;       //   fp32 (cx_exact.cu); any such row sends every search to the exact path
   bool want_shadow = true;
   std::vector<uint8_t> h_ids;
   std::vector<uint32_t> h_meta, h_agent;
+  std::vector<uint64_t> h_seq;
   std::unordered_map<cx::Id128, uint32_t, cx::Id128Hash> id2row;
   std::unordered_map<cx::Id128, std::pair<uint32_t, uint32_t>, cx::Id128Hash> orphan_meta;
   cx::Interner kinds, agents;
   cudaStream_t mut_stream = nullptr;
+  cudaEvent_t ev_mut = nullptr;          // recorded on mut_stream after every mutation
+  std::atomic<bool> mut_dirty{false};    // a mutation was enqueued that no search has waited for yet
   std::mutex ws_mu;
   std::vector<cx::Workspace*> ws_free;
   // options
@@ -119,9 +172,15 @@ struct cx_index {
                                               // (0/1 = one phase; 0xFFFFFFFF = auto: one phase for B <= 256 and k <= 16, else 8 for k <= 16, 4 above)
   int profile = 0;
   bool blocking_sync = false;      // search calls sleep on an event instead of spinning while the GPU works
+  bool use_graphs = true;          // replay repeated device-resident search shapes as one CUDA graph launch
+  cx::TensorTuning tensor_tune;    // CTA form / epilogue warps of the tensor pass (per index, read-only while searching)
   // stats
   std::atomic<uint64_t> launches{0}, q_stream{0}, q_tensor{0}, q_exact{0}, fallbacks{0}, h2d{0}, d2h{0};
-  std::atomic<uint64_t> pass_ns{0}, pass_launches{0};
+  std::atomic<uint64_t> pass_ns{0}, pass_launches{0}, graph_launches{0}, grow_events{0};
+
+  // non-null: this handle is a row-sharded index over several devices (cx_sharded.cu); none of the
+  // single-device fields above is used and every entry point forwards to the shard set
+  cx::ShardSet* shards = nullptr;
 
   uint32_t n_irregular() const { return h_irr ? *h_irr : 0u; }
 
@@ -163,5 +222,66 @@ struct WsLease {
 };
 
 enum { PATH_AUTO = 0, PATH_STREAM = 1, PATH_TENSOR = 2, PATH_EXACT = 3 };
+
+// wait (on the host) for mutations that were enqueued but not yet waited for: after it the store, the
+// irregular-row count and every host mirror are current
+cx_status settle(cx_index* h);
+
+// The dedup scanner's pair rules (linker/dedup.rs:91-105) for a threshold scan whose queries are rows of an index
+struct PairRules {
+  const uint32_t* d_self_rows = nullptr;  // single index: device [B], the row each query is; it is skipped
+  uint32_t self_base = 0;                 // ... and equals self_base + b for query b
+  bool upper_only = false;                // ... and only rows above it are kept (each unordered pair once)
+  uint32_t first_row = 0;                 // rows below this one cannot qualify (the scan starts at its tile)
+  const uint64_t* d_q_seq = nullptr;      // multi-device: global insertion number of each query (device [B]); a row
+  const uint64_t* h_q_seq = nullptr;      //   qualifies when its own number is larger.  Host copy of the same.
+};
+
+// single-device internals shared with the multi-device index (cx_sharded.cu)
+cx_status index_threshold_device(cx_index* h, const float* d_queries, uint32_t qlen, uint32_t q_stride, uint64_t B,
+                                 float threshold, const cx_filter* filter, uint64_t cap, uint32_t* d_rows,
+                                 float* d_score, float* d_dist, uint8_t* d_ids, uint32_t* d_n, uint32_t* d_total,
+                                 uint64_t* h_total, const PairRules* pair);
+// cx_search_batch_device(_begin) for queries of any length ([B][qlen], the reference never checks it)
+cx_status index_search_device(cx_index* h, const float* d_queries, uint32_t qlen, uint64_t B, uint64_t k,
+                              const cx_filter* filter, uint32_t* d_out_rows, float* d_out_score, float* d_out_distance,
+                              uint8_t* d_out_ids, uint32_t* d_out_n, void* stream, void** ticket);
+cx_status index_create(uint32_t dimension, int device, bool with_seq, cx_index** out);
+cx_status index_prepare_store(cx_index* h);
+cx_status index_insert(cx_index* h, const uint8_t* ids, const float* rows, uint64_t n, uint32_t len, bool on_device,
+                       const uint64_t* seq);
+cx_status index_remove(cx_index* h, const uint8_t id[16]);
+cx_status index_set_metadata(cx_index* h, const uint8_t id[16], const char* kind, const char* agent);
+cx_status index_rebuild(cx_index* h);
+cx_status index_set_option(cx_index* h, const char* key, int64_t value);
+cx_status index_save_vectors(cx_index* h, FILE* fp, uint64_t r0, uint64_t r1);
+uint64_t index_meta_count(const cx_index* h);
+bool index_save_meta(const cx_index* h, FILE* fp);
+cx_status index_load_into(const char* path, cx_status (*make)(uint32_t, void*, cx_index**), void* ctx, cx_index** out);
+void index_add_stats(const cx_index* h, cx_stats* out);
+
+// multi-device index (cx_sharded.cu): every entry point of the C ABI forwards here when h->shards is set
+void shard_destroy(cx_index* h);
+cx_status shard_reserve(cx_index* h, uint64_t n_rows);
+cx_status shard_insert(cx_index* h, const uint8_t* ids, const float* rows, uint64_t n, uint32_t len, bool on_device);
+cx_status shard_remove(cx_index* h, const uint8_t id[16]);
+cx_status shard_set_metadata(cx_index* h, const uint8_t id[16], const char* kind, const char* agent);
+uint64_t shard_len(const cx_index* h);
+cx_status shard_rebuild(cx_index* h);
+cx_status shard_save(cx_index* h, const char* path);
+cx_status shard_stats(cx_index* h, cx_stats* out);
+cx_status shard_set_option(cx_index* h, const char* key, int64_t value);
+cx_status shard_search_host(cx_index* h, const float* queries, uint64_t B, uint32_t qlen, uint64_t k,
+                            const cx_filter* filter, bool threshold_mode, float threshold, uint8_t* out_ids,
+                            float* out_score, float* out_dist, uint64_t* out_n, uint64_t* out_total);
+cx_status shard_dedup_scan(cx_index* h, float threshold, uint32_t per_node_cap, uint64_t max_pairs, uint8_t* out_a_ids,
+                           uint8_t* out_b_ids, float* out_score, uint64_t* out_n, uint64_t* out_total);
+cx_status shard_autolink_batch(cx_index* h, const uint8_t* new_ids, const float* embeddings, uint64_t B, uint64_t k,
+                               float threshold, uint32_t max_edges_per_node, uint8_t* out_to_ids, float* out_score,
+                               uint32_t* out_n);
+cx_status shard_search_device(cx_index* h, const float* d_queries, uint64_t B, uint64_t k, const cx_filter* filter,
+                              uint32_t* d_out_rows, float* d_out_score, float* d_out_distance, uint8_t* d_out_ids,
+                              uint32_t* d_out_n, void* stream, void** ticket);
+cx_status shard_search_device_end(cx_index* h, void* ticket, uint64_t* n_redone);
 
 }  // namespace cx

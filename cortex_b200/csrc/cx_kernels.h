@@ -52,7 +52,9 @@ struct ResultView {
 // K4: norms (reference order), reciprocal norms, bf16 shadow rows for rows [r0, r0+n)
 void launch_prepare_rows(float* E, float* norm, float* rnorm, void* E16, uint32_t dim, uint32_t ld,
                          uint32_t ld16, uint32_t r0, uint32_t n, cudaStream_t s);
-void launch_count_irregular(const float* rnorm, uint32_t n, uint32_t* out, cudaStream_t s);
+// *counter += sign * (rows of [r0, r0+n) with a NaN reciprocal norm that are not removed)
+void launch_count_irregular(const float* rnorm, const uint32_t* meta, uint32_t r0, uint32_t n, int sign,
+                            uint32_t* counter, cudaStream_t s);
 // queries: reference-order norm over qlen, reciprocal
 void launch_prepare_queries(const float* Q, float* qnorm, float* rqnorm, uint32_t nq, uint32_t qlen,
                             uint32_t ldq, cudaStream_t s);
@@ -83,9 +85,11 @@ cudaError_t launch_select_rescore(const StoreView& st, const QueryView& qv, uint
 // qv.qnorm must hold the query norms.  self_rows (optional): skip that row; upper_only: keep
 // only rows above it (the dedup scanner's unordered pairs, linker/dedup.rs:96-105).
 size_t threshold_rescore_smem(uint32_t ld);
+// q_seq / row_seq (multi-device pair scans): keep row r only if row_seq[r] > q_seq[q].
 cudaError_t launch_threshold_rescore(const StoreView& st, const QueryView& qv, uint32_t q0, uint32_t nq,
                                      const CandView& cv, const ResultView& rv, uint32_t* total, float threshold,
-                                     const uint32_t* self_rows, bool upper_only, cudaStream_t s);
+                                     const uint32_t* self_rows, bool upper_only, cudaStream_t s,
+                                     const uint64_t* q_seq = nullptr, const uint64_t* row_seq = nullptr);
 
 // K2: tcgen05 bf16 pass over the normalised shadow matrix.  Q16 = normalised bf16 queries
 // [round_up(nq_total,128)][ld16] made by launch_query_bf16.  One launch serves at most
@@ -93,9 +97,15 @@ cudaError_t launch_threshold_rescore(const StoreView& st, const QueryView& qv, u
 // cv.KP must be tensor_keep(k) (32 / 64 / 128 scores tracked per query in registers).
 uint32_t tensor_keep(uint32_t k);
 bool tensor_scan_eligible(uint32_t ld16, uint32_t k);
-void tensor_set_debug(int mode);  // measurement hook (wrong results): 1 = no epilogue work, 2 = no hit handling
-void tensor_set_epi_warps(int n);  // 8 or 16 epilogue warps per CTA
-void tensor_set_pair(int on);  // test hook: 0 = never use the CTA-pair (cta_group::2) form
+// Per-index tuning of the tensor pass, read-only while searches run: pair = CTA-pair (cta_group::2) form,
+// epi_warps = 8 | 16 epilogue warps per CTA.  debug is honoured only by -DCX_PROBE builds (measurement
+// hook, results become wrong: 1 no epilogue work, 2 no hit handling, 4 no E traffic).
+struct TensorTuning {
+  int pair = 0;
+  int epi_warps = 8;
+  int debug = 0;
+};
+void tensor_report_clock();  // CX_PROBE builds: print the effective SM clock of block 0 in the last debug-mode launch
 size_t tensor_scratch_bytes(int sm_count);
 void launch_query_bf16(const float* Q, uint32_t ldq, uint32_t dim, uint32_t nq, uint32_t nq_pad, void* Q16,
                        uint32_t ld16, cudaStream_t s);
@@ -104,13 +114,13 @@ void launch_query_bf16(const float* Q, uint32_t ldq, uint32_t dim, uint32_t nq, 
 uint32_t tensor_sample_tiles(uint32_t n_rows, uint32_t nq);
 cudaError_t launch_tensor_bootstrap(const StoreView& st, const void* Q16, uint32_t q0, uint32_t nq,
                                     const DevFilter& flt, bool check_rows, const CandView& cv, float* dump,
-                                    uint32_t n_slots, int sm_count, cudaStream_t s);
+                                    uint32_t n_slots, int sm_count, cudaStream_t s, const TensorTuning& tune);
 // One phase of the scan: row tiles [tile0, tile0 + n_tiles) of tensor_tiles(n_rows) (256 rows each).
 // check_rows: a filter is active or rows were removed -> test metadata before nominating a row
 cudaError_t launch_tensor_scan(const StoreView& st, const void* Q16, uint32_t q0, uint32_t nq,
                                const DevFilter& flt, bool check_rows, const CandView& cv, uint64_t* lists,
                                uint32_t tile0, uint32_t n_tiles, int sm_count, cudaStream_t s,
-                               bool static_tau = false);
+                               const TensorTuning& tune, bool static_tau = false);
 // Threshold scans: fix every query's cut-off at the approximate cosine thr_cos (then scan with static_tau).
 void launch_fill_tau(const CandView& cv, uint32_t q0, uint32_t nq, float thr_cos, cudaStream_t s);
 uint32_t tensor_tiles(uint32_t n_rows);
@@ -118,8 +128,11 @@ uint32_t tensor_tiles(uint32_t n_rows);
 cudaError_t launch_tau_refine(const CandView& cv, uint32_t q0, uint32_t nq, float margin, cudaStream_t s);
 
 // Exact path: every row scored with reference arithmetic -> keys[n_rows] for one query
+// self_row / upper_only: the dedup scanner's pair rules (skip the query's own row; keep only rows above it)
+// row_seq / q_seq (multi-device pair scans): keep row r only if row_seq[r] > q_seq
 void launch_exact_keys(const StoreView& st, const QueryView& qv, uint32_t q, const DevFilter& flt,
-                       uint64_t* keys, cudaStream_t s);
+                       uint64_t* keys, cudaStream_t s, uint32_t self_row = 0xFFFFFFFFu, bool upper_only = false,
+                       const uint64_t* row_seq = nullptr, uint64_t q_seq = 0);
 // sort keys descending (cub radix sort); tmp sized by exact_sort_tmp_bytes
 size_t exact_sort_tmp_bytes(uint32_t n);
 cudaError_t exact_sort(uint64_t* keys_in, uint64_t* keys_out, uint32_t n, void* tmp, size_t tmp_bytes,
@@ -135,9 +148,20 @@ void launch_autolink_filter(const uint32_t* rows, const float* score, const uint
                             uint32_t* out_rows, float* out_score, uint8_t* out_ids, uint32_t* out_n,
                             cudaStream_t s);
 
+// dst[i] = base + i
+void launch_iota(uint32_t* dst, uint32_t n, uint32_t base, cudaStream_t s);
+// Dedup scan: per-node partner lists [B][kd] -> dense (a row, b row, score bits) triples.  Nodes whose own
+// row (r0 + i) was removed contribute nothing (n and tot are zeroed in place).  off [B+1] receives the
+// exclusive prefix sum of the counts (off[B] = pairs in this block); at most `limit` triples are written.
+void launch_compact_pairs(const uint32_t* rows, const float* score, uint32_t* n, uint32_t* tot, const uint32_t* meta,
+                          uint32_t r0, uint32_t B, uint32_t kd, uint32_t* off, uint32_t* pairs, uint32_t limit,
+                          cudaStream_t s);
+
+void launch_compact_offsets(uint32_t* n, const uint32_t* dead, uint32_t B, uint32_t* off, cudaStream_t s);
+
 // compaction helper for rebuild(): dst[i] = src[live[i]] for all per-row arrays
-void launch_gather_rows(const StoreView& src, float* E, float* norm, float* rnorm, uint32_t* meta,
-                        uint32_t* agent, uint8_t* ids, void* E16, const uint32_t* live, uint32_t n_live,
-                        cudaStream_t s);
+void launch_gather_rows(const StoreView& src, const uint64_t* src_seq, float* E, float* norm, float* rnorm,
+                        uint32_t* meta, uint32_t* agent, uint8_t* ids, void* E16, uint64_t* seq,
+                        const uint32_t* live, uint32_t n_live, cudaStream_t s);
 
 }  // namespace cx

@@ -117,6 +117,88 @@ void launch_autolink_filter(const uint32_t* rows, const float* score, const uint
                                                          out_rows, out_score, out_ids, out_n);
 }
 
+__global__ void iota_kernel(uint32_t* __restrict__ dst, uint32_t n, uint32_t base) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = base + i;
+}
+void launch_iota(uint32_t* dst, uint32_t n, uint32_t base, cudaStream_t s) {
+  if (n) iota_kernel<<<(n + 255) / 256, 256, 0, s>>>(dst, n, base);
+}
+
+// ---- dedup scan: per-node partner lists -> dense triples ------------------------------------
+// One CTA: exclusive prefix sum of the per-node counts (removed nodes count nothing: dedup.rs:73-76).
+constexpr int CP_THREADS = 1024;
+__global__ void __launch_bounds__(CP_THREADS) pair_offsets_kernel(uint32_t* __restrict__ n, uint32_t* __restrict__ tot,
+                                                                  const uint32_t* __restrict__ meta, uint32_t r0,
+                                                                  uint32_t B, uint32_t* __restrict__ off) {
+  __shared__ uint32_t warp_sum[CP_THREADS / 32];
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t per = (B + CP_THREADS - 1) / CP_THREADS;
+  const uint32_t i0 = tid * per, i1 = min(B, i0 + per);
+  uint32_t mine = 0;
+  for (uint32_t i = i0; i < i1; ++i) {
+    if (meta[r0 + i] & META_DEAD) {
+      n[i] = 0;
+      if (tot) tot[i] = 0;
+    }
+    mine += n[i];
+  }
+  uint32_t incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= (uint32_t)o) incl += t;
+  }
+  if (lane == 31) warp_sum[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = warp_sum[lane];
+    uint32_t wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= (uint32_t)o) wi += t;
+    }
+    warp_sum[lane] = wi - w;  // exclusive over warps
+  }
+  __syncthreads();
+  uint32_t run = warp_sum[warp] + incl - mine;
+  for (uint32_t i = i0; i < i1; ++i) {
+    off[i] = run;
+    run += n[i];
+  }
+  if (tid == CP_THREADS - 1) off[B] = run;  // the last thread's chunk ends the array (empty chunks included)
+}
+
+// one warp per node: its partners, in order, to their dense positions
+__global__ void pair_write_kernel(const uint32_t* __restrict__ rows, const float* __restrict__ score,
+                                  const uint32_t* __restrict__ n, const uint32_t* __restrict__ off, uint32_t r0,
+                                  uint32_t B, uint32_t kd, uint32_t* __restrict__ pairs, uint32_t limit) {
+  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= B) return;
+  const uint32_t m = n[w], base = off[w];
+  for (uint32_t j = lane; j < m; j += 32) {
+    const uint32_t pos = base + j;
+    if (pos >= limit) break;
+    pairs[3 * (size_t)pos] = r0 + w;
+    pairs[3 * (size_t)pos + 1] = rows[(size_t)w * kd + j];
+    pairs[3 * (size_t)pos + 2] = __float_as_uint(score[(size_t)w * kd + j]);
+  }
+}
+
+void launch_compact_pairs(const uint32_t* rows, const float* score, uint32_t* n, uint32_t* tot, const uint32_t* meta,
+                          uint32_t r0, uint32_t B, uint32_t kd, uint32_t* off, uint32_t* pairs, uint32_t limit,
+                          cudaStream_t s) {
+  if (!B) return;
+  pair_offsets_kernel<<<1, CP_THREADS, 0, s>>>(n, tot, meta, r0, B, off);
+  if (limit) pair_write_kernel<<<(B + 7) / 8, 256, 0, s>>>(rows, score, n, off, r0, B, kd, pairs, limit);
+}
+
+// the same prefix sum over counts with an explicit "removed" flag per node (multi-device dedup scan)
+void launch_compact_offsets(uint32_t* n, const uint32_t* dead, uint32_t B, uint32_t* off, cudaStream_t s) {
+  if (B) pair_offsets_kernel<<<1, CP_THREADS, 0, s>>>(n, nullptr, dead, 0, B, off);
+}
+
 }  // namespace cx
 
 using namespace cx;

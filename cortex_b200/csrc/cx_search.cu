@@ -121,10 +121,6 @@ struct SearchBufs {
   float* score = nullptr;
   float* dist = nullptr;
   uint8_t* ids = nullptr;
-  uint64_t* ekeys_a = nullptr;
-  uint64_t* ekeys_b = nullptr;
-  void* sort_tmp = nullptr;
-  size_t sort_tmp_bytes = 0;
   uint32_t* n_total = nullptr;
   uint32_t* totals = nullptr;     // threshold scans: rows that qualify, per query
 };
@@ -300,7 +296,6 @@ Plan make_plan(const cx_index* h, uint64_t B, uint32_t qlen, uint32_t ldq, uint3
 size_t carve_bufs(void* base, const cx_index* h, const Plan& pl, uint32_t n_excl, bool own_queries,
                   bool own_results, SearchBufs* sb) {
   Carver c(base);
-  const uint32_t n_rows = (uint32_t)h->n_rows;
   sb->dQ = own_queries ? c.take<float>(pl.B * pl.ldq) : nullptr;
   sb->qnorm = c.take<float>(pl.B);
   sb->rqnorm = c.take<float>(pl.B);
@@ -337,21 +332,19 @@ size_t carve_bufs(void* base, const cx_index* h, const Plan& pl, uint32_t n_excl
   } else {
     sb->ok = c.take<uint32_t>(pl.B);
   }
-  sb->ekeys_a = c.take<uint64_t>(n_rows);
-  sb->ekeys_b = c.take<uint64_t>(n_rows);
-  sb->sort_tmp_bytes = exact_sort_tmp_bytes(n_rows);
-  sb->sort_tmp = c.take<char>(sb->sort_tmp_bytes);
   return align_up(c.off, 256);
 }
 
-// Core.  Queries are on the device at sb.dQ [B][ldq]; results land in sb.rows/score/
-// dist/ids/n (device).  If h_block != nullptr the whole ResultBlock is also copied to
-// it (pinned host).  h_ok: pinned host scratch of B words.  Returns with the stream idle.
 // Extras of a pair scan (the dedup self-join): queries are rows of the index itself.
 struct PairScan {
-  const uint32_t* self_rows;  // device [B]: the row each query is
-  bool upper_only;            // keep only partners above the query's own row
-  uint32_t tile0;             // first row tile worth scanning (rows below it cannot qualify)
+  const uint32_t* self_rows = nullptr;  // device [B]: the row each query is
+  uint32_t self_base = 0;               // ... which is self_base + b for query b (host-side copy of the same fact)
+  bool upper_only = false;              // keep only partners above the query's own row
+  uint32_t tile0 = 0;                   // first row tile worth scanning (rows below it cannot qualify)
+  // multi-device form: the queries are rows of some shard, the corpus is this shard; a partner qualifies
+  // when its global insertion number is above the query's (which also skips the query itself)
+  const uint64_t* q_seq = nullptr;      // device [B]
+  const uint64_t* h_q_seq = nullptr;    // host copy
 };
 
 // phase: RUN_ALL = the whole call; RUN_ENQUEUE = everything up to (and including) the copy of the
@@ -360,10 +353,103 @@ struct PairScan {
 enum { RUN_ALL = 0, RUN_ENQUEUE = 1, RUN_FINISH = 2 };
 constexpr cx_status CX_PENDING = (cx_status)-1;
 
+// Identity of a device-resident search for graph replay: two calls with equal keys enqueue exactly the
+// same kernels with exactly the same arguments.
+struct GraphKey {
+  uint64_t w[8];
+  bool operator==(const uint64_t (&o)[8]) const { return memcmp(w, o, sizeof w) == 0; }
+};
+
+uint64_t fnv(uint64_t hsh, const void* p, size_t n) {
+  const unsigned char* c = (const unsigned char*)p;
+  for (size_t i = 0; i < n; ++i) hsh = (hsh ^ c[i]) * 0x100000001B3ull;
+  return hsh;
+}
+
+struct Launcher {
+  cx_index* h;
+  Workspace* ws;
+  cudaStream_t s;
+  bool capturing = false;
+  uint32_t n_launch = 0;
+  cudaError_t record(cudaEvent_t ev) const {
+    // inside a capture a plain record would become an internal dependency; the external flag makes
+    // it a real timing node that can be read after the graph ran
+    return capturing ? cudaEventRecordWithFlags(ev, s, cudaEventRecordExternal) : cudaEventRecord(ev, s);
+  }
+};
+
+// The fast top-k path, enqueue part: nominate (K1 or K2 in phases) -> select + exact rescore + verify
+// -> copy of the verification flags (or of the whole result block) to the host.
+cx_status enqueue_topk(Launcher& L, const StoreView& st, const QueryView& qv, const DevFilter& flt, CandView cv,
+                       const ResultView& rv, const SearchBufs& sb, const Plan& pl, char* h_block, uint32_t* h_ok) {
+  cx_index* h = L.h;
+  cudaStream_t s = L.s;
+  const uint64_t B = pl.B;
+  const ResultBlock rb = ResultBlock::make(B, pl.kd);
+  if (h->profile) CU(L.record(L.ws->ev0));
+  if (pl.tensor) {
+    launch_query_bf16(sb.dQ, pl.ldq, h->dim, (uint32_t)B, (uint32_t)align_up(B, 128), sb.q16, h->ld16, s);
+    L.n_launch += 1;
+    const bool check_rows = flt.has_kinds || flt.has_agent || flt.n_excl || h->n_live != h->n_rows;
+    // cut-off bootstrap for every launch group first (the sample buffer is reused in stream order)
+    uint64_t q0 = 0;
+    for (const uint32_t nq : pl.groups) {
+      CU(launch_tensor_bootstrap(st, sb.q16, (uint32_t)q0, nq, flt, check_rows, cv, sb.dump, pl.n_slots, h->sm_count,
+                                 s, h->tensor_tune));
+      L.n_launch += 2;
+      q0 += nq;
+    }
+    const std::vector<uint32_t> phases = tensor_phases(tensor_tiles(st.n_rows), pl.n_slots, pl.growth, nullptr);
+    q0 = 0;
+    for (const uint32_t nq : pl.groups) {
+      uint32_t tile0 = 0;
+      for (size_t ph = 0; ph < phases.size(); ++ph) {
+        if (ph) {  // tighten the cut-off with what the earlier phases found
+          CU(launch_tau_refine(cv, (uint32_t)q0, nq, 2.0f * eps_tensor(h->dim), s));
+          L.n_launch += 1;
+        }
+        CU(launch_tensor_scan(st, sb.q16, (uint32_t)q0, nq, flt, check_rows, cv, sb.lists, tile0, phases[ph],
+                              h->sm_count, s, h->tensor_tune));
+        tile0 += phases[ph];
+        L.n_launch += 1;
+      }
+      q0 += nq;
+    }
+  } else {
+    for (uint64_t q0 = 0; q0 < B; q0 += 8) {
+      const uint32_t nq = (uint32_t)(B - q0 < 8 ? B - q0 : 8);
+      CU(launch_stream_scan(st, qv, (uint32_t)q0, nq, flt, cv, h->sm_count, s));
+      L.n_launch += 1;
+    }
+  }
+  if (h->profile) CU(L.record(L.ws->ev1));
+  CU(launch_select_rescore(st, qv, 0, (uint32_t)B, cv, rv, pl.tensor ? eps_tensor(h->dim) : eps_stream(h->dim),
+                           /*scale_by_rqn=*/pl.tensor ? 0 : 1, s));
+  L.n_launch += 1;
+  if (h_block) CU(cudaMemcpyAsync(h_block, sb.res, rb.total, cudaMemcpyDeviceToHost, s));
+  else CU(cudaMemcpyAsync(h_ok, sb.ok, B * 4, cudaMemcpyDeviceToHost, s));
+  return CX_OK;
+}
+
+void add_pass_time(cx_index* h, Workspace* ws, uint32_t n_pass) {
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, ws->ev0, ws->ev1) == cudaSuccess) {
+    h->pass_ns += (uint64_t)(ms * 1e6);
+    h->pass_launches += n_pass;
+  } else {
+    (void)cudaGetLastError();
+  }
+}
+
+// Core.  Queries are on the device at sb.dQ [B][ldq]; results land in sb.rows/score/
+// dist/ids/n (device).  If h_block != nullptr the whole ResultBlock is also copied to
+// it (pinned host).  h_ok: pinned host scratch of B words.  Returns with the stream idle.
+// gk (optional): identity of the call for graph replay of the enqueue part.
 cx_status run_search(cx_index* h, Workspace* ws, const FilterHost& fh, const SearchBufs& sb, const Plan& pl,
                      bool threshold_mode, float threshold, char* h_block, uint32_t* h_ok,
                      uint64_t* h_total /* threshold mode: per-query totals */, const PairScan* tp = nullptr,
-                     int phase = RUN_ALL) {
+                     int phase = RUN_ALL, const GraphKey* gk = nullptr) {
   cudaStream_t s = ws->stream;
   const uint64_t B = pl.B;
   StoreView st = h->view();
@@ -422,7 +508,7 @@ cx_status run_search(cx_index* h, Workspace* ws, const FilterHost& fh, const Sea
       uint64_t q0 = 0;
       for (const uint32_t nq : pl.groups) {
         CU(launch_tensor_scan(st, sb.q16, (uint32_t)q0, nq, flt, check_rows, cv, sb.lists, t0, nt, h->sm_count, s,
-                              /*static_tau=*/true));
+                              h->tensor_tune, /*static_tau=*/true));
         ++n_pass;
         q0 += nq;
       }
@@ -436,7 +522,7 @@ cx_status run_search(cx_index* h, Workspace* ws, const FilterHost& fh, const Sea
     }
     if (h->profile) CU(cudaEventRecord(ws->ev1, s));
     CU(launch_threshold_rescore(st, qv, 0, (uint32_t)B, cv, rv, sb.totals, threshold, tp ? tp->self_rows : nullptr,
-                                tp ? tp->upper_only : false, s));
+                                tp ? tp->upper_only : false, s, tp ? tp->q_seq : nullptr, h->dSeq));
     h->launches += n_pass + 1;
     std::vector<uint32_t> tot32;
     if (h_total) tot32.resize(B);
@@ -448,12 +534,7 @@ cx_status run_search(cx_index* h, Workspace* ws, const FilterHost& fh, const Sea
     }
     if (h_total) CU(cudaMemcpyAsync(tot32.data(), sb.totals, B * 4, cudaMemcpyDeviceToHost, s));
     CU(ws->wait(h->blocking_sync));
-    if (h->profile) {
-      float ms = 0.f;
-      CU(cudaEventElapsedTime(&ms, ws->ev0, ws->ev1));
-      h->pass_ns += (uint64_t)(ms * 1e6);
-      h->pass_launches += n_pass;
-    }
+    if (h->profile) add_pass_time(h, ws, n_pass);
     ws->state_dirty = false;
     for (uint64_t b = 0; b < B; ++b) {
       if (!h_ok[b]) redo.push_back((uint32_t)b);
@@ -462,7 +543,8 @@ cx_status run_search(cx_index* h, Workspace* ws, const FilterHost& fh, const Sea
     (pl.tensor ? h->q_tensor : h->q_stream) += B - redo.size();
     h->fallbacks += redo.size();
     if (redo.empty()) return CX_OK;
-    if (tp) return fail(CX_ERR_VALIDATION, "threshold scan overflow");  // pair scans have no per-query exact fallback
+    // what overflowed its nominee list (a node with thousands of near-threshold partners) goes to the
+    // exact path below, pair rules included
   } else if (pl.fast) {
     CandView cv;
     cv.keys = sb.cand_keys;
@@ -479,59 +561,53 @@ cx_status run_search(cx_index* h, Workspace* ws, const FilterHost& fh, const Sea
       ws->state_dirty = true;  // until the select kernel has re-zeroed it and the stream drained cleanly
       cv.cnt = ws->d_cnt;
       cv.gtau = ws->d_gtau;
-      if (pl.tensor) {
-        launch_query_bf16(sb.dQ, pl.ldq, h->dim, (uint32_t)B, (uint32_t)align_up(B, 128), sb.q16, h->ld16, s);
-        h->launches += 1;
-        const bool check_rows = flt.has_kinds || flt.has_agent || flt.n_excl || h->n_live != h->n_rows;
-        // cut-off bootstrap for every launch group first (the sample buffer is reused in stream order)
-        uint64_t q0 = 0;
-        for (const uint32_t nq : pl.groups) {
-          CU(launch_tensor_bootstrap(st, sb.q16, (uint32_t)q0, nq, flt, check_rows, cv, sb.dump, pl.n_slots,
-                                     h->sm_count, s));
-          h->launches += 2;
-          q0 += nq;
+      Launcher L{h, ws, s};
+      const bool graphable = gk && h->use_graphs && !ws->graph_broken;
+      if (graphable && ws->graph && *gk == ws->graph_key) {
+        // the same call as the one recorded: one launch replays the whole sequence
+        CU(cudaGraphLaunch(ws->graph, s));
+        h->graph_launches += 1;
+        h->launches += ws->graph_nlaunch;
+      } else if (graphable && *gk == ws->last_key) {
+        // second time in a row: record the sequence while enqueueing nothing, then launch the recording
+        ws->drop_graph();
+        cudaGraph_t g = nullptr;
+        cx_status est = CX_OK;
+        cudaError_t ce = cudaStreamBeginCapture(s, cudaStreamCaptureModeRelaxed);
+        if (ce == cudaSuccess) {
+          L.capturing = true;
+          est = enqueue_topk(L, st, qv, flt, cv, rv, sb, pl, h_block, h_ok);
+          ce = cudaStreamEndCapture(s, &g);
+          L.capturing = false;
         }
-        if (h->profile) CU(cudaEventRecord(ws->ev0, s));
-        const std::vector<uint32_t> phases =
-            tensor_phases(tensor_tiles(st.n_rows), pl.n_slots, pl.growth, nullptr);
-        q0 = 0;
-        for (const uint32_t nq : pl.groups) {
-          uint32_t tile0 = 0;
-          for (size_t ph = 0; ph < phases.size(); ++ph) {
-            if (ph) {  // tighten the cut-off with what the earlier phases found
-              CU(launch_tau_refine(cv, (uint32_t)q0, nq, 2.0f * eps_tensor(h->dim), s));
-              h->launches += 1;
-            }
-            CU(launch_tensor_scan(st, sb.q16, (uint32_t)q0, nq, flt, check_rows, cv, sb.lists, tile0, phases[ph],
-                                  h->sm_count, s));
-            tile0 += phases[ph];
-            h->launches += 1;
-          }
-          q0 += nq;
+        if (ce == cudaSuccess && est == CX_OK && g) ce = cudaGraphInstantiate(&ws->graph, g, 0);
+        if (g) cudaGraphDestroy(g);
+        if (ce != cudaSuccess || est != CX_OK || !ws->graph) {
+          // recording is an optimisation: fall back to plain launches for this workspace
+          (void)cudaGetLastError();
+          ws->drop_graph();
+          ws->graph_broken = true;
+          Launcher L2{h, ws, s};
+          cx_status st2 = enqueue_topk(L2, st, qv, flt, cv, rv, sb, pl, h_block, h_ok);
+          if (st2 != CX_OK) return st2;
+          h->launches += L2.n_launch;
+        } else {
+          memcpy(ws->graph_key, gk->w, sizeof ws->graph_key);
+          ws->graph_nlaunch = L.n_launch;
+          CU(cudaGraphLaunch(ws->graph, s));
+          h->graph_launches += 1;
+          h->launches += L.n_launch;
         }
       } else {
-        if (h->profile) CU(cudaEventRecord(ws->ev0, s));
-        for (uint64_t q0 = 0; q0 < B; q0 += 8) {
-          const uint32_t nq = (uint32_t)(B - q0 < 8 ? B - q0 : 8);
-          CU(launch_stream_scan(st, qv, (uint32_t)q0, nq, flt, cv, h->sm_count, s));
-        }
-        h->launches += n_pass;
+        if (gk) memcpy(ws->last_key, gk->w, sizeof ws->last_key);
+        cx_status est = enqueue_topk(L, st, qv, flt, cv, rv, sb, pl, h_block, h_ok);
+        if (est != CX_OK) return est;
+        h->launches += L.n_launch;
       }
-      if (h->profile) CU(cudaEventRecord(ws->ev1, s));
-      CU(launch_select_rescore(st, qv, 0, (uint32_t)B, cv, rv, pl.tensor ? eps_tensor(h->dim) : eps_stream(h->dim),
-                               /*scale_by_rqn=*/pl.tensor ? 0 : 1, s));
-      h->launches += 1;
-      if (h_block) CU(cudaMemcpyAsync(h_block, sb.res, rb.total, cudaMemcpyDeviceToHost, s));
-      else CU(cudaMemcpyAsync(h_ok, sb.ok, B * 4, cudaMemcpyDeviceToHost, s));
       if (phase == RUN_ENQUEUE) return CX_PENDING;
     }
     CU(ws->wait(h->blocking_sync));
-    if (h->profile) {
-      float ms = 0.f;
-      CU(cudaEventElapsedTime(&ms, ws->ev0, ws->ev1));
-      h->pass_ns += (uint64_t)(ms * 1e6);
-      h->pass_launches += n_pass;
-    }
+    if (h->profile) add_pass_time(h, ws, n_pass);
     for (uint64_t b = 0; b < B; ++b)
       if (!h_ok[b]) redo.push_back((uint32_t)b);
     (pl.tensor ? h->q_tensor : h->q_stream) += B - redo.size();
@@ -585,16 +661,25 @@ cx_status run_search(cx_index* h, Workspace* ws, const FilterHost& fh, const Sea
     for (uint64_t b = 0; b < B; ++b) redo[b] = (uint32_t)b;
   }
 
-  // exact path
+  // exact path: reference arithmetic for every row, radix sort, emit.  Its buffers (two key arrays over
+  // the whole shard + sort scratch) belong to the workspace and exist only once a query got here.
   uint32_t min_ord = 1;  // every real key, NaN included (they sort last)
   if (threshold_mode) {
     if (threshold != threshold) min_ord = 0xFFFFFFFFu;  // score >= NaN is false
     else min_ord = ord_from_score(threshold > 0.0f ? threshold : 0.0f);
   }
+  const size_t keys_bytes = align_up((size_t)st.n_rows * 8, 256), sort_bytes = exact_sort_tmp_bytes(st.n_rows);
+  CU(ws->ensure_exact(2 * keys_bytes + sort_bytes));
+  uint64_t* ekeys_a = (uint64_t*)ws->dx;
+  uint64_t* ekeys_b = (uint64_t*)((char*)ws->dx + keys_bytes);
+  void* sort_tmp = (char*)ws->dx + 2 * keys_bytes;
   for (uint32_t b : redo) {
-    launch_exact_keys(st, qv, b, flt, sb.ekeys_a, s);
-    CU(exact_sort(sb.ekeys_a, sb.ekeys_b, st.n_rows, sb.sort_tmp, sb.sort_tmp_bytes, s));
-    launch_exact_emit(st, qv, b, sb.ekeys_b, st.n_rows, pl.kd, min_ord, sb.rows + (size_t)b * pl.kd,
+    if (tp && tp->q_seq)
+      launch_exact_keys(st, qv, b, flt, ekeys_a, s, 0xFFFFFFFFu, false, h->dSeq, tp->h_q_seq[b]);
+    else
+      launch_exact_keys(st, qv, b, flt, ekeys_a, s, tp ? tp->self_base + b : 0xFFFFFFFFu, tp ? tp->upper_only : false);
+    CU(exact_sort(ekeys_a, ekeys_b, st.n_rows, sort_tmp, sort_bytes, s));
+    launch_exact_emit(st, qv, b, ekeys_b, st.n_rows, pl.kd, min_ord, sb.rows + (size_t)b * pl.kd,
                       sb.score + (size_t)b * pl.kd, sb.dist + (size_t)b * pl.kd,
                       sb.ids ? sb.ids + (size_t)b * pl.kd * 16 : nullptr, sb.n + b, sb.n_total, s);
     h->launches += 4;
@@ -612,6 +697,105 @@ cx_status run_search(cx_index* h, Workspace* ws, const FilterHost& fh, const Sea
   return CX_OK;
 }
 
+// Device part of a threshold scan whose queries already sit in device memory (used by the host
+// entry points, the dedup self-join and the multi-device index).  Results [B][kd] land in the
+// workspace-owned block (sb.*), per-query totals in totals[].  Returns with the stream idle.
+struct ThresholdCall {
+  WsLease lease;
+  FilterHost fh;
+  SearchBufs sb;
+  Plan pl;
+  explicit ThresholdCall(cx_index* h) : lease(h) {}
+};
+
+}  // namespace
+
+namespace cx {
+
+// Batched search_threshold on one device with device-resident queries [B][dim] and device-resident
+// results: rows / score / dist [B][cap] (+ ids if d_ids), n [B] entries written, d_total [B] rows that
+// qualify (all on this index's device).  pair (optional) applies the dedup scanner's pair rules.
+// Blocks until the results are complete.
+cx_status index_threshold_device(cx_index* h, const float* d_queries, uint32_t qlen, uint32_t q_stride, uint64_t B,
+                                 float threshold, const cx_filter* filter, uint64_t cap, uint32_t* d_rows,
+                                 float* d_score, float* d_dist, uint8_t* d_ids, uint32_t* d_n, uint32_t* d_total,
+                                 uint64_t* h_total, const PairRules* pair) {
+  if (!B) return CX_OK;
+  CU(cudaSetDevice(h->device));
+  cx_status st = settle(h);
+  if (st != CX_OK) return st;
+  const uint64_t kd64 = cap < h->n_rows ? cap : h->n_rows;
+  ThresholdCall t(h);
+  CU(t.lease.init());
+  Workspace* ws = t.lease.ws;
+  if (h_total)
+    for (uint64_t b = 0; b < B; ++b) h_total[b] = 0;
+  if (h->n_live == 0 || kd64 == 0) {
+    CU(cudaMemsetAsync(d_n, 0, B * 4, ws->stream));
+    if (d_total) CU(cudaMemsetAsync(d_total, 0, B * 4, ws->stream));
+    CU(ws->wait(h->blocking_sync));
+    return CX_OK;
+  }
+  const uint32_t kd = (uint32_t)kd64;
+  const uint32_t ldq = (uint32_t)align_up(qlen > h->ld ? qlen : h->ld, 4);
+  build_filter(h, filter, &t.fh);
+  t.pl = make_plan(h, B, qlen, ldq, kd, true, threshold);
+  const bool own_q = q_stride != ldq;  // rows of the store itself are already padded to ld
+  const uint32_t n_excl = (uint32_t)t.fh.excl_rows.size();
+  const bool direct_out = kd == cap;  // the caller's [B][cap] layout is the kernels' [B][kd] layout
+  const size_t dbytes = carve_bufs(nullptr, h, t.pl, n_excl, own_q, !direct_out, &t.sb);
+  CU(ws->ensure(dbytes, align_up(B * 4, 256)));
+  carve_bufs(ws->d, h, t.pl, n_excl, own_q, !direct_out, &t.sb);
+  SearchBufs& sb = t.sb;
+  cudaStream_t s = ws->stream;
+  if (own_q) {
+    CU(cudaMemsetAsync(sb.dQ, 0, B * ldq * 4, s));
+    CU(cudaMemcpy2DAsync(sb.dQ, ldq * 4, d_queries, (size_t)q_stride * 4, (size_t)qlen * 4, B, cudaMemcpyDeviceToDevice, s));
+  } else {
+    sb.dQ = const_cast<float*>(d_queries);
+  }
+  if (direct_out) {
+    sb.rows = d_rows;
+    sb.score = d_score;
+    sb.dist = d_dist;
+    sb.ids = d_ids;
+    sb.n = d_n;
+  }
+  std::vector<uint64_t> totals(B, 0);
+  PairScan tp;
+  if (pair) {
+    tp.self_rows = pair->d_self_rows;
+    tp.self_base = pair->self_base;
+    tp.upper_only = pair->upper_only;
+    tp.tile0 = pair->first_row / 256;
+    tp.q_seq = pair->d_q_seq;
+    tp.h_q_seq = pair->h_q_seq;
+  }
+  st = run_search(h, ws, t.fh, sb, t.pl, true, threshold, nullptr, (uint32_t*)ws->hp, totals.data(),
+                  pair ? &tp : nullptr);
+  if (st != CX_OK) return st;
+  if (!direct_out) {  // cap > rows in the shard: spread [B][kd] into the caller's [B][cap]
+    CU(cudaMemcpy2DAsync(d_rows, cap * 4, sb.rows, kd * 4, kd * 4, B, cudaMemcpyDeviceToDevice, s));
+    CU(cudaMemcpy2DAsync(d_score, cap * 4, sb.score, kd * 4, kd * 4, B, cudaMemcpyDeviceToDevice, s));
+    CU(cudaMemcpy2DAsync(d_dist, cap * 4, sb.dist, kd * 4, kd * 4, B, cudaMemcpyDeviceToDevice, s));
+    if (d_ids) CU(cudaMemcpy2DAsync(d_ids, cap * 16, sb.ids, kd * 16, kd * 16, B, cudaMemcpyDeviceToDevice, s));
+    CU(cudaMemcpyAsync(d_n, sb.n, B * 4, cudaMemcpyDeviceToDevice, s));
+  }
+  if (h_total)
+    for (uint64_t b = 0; b < B; ++b) h_total[b] = totals[b];
+  if (d_total) {
+    uint32_t* ht = (uint32_t*)ws->hp;
+    for (uint64_t b = 0; b < B; ++b) ht[b] = (uint32_t)totals[b];
+    CU(cudaMemcpyAsync(d_total, ht, B * 4, cudaMemcpyHostToDevice, s));
+  }
+  CU(ws->wait(h->blocking_sync));
+  return CX_OK;
+}
+
+}  // namespace cx
+
+namespace {
+
 cx_status search_host(cx_index* h, const float* queries, uint64_t B, uint32_t qlen, uint64_t k,
                       const cx_filter* filter, bool threshold_mode, float threshold, uint8_t* out_ids,
                       float* out_score, float* out_dist, uint64_t* out_n, uint64_t* out_total) {
@@ -621,8 +805,13 @@ cx_status search_host(cx_index* h, const float* queries, uint64_t B, uint32_t ql
   for (uint64_t b = 0; b < B; ++b) out_n[b] = 0;
   if (out_total)
     for (uint64_t b = 0; b < B; ++b) out_total[b] = 0;
+  if (h->shards)
+    return shard_search_host(h, queries, B, qlen, k, filter, threshold_mode, threshold, out_ids, out_score, out_dist,
+                             out_n, out_total);
   if (h->n_live == 0 || B == 0) return CX_OK;  // index.rs:331: empty -> Ok(vec![])
   CU(cudaSetDevice(h->device));
+  cx_status sst = settle(h);
+  if (sst != CX_OK) return sst;
   const uint64_t kd64 = k < h->n_rows ? k : h->n_rows;
   if (kd64 == 0) return CX_OK;
   const uint32_t kd = (uint32_t)kd64;
@@ -658,9 +847,13 @@ cx_status search_host(cx_index* h, const float* queries, uint64_t B, uint32_t ql
     CU(cudaMemcpyAsync(sb.dQ, queries, B * ldq * 4, cudaMemcpyHostToDevice, s));
   } else {
     // stage queries, zero padded to ldq
-    for (uint64_t b = 0; b < B; ++b) {
-      memcpy(hQ + b * ldq, queries + b * qlen, (size_t)qlen * 4);
-      for (uint32_t d = qlen; d < ldq; ++d) hQ[b * ldq + d] = 0.0f;
+    if (qlen == ldq) {
+      memcpy(hQ, queries, (size_t)B * qlen * 4);
+    } else {
+      for (uint64_t b = 0; b < B; ++b) {
+        memcpy(hQ + b * ldq, queries + b * qlen, (size_t)qlen * 4);
+        for (uint32_t d = qlen; d < ldq; ++d) hQ[b * ldq + d] = 0.0f;
+      }
     }
     CU(cudaMemcpyAsync(sb.dQ, hQ, B * ldq * 4, cudaMemcpyHostToDevice, s));
   }
@@ -677,6 +870,16 @@ cx_status search_host(cx_index* h, const float* queries, uint64_t B, uint32_t ql
   const float* h_score = (const float*)(h_block + rb.score);
   const float* h_dist = (const float*)(h_block + rb.dist);
   const uint8_t* h_ids = (const uint8_t*)(h_block + rb.ids);
+  if (kd == k) {  // same layout on both sides: three block copies instead of 3B row copies
+    for (uint64_t b = 0; b < B; ++b) {
+      out_n[b] = h_n[b];
+      if (out_total) out_total[b] = threshold_mode ? totals[b] : h_n[b];
+    }
+    if (out_score) memcpy(out_score, h_score, (size_t)B * kd * 4);
+    if (out_dist) memcpy(out_dist, h_dist, (size_t)B * kd * 4);
+    if (out_ids) memcpy(out_ids, h_ids, (size_t)B * kd * 16);
+    return CX_OK;
+  }
   for (uint64_t b = 0; b < B; ++b) {
     const uint32_t n = h_n[b];
     out_n[b] = n;
@@ -750,7 +953,9 @@ extern "C" cx_status cx_search_threshold_batch(cx_index* h, const float* queries
 // row tiles at or above the batch (a pair is reported from its lower row), and the exact
 // rescoring keeps `score >= threshold` among partners above the query's own row.
 // Pairs come out ordered by (row of a asc, score desc, row of b asc) -- the order the reference
-// produces when storage lists nodes in insertion order.
+// produces when storage lists nodes in insertion order.  The per-node lists are compacted on the
+// device (prefix sum over the per-node counts, dense (a, b, score) triples): the copy back is the
+// size of the output, not of the [nodes][per_node_cap] result block.
 extern "C" cx_status cx_dedup_scan(cx_index* h, float threshold, uint32_t per_node_cap, uint64_t max_pairs,
                                    uint8_t* out_a_ids, uint8_t* out_b_ids, float* out_score, uint64_t* out_n,
                                    uint64_t* out_total) {
@@ -758,56 +963,74 @@ extern "C" cx_status cx_dedup_scan(cx_index* h, float threshold, uint32_t per_no
   if (!out_n) return fail(CX_ERR_VALIDATION, "null out_n");
   *out_n = 0;
   if (out_total) *out_total = 0;
-  if (h->n_live < 2 || !per_node_cap || threshold != threshold) return CX_OK;
   if (max_pairs && (!out_a_ids || !out_b_ids || !out_score)) return fail(CX_ERR_VALIDATION, "null output buffer");
+  if (h->shards)
+    return shard_dedup_scan(h, threshold, per_node_cap, max_pairs, out_a_ids, out_b_ids, out_score, out_n, out_total);
+  if (h->n_live < 2 || !per_node_cap || threshold != threshold) return CX_OK;
   CU(cudaSetDevice(h->device));
+  cx_status sst = settle(h);
+  if (sst != CX_OK) return sst;
   const uint32_t n_rows = (uint32_t)h->n_rows;
   const uint32_t kd = per_node_cap < n_rows ? per_node_cap : n_rows;
-  FilterHost fh;
-  build_filter(h, nullptr, &fh);
   const uint64_t QB = (uint64_t)h->sm_count * 128u;  // one tensor-pass launch group
   uint64_t n_out = 0, n_tot = 0;
-  std::vector<uint32_t> self(QB);
+  // outer workspace: self rows, per-node results, the compacted pairs and their pinned mirror
+  WsLease outer(h);
+  CU(outer.init());
+  Workspace* wo = outer.ws;
+  const uint64_t Bmax = n_rows < QB ? n_rows : QB;
+  const size_t o_self = 0, o_rows = align_up(o_self + Bmax * 4, 256), o_sc = align_up(o_rows + Bmax * kd * 4, 256),
+               o_di = align_up(o_sc + Bmax * kd * 4, 256), o_n = align_up(o_di + Bmax * kd * 4, 256),
+               o_tot = align_up(o_n + Bmax * 4, 256), o_off = align_up(o_tot + Bmax * 4, 256),
+               o_pairs = align_up(o_off + (Bmax + 1) * 4, 256);
+  const uint64_t pair_cap = std::min<uint64_t>(Bmax * kd, max_pairs ? max_pairs : 1);
+  const size_t dev_bytes = o_pairs + pair_cap * 12;
+  const size_t host_bytes = align_up(pair_cap * 12, 256) + align_up(Bmax * 4, 256) + 256;
+  CU(wo->ensure_aux(dev_bytes, host_bytes));
+  char* d = (char*)wo->aux;
+  char* hpin = (char*)wo->aux_h;
+  uint32_t* h_pairs = (uint32_t*)hpin;
+  uint32_t* h_tot = (uint32_t*)(hpin + align_up(pair_cap * 12, 256));
+  uint32_t* h_cnt = (uint32_t*)(hpin + align_up(pair_cap * 12, 256) + align_up(Bmax * 4, 256));
   for (uint64_t r0 = 0; r0 < n_rows; r0 += QB) {
     const uint64_t B = n_rows - r0 < QB ? n_rows - r0 : QB;
-    Plan pl = make_plan(h, B, h->dim, h->ld, kd, true, threshold);
-    if (!pl.thr_fast)
-      return fail(CX_ERR_VALIDATION,
-                  "dedup scan needs a threshold >= %.2f, at least 256 rows and no row whose norm under- or "
-                  "overflows fp32 (%u such rows)", THR_FAST_MIN, h->n_irregular());
-    WsLease lease(h);
-    CU(lease.init());
-    Workspace* ws = lease.ws;
-    SearchBufs sb;
-    const size_t dbytes = carve_bufs(nullptr, h, pl, 0, false, true, &sb) + align_up(B * 4, 256);
-    const ResultBlock rb = ResultBlock::make(B, kd);
-    CU(ws->ensure(dbytes, rb.total + align_up(B * 8, 256)));
-    const size_t used = carve_bufs(ws->d, h, pl, 0, false, true, &sb);
-    uint32_t* d_self = (uint32_t*)((char*)ws->d + used);
-    sb.dQ = h->dE + (size_t)r0 * h->ld;  // the rows are the queries
-    for (uint64_t i = 0; i < B; ++i) self[i] = (uint32_t)(r0 + i);
-    CU(cudaMemcpyAsync(d_self, self.data(), B * 4, cudaMemcpyHostToDevice, ws->stream));
-    PairScan tp;
-    tp.self_rows = d_self;
-    tp.upper_only = true;
-    tp.tile0 = (uint32_t)(r0 / 256);
-    char* h_block = (char*)ws->hp;
-    std::vector<uint64_t> totals(B, 0);
-    cx_status stt = run_search(h, ws, fh, sb, pl, true, threshold, h_block, nullptr, totals.data(), &tp);
+    launch_iota(reinterpret_cast<uint32_t*>(d + o_self), (uint32_t)B, (uint32_t)r0, wo->stream);
+    CU(cudaStreamSynchronize(wo->stream));
+    PairRules pr;
+    pr.d_self_rows = reinterpret_cast<uint32_t*>(d + o_self);
+    pr.self_base = (uint32_t)r0;
+    pr.upper_only = true;
+    pr.first_row = (uint32_t)r0;
+    cx_status stt = index_threshold_device(h, h->dE + (size_t)r0 * h->ld, h->dim, h->ld, B, threshold, nullptr, kd,
+                                           reinterpret_cast<uint32_t*>(d + o_rows), reinterpret_cast<float*>(d + o_sc),
+                                           reinterpret_cast<float*>(d + o_di), nullptr,
+                                           reinterpret_cast<uint32_t*>(d + o_n), reinterpret_cast<uint32_t*>(d + o_tot),
+                                           nullptr, &pr);
     if (stt != CX_OK) return stt;
-    h->d2h += rb.total;
-    const uint32_t* h_n = (const uint32_t*)(h_block + rb.n);
-    const uint32_t* h_rows = (const uint32_t*)(h_block + rb.rows);
-    const float* h_score = (const float*)(h_block + rb.score);
-    for (uint64_t i = 0; i < B; ++i) {
-      if (h->h_meta[r0 + i] & META_DEAD) continue;  // removed nodes search for nothing (dedup.rs:73-76)
-      n_tot += totals[i];
-      for (uint32_t j = 0; j < h_n[i] && n_out < max_pairs; ++j, ++n_out) {
-        memcpy(out_a_ids + 16 * n_out, h->h_ids.data() + 16 * (r0 + i), 16);
-        memcpy(out_b_ids + 16 * n_out, h->h_ids.data() + 16 * (size_t)h_rows[i * kd + j], 16);
-        out_score[n_out] = h_score[i * kd + j];
+    // removed nodes search for nothing (dedup.rs:73-76): their counts are zeroed by the compaction
+    const uint64_t room = max_pairs - n_out;
+    launch_compact_pairs(reinterpret_cast<uint32_t*>(d + o_rows), reinterpret_cast<float*>(d + o_sc),
+                         reinterpret_cast<uint32_t*>(d + o_n), reinterpret_cast<uint32_t*>(d + o_tot), h->dMeta,
+                         (uint32_t)r0, (uint32_t)B, kd, reinterpret_cast<uint32_t*>(d + o_off),
+                         reinterpret_cast<uint32_t*>(d + o_pairs), (uint32_t)std::min<uint64_t>(room, pair_cap),
+                         wo->stream);
+    h->launches += 3;
+    CU(cudaMemcpyAsync(h_cnt, d + o_off + B * 4, 4, cudaMemcpyDeviceToHost, wo->stream));
+    CU(cudaMemcpyAsync(h_tot, d + o_tot, B * 4, cudaMemcpyDeviceToHost, wo->stream));
+    CU(cudaStreamSynchronize(wo->stream));
+    const uint64_t got = std::min<uint64_t>(*h_cnt, std::min<uint64_t>(room, pair_cap));
+    for (uint64_t i = 0; i < B; ++i) n_tot += h_tot[i];  // already zero for removed nodes
+    if (got) {
+      CU(cudaMemcpyAsync(h_pairs, d + o_pairs, got * 12, cudaMemcpyDeviceToHost, wo->stream));
+      CU(cudaStreamSynchronize(wo->stream));
+      h->d2h += got * 12;
+      for (uint64_t j = 0; j < got; ++j, ++n_out) {
+        memcpy(out_a_ids + 16 * n_out, h->h_ids.data() + 16 * (size_t)h_pairs[3 * j], 16);
+        memcpy(out_b_ids + 16 * n_out, h->h_ids.data() + 16 * (size_t)h_pairs[3 * j + 1], 16);
+        memcpy(out_score + n_out, &h_pairs[3 * j + 2], 4);
       }
     }
+    h->d2h += B * 4 + 4;
   }
   *out_n = n_out;
   if (out_total) *out_total = n_tot;
@@ -824,15 +1047,18 @@ struct DeviceSearch {
 };
 
 // Shared by the one-call and the begin / end forms.  ticket == nullptr: run to completion.
-static cx_status device_search(cx_index* h, const float* d_queries, uint64_t B, uint64_t k, const cx_filter* filter,
-                               uint32_t* d_out_rows, float* d_out_score, float* d_out_distance, uint8_t* d_out_ids,
-                               uint32_t* d_out_n, void* stream, void** ticket) {
+cx_status cx::index_search_device(cx_index* h, const float* d_queries, uint32_t qlen, uint64_t B, uint64_t k,
+                                  const cx_filter* filter, uint32_t* d_out_rows, float* d_out_score,
+                                  float* d_out_distance, uint8_t* d_out_ids, uint32_t* d_out_n, void* stream,
+                                  void** ticket) {
   if (ticket) *ticket = nullptr;
   if (!h) return fail(CX_ERR_VALIDATION, "null index");
   if (!d_queries || !d_out_rows || !d_out_score || !d_out_distance || !d_out_n)
     return fail(CX_ERR_VALIDATION, "null device buffer");
   if (B == 0) return CX_OK;
   CU(cudaSetDevice(h->device));
+  cx_status sst = settle(h);
+  if (sst != CX_OK) return sst;
   cudaStream_t user = (cudaStream_t)stream;
   if (h->n_live == 0 || k == 0) {
     CU(cudaMemsetAsync(d_out_n, 0, B * 4, user));
@@ -840,13 +1066,13 @@ static cx_status device_search(cx_index* h, const float* d_queries, uint64_t B, 
   }
   if (k > h->n_rows) return fail(CX_ERR_VALIDATION, "device search needs k <= rows in the shard");
   const uint32_t kd = (uint32_t)k;
-  const uint32_t ldq = h->ld;
+  const uint32_t ldq = (uint32_t)align_up(qlen > h->ld ? qlen : h->ld, 4);
   std::unique_ptr<DeviceSearch> t(new DeviceSearch(h));
   build_filter(h, filter, &t->fh);
-  t->pl = make_plan(h, B, h->dim, ldq, kd, false);
+  t->pl = make_plan(h, B, qlen, ldq, kd, false);
   CU(t->lease.init());
   Workspace* ws = t->lease.ws;
-  const bool own_q = h->dim != h->ld;
+  const bool own_q = qlen != ldq;
   const size_t dbytes = carve_bufs(nullptr, h, t->pl, (uint32_t)t->fh.excl_rows.size(), own_q, false, &t->sb);
   CU(ws->ensure(dbytes, align_up(B * 4, 256)));
   carve_bufs(ws->d, h, t->pl, (uint32_t)t->fh.excl_rows.size(), own_q, false, &t->sb);
@@ -856,7 +1082,7 @@ static cx_status device_search(cx_index* h, const float* d_queries, uint64_t B, 
   CU(cudaStreamWaitEvent(ws->stream, ws->ev_sync, 0));
   if (own_q) {
     CU(cudaMemsetAsync(sb.dQ, 0, B * ldq * 4, ws->stream));
-    CU(cudaMemcpy2DAsync(sb.dQ, ldq * 4, d_queries, h->dim * 4, h->dim * 4, B, cudaMemcpyDeviceToDevice,
+    CU(cudaMemcpy2DAsync(sb.dQ, ldq * 4, d_queries, (size_t)qlen * 4, (size_t)qlen * 4, B, cudaMemcpyDeviceToDevice,
                          ws->stream));
   } else {
     sb.dQ = const_cast<float*>(d_queries);
@@ -866,9 +1092,34 @@ static cx_status device_search(cx_index* h, const float* d_queries, uint64_t B, 
   sb.dist = d_out_distance;
   sb.ids = d_out_ids;
   sb.n = d_out_n;
+  // identity of this call for graph replay: everything that shapes the kernels or their arguments
+  GraphKey gk;
+  {
+    const DevFilter& f = t->fh.dev;
+    uint64_t hs = 0xCBF29CE484222325ull;
+    hs = fnv(hs, f.kind_mask, sizeof f.kind_mask);
+    hs = fnv(hs, &f.agent, sizeof f.agent);
+    hs = fnv(hs, &f.has_kinds, sizeof f.has_kinds);
+    hs = fnv(hs, &f.has_agent, sizeof f.has_agent);
+    const uint64_t misc[10] = {(uint64_t)(uintptr_t)d_out_distance, (uint64_t)(uintptr_t)d_out_ids,
+                               (uint64_t)(uintptr_t)d_out_n,       (uint64_t)(uintptr_t)ws->hp,
+                               (uint64_t)h->force_path,            (uint64_t)h->tensor_min_batch,
+                               (uint64_t)h->tensor_phase_growth,   (uint64_t)h->profile,
+                               (uint64_t)(h->tensor_tune.pair * 64 + h->tensor_tune.epi_warps + 1024 * h->tensor_tune.debug),
+                               (uint64_t)t->fh.excl_rows.size()};
+    hs = fnv(hs, misc, sizeof misc);
+    gk.w[0] = B;
+    gk.w[1] = kd | ((uint64_t)qlen << 32);
+    gk.w[2] = h->n_rows;
+    gk.w[3] = h->n_live;
+    gk.w[4] = (uint64_t)(uintptr_t)d_queries;
+    gk.w[5] = (uint64_t)(uintptr_t)d_out_rows;
+    gk.w[6] = (uint64_t)(uintptr_t)d_out_score ^ ((uint64_t)(uintptr_t)ws->d << 1) ^ ((uint64_t)(uintptr_t)h->dE >> 3);
+    gk.w[7] = hs | 1ull;  // never all-zero (an empty key slot)
+  }
   const bool split = ticket != nullptr && t->pl.fast;
   cx_status st = run_search(h, ws, t->fh, sb, t->pl, false, 0.0f, nullptr, (uint32_t*)ws->hp, nullptr, nullptr,
-                            split ? RUN_ENQUEUE : RUN_ALL);
+                            split ? RUN_ENQUEUE : RUN_ALL, &gk);
   if (st == CX_PENDING) {
     // the caller's stream continues after the results (they are final unless _end reports retries)
     CU(cudaEventRecord(ws->ev_sync, ws->stream));
@@ -884,8 +1135,11 @@ extern "C" cx_status cx_search_batch_device(cx_index* h, const float* d_queries,
                                             const cx_filter* filter, uint32_t* d_out_rows, float* d_out_score,
                                             float* d_out_distance, uint8_t* d_out_ids, uint32_t* d_out_n,
                                             void* stream) {
-  return device_search(h, d_queries, B, k, filter, d_out_rows, d_out_score, d_out_distance, d_out_ids, d_out_n,
-                       stream, nullptr);
+  if (h && h->shards)
+    return shard_search_device(h, d_queries, B, k, filter, d_out_rows, d_out_score, d_out_distance, d_out_ids, d_out_n,
+                               stream, nullptr);
+  return index_search_device(h, d_queries, h ? h->dim : 0, B, k, filter, d_out_rows, d_out_score, d_out_distance,
+                             d_out_ids, d_out_n, stream, nullptr);
 }
 
 extern "C" cx_status cx_search_batch_device_begin(cx_index* h, const float* d_queries, uint64_t B, uint64_t k,
@@ -893,8 +1147,11 @@ extern "C" cx_status cx_search_batch_device_begin(cx_index* h, const float* d_qu
                                                   float* d_out_score, float* d_out_distance, uint8_t* d_out_ids,
                                                   uint32_t* d_out_n, void* stream, void** ticket) {
   if (!ticket) return fail(CX_ERR_VALIDATION, "null ticket");
-  return device_search(h, d_queries, B, k, filter, d_out_rows, d_out_score, d_out_distance, d_out_ids, d_out_n,
-                       stream, ticket);
+  if (h && h->shards)
+    return shard_search_device(h, d_queries, B, k, filter, d_out_rows, d_out_score, d_out_distance, d_out_ids, d_out_n,
+                               stream, ticket);
+  return index_search_device(h, d_queries, h ? h->dim : 0, B, k, filter, d_out_rows, d_out_score, d_out_distance,
+                             d_out_ids, d_out_n, stream, ticket);
 }
 
 extern "C" cx_status cx_search_ticket_ok(void* ticket, const uint32_t** d_ok) {
@@ -906,8 +1163,9 @@ extern "C" cx_status cx_search_ticket_ok(void* ticket, const uint32_t** d_ok) {
 extern "C" cx_status cx_search_batch_device_end(cx_index* h, void* ticket, uint64_t* n_redone) {
   if (n_redone) *n_redone = 0;
   if (!ticket) return CX_OK;  // _begin already ran the call to completion
-  std::unique_ptr<DeviceSearch> t((DeviceSearch*)ticket);
   if (!h) return fail(CX_ERR_VALIDATION, "null index");
+  if (h->shards) return shard_search_device_end(h, ticket, n_redone);
+  std::unique_ptr<DeviceSearch> t((DeviceSearch*)ticket);
   CU(cudaSetDevice(h->device));
   Workspace* ws = t->lease.ws;
   const uint64_t before = h->fallbacks.load();
@@ -930,6 +1188,8 @@ extern "C" cx_status cx_autolink_batch_device(cx_index* h, const float* d_embedd
                                               uint32_t* d_scratch_n, uint32_t* d_out_rows, float* d_out_score,
                                               uint8_t* d_out_ids, uint32_t* d_out_n, void* stream) {
   if (!h) return fail(CX_ERR_VALIDATION, "null index");
+  if (h->shards)
+    return fail(CX_ERR_VALIDATION, "cx_autolink_batch_device: use cx_autolink_batch on a multi-device index");
   if (!d_scratch_rows || !d_scratch_score || !d_scratch_distance || !d_scratch_n || !d_out_rows || !d_out_score ||
       !d_out_n)
     return fail(CX_ERR_VALIDATION, "null device buffer");
@@ -958,45 +1218,52 @@ extern "C" cx_status cx_autolink_batch(cx_index* h, const uint8_t* new_ids, cons
   if (len != h->dim)
     return fail(CX_ERR_VALIDATION, "Embedding dimension mismatch: expected %u, got %u", h->dim, len);
   for (uint64_t b = 0; b < B; ++b) out_n[b] = 0;
+  if (h->shards)
+    return shard_autolink_batch(h, new_ids, embeddings, B, k, threshold, max_edges_per_node, out_to_ids, out_score, out_n);
   if (!B || h->n_live == 0 || !max_edges_per_node || !k) return CX_OK;
   CU(cudaSetDevice(h->device));
+  cx_status sst = settle(h);
+  if (sst != CX_OK) return sst;
   const uint64_t kk = k < h->n_rows ? k : h->n_rows;
   const uint32_t me = max_edges_per_node;
-  std::vector<uint32_t> self(B, 0xFFFFFFFFu);
-  if (new_ids)
-    for (uint64_t b = 0; b < B; ++b) {
-      auto it = h->id2row.find(load_id(new_ids + 16 * b));
-      if (it != h->id2row.end()) self[b] = it->second;
-    }
-  // one device block for everything this call needs
+  // everything this call stages lives in a leased workspace (no allocation per call once warm)
+  WsLease outer(h);
+  CU(outer.init());
+  Workspace* wo = outer.ws;
   size_t off = 0;
   auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
   const size_t o_q = take(B * h->dim * 4), o_self = take(B * 4), o_rows = take(B * kk * 4), o_sc = take(B * kk * 4),
                o_di = take(B * kk * 4), o_n = take(B * 4), o_or = take(B * me * 4), o_os = take(B * me * 4),
                o_oi = take(B * me * 16), o_on = take(B * 4);
-  char* d = nullptr;
-  CU(cudaMalloc((void**)&d, off));
-  cudaStream_t s = h->mut_stream;  // not a mutation, but a stream this handle owns; callers serialise cycles
-  cx_status st = CX_OK;
-  do {
-    if (cudaMemcpyAsync(d + o_q, embeddings, B * h->dim * 4, cudaMemcpyHostToDevice, s) != cudaSuccess ||
-        cudaMemcpyAsync(d + o_self, self.data(), B * 4, cudaMemcpyHostToDevice, s) != cudaSuccess) {
-      st = fail(CX_ERR_CUDA, "upload failed in cx_autolink_batch");
-      break;
+  // pinned mirror: [self rows | out score | out ids | out n]
+  const size_t p_self = 0, p_os = align_up(p_self + B * 4, 256), p_oi = align_up(p_os + B * me * 4, 256),
+               p_on = align_up(p_oi + B * me * 16, 256), p_total = p_on + B * 4;
+  CU(wo->ensure_aux(off, p_total));
+  char* d = (char*)wo->aux;
+  char* hp = (char*)wo->aux_h;
+  uint32_t* self = (uint32_t*)(hp + p_self);
+  for (uint64_t b = 0; b < B; ++b) self[b] = 0xFFFFFFFFu;
+  if (new_ids)
+    for (uint64_t b = 0; b < B; ++b) {
+      auto it = h->id2row.find(load_id(new_ids + 16 * b));
+      if (it != h->id2row.end()) self[b] = it->second;
     }
-    st = cx_autolink_batch_device(h, (const float*)(d + o_q), B, kk, threshold, me, (const uint32_t*)(d + o_self),
-                                  (uint32_t*)(d + o_rows), (float*)(d + o_sc), (float*)(d + o_di),
-                                  (uint32_t*)(d + o_n), (uint32_t*)(d + o_or), (float*)(d + o_os),
-                                  (uint8_t*)(d + o_oi), (uint32_t*)(d + o_on), s);
-    if (st != CX_OK) break;
-    if (cudaMemcpyAsync(out_score, d + o_os, B * me * 4, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
-        cudaMemcpyAsync(out_to_ids, d + o_oi, B * me * 16, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
-        cudaMemcpyAsync(out_n, d + o_on, B * 4, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
-        cudaStreamSynchronize(s) != cudaSuccess)
-      st = fail(CX_ERR_CUDA, "download failed in cx_autolink_batch");
-  } while (0);
-  cudaFree(d);
+  cudaStream_t s = wo->stream;
+  CU(cudaMemcpyAsync(d + o_q, embeddings, B * h->dim * 4, cudaMemcpyHostToDevice, s));
+  CU(cudaMemcpyAsync(d + o_self, self, B * 4, cudaMemcpyHostToDevice, s));
+  cx_status st = cx_autolink_batch_device(h, (const float*)(d + o_q), B, kk, threshold, me, (const uint32_t*)(d + o_self),
+                                          (uint32_t*)(d + o_rows), (float*)(d + o_sc), (float*)(d + o_di),
+                                          (uint32_t*)(d + o_n), (uint32_t*)(d + o_or), (float*)(d + o_os),
+                                          (uint8_t*)(d + o_oi), (uint32_t*)(d + o_on), s);
+  if (st != CX_OK) return st;
+  CU(cudaMemcpyAsync(hp + p_os, d + o_os, B * me * 4, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(hp + p_oi, d + o_oi, B * me * 16, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(hp + p_on, d + o_on, B * 4, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  memcpy(out_score, hp + p_os, B * me * 4);
+  memcpy(out_to_ids, hp + p_oi, B * me * 16);
+  memcpy(out_n, hp + p_on, B * 4);
   h->h2d += B * h->dim * 4;
   h->d2h += B * me * 20 + B * 4;
-  return st;
+  return CX_OK;
 }

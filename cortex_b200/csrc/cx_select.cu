@@ -31,6 +31,7 @@ constexpr int SEL_MAX_KS = 256;
 constexpr uint32_t SEL_K2 = 1024;         // survivors that can be ordered
 constexpr uint32_t SEL_STAGE = 2048;      // radix-select staging words
 constexpr uint32_t SEL_RANK_MAX = 256;    // up to this many survivors are ordered by rank counting (no barriers)
+constexpr double SCORE_QUANTUM_MARGIN = 1.1920928955078125e-7;  // 2^-23: twice the score quantum below 0.5
 
 // rows per staging round: as many as fit 64 KB of shared memory, a power of two <= 32
 __host__ __device__ inline uint32_t select_batch(uint32_t ld) {
@@ -259,7 +260,7 @@ __global__ void __launch_bounds__(SEL_THREADS) select_rescore_kernel(const Selec
     rank_rows(KS, false);
     const float simk = s_simk;
     if (simk == simk) {
-      float band = simk - p.eps;                 // cosine units
+      float band = simk - p.eps - 2.0f * (float)SCORE_QUANTUM_MARGIN;  // cosine units; covers the verify margin
       if (p.scale_by_rqn) band = band * na;      // streaming-pass keys are cosine * |q|
       uint32_t KS1 = KS;
       while (KS1 < M && KS1 < (uint32_t)SEL_MAX_KS && float_from_ord(key_ord(keys[KS1])) >= band) ++KS1;
@@ -282,7 +283,11 @@ __global__ void __launch_bounds__(SEL_THREADS) select_rescore_kernel(const Selec
       else if (U != 0ull) {
         float u = float_from_ord(key_ord(U));
         if (p.scale_by_rqn) u = u * __frcp_rn(na);
-        ok = (sk > 0.0f) && (simk > u + p.eps);
+        // every row that was not rescored has a reference cosine <= u + eps.  Its SCORE must be strictly
+        // below score_k (an equal score with a lower row would sort ahead): 1 - (1 - sim) rounds sim to a
+        // multiple of 2^-24 at worst (index.rs:177,255), so two cosines more than 2^-23 apart can never
+        // produce the same score.  Summed in double so that the margin itself is not rounded away.
+        ok = (sk > 0.0f) && ((double)simk > (double)u + (double)p.eps + SCORE_QUANTUM_MARGIN);
       }
     }
     p.rv.ok[q] = ok ? 1u : 0u;
@@ -315,6 +320,8 @@ struct ThresholdParams {
   float threshold;
   const uint32_t* self_rows;  // optional [nq]: row to skip (the query's own row), 0xFFFFFFFF = none
   uint32_t upper_only;        // 1: keep only rows above self_rows[q] (unordered pairs, each once)
+  const uint64_t* q_seq;      // optional [nq] + row_seq [rows]: keep only rows with row_seq[row] > q_seq[q]
+  const uint64_t* row_seq;    //   (pair scans of a multi-device index: global insertion numbers)
   ResultView rv;         // k = output capacity per query; n = written; ok
   uint32_t* total;       // [nq] how many qualify
 };
@@ -359,6 +366,8 @@ __global__ void __launch_bounds__(THR_THREADS) threshold_rescore_kernel(const Th
   const uint32_t n_src = min(n_app, p.cap);
   const uint64_t* src = p.keys + (size_t)q * p.cap;
   const uint32_t self = p.self_rows ? p.self_rows[q] : 0xFFFFFFFFu;
+  const bool by_seq = p.q_seq != nullptr && p.row_seq != nullptr;
+  const uint64_t my_seq = by_seq ? p.q_seq[q] : 0ull;
   if (tid == 0) s_m = 0;
   for (uint32_t d = tid; d < ld; d += THR_THREADS) q_s[d] = d < p.qlen ? p.Q[(size_t)q * p.ldq + d] : 0.0f;
   __syncthreads();
@@ -384,7 +393,7 @@ __global__ void __launch_bounds__(THR_THREADS) threshold_rescore_kernel(const Th
     __syncthreads();
     if (tid < nb) {
       const uint32_t row = key_row(src[base + tid]);
-      const bool wanted = row != self && !(p.upper_only && row < self);
+      const bool wanted = by_seq ? __ldg(p.row_seq + row) > my_seq : (row != self && !(p.upper_only && row < self));
       if (wanted) {
         const float* r = stage + tid * sstride;
         const uint32_t n = p.qlen < dim ? p.qlen : dim;
@@ -423,7 +432,7 @@ __global__ void __launch_bounds__(THR_THREADS) threshold_rescore_kernel(const Th
   // a query whose norm under- / overflowed is not covered by the nominating pass's error bound: exact
   // path.  (In a pair scan the queries are rows of the index, all regular or all-zero there: an all-zero
   // row scores NaN against everything and simply has no partners.)
-  const bool q_regular = (na >= NORM_REGULAR_MIN && na <= NORM_REGULAR_MAX) || p.self_rows != nullptr;
+  const bool q_regular = (na >= NORM_REGULAR_MIN && na <= NORM_REGULAR_MAX) || p.self_rows != nullptr || by_seq;
   const bool ok = n_app <= p.cap && M <= THR_MAX && q_regular;
   if (ok && M) {
     // order (key, idx) by key descending: bitonic network over a power of two, padded with 0
@@ -476,9 +485,12 @@ __global__ void __launch_bounds__(THR_THREADS) threshold_rescore_kernel(const Th
 
 cudaError_t launch_threshold_rescore(const StoreView& st, const QueryView& qv, uint32_t q0, uint32_t nq,
                                      const CandView& cv, const ResultView& rv, uint32_t* total, float threshold,
-                                     const uint32_t* self_rows, bool upper_only, cudaStream_t s) {
+                                     const uint32_t* self_rows, bool upper_only, cudaStream_t s,
+                                     const uint64_t* q_seq, const uint64_t* row_seq) {
   if (!nq) return cudaSuccess;
   ThresholdParams p;
+  p.q_seq = q_seq ? q_seq + q0 : nullptr;
+  p.row_seq = row_seq;
   p.st = st;
   p.Q = qv.Q + (size_t)q0 * qv.ldq;
   p.qnorm = qv.qnorm + q0;

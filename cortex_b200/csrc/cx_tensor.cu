@@ -707,9 +707,6 @@ uint32_t tensor_sample_tiles(uint32_t n_rows, uint32_t nq) {
   return want < n_tiles ? want : n_tiles;
 }
 
-static int g_tensor_epi_warps = 8;  // epilogue warps per CTA (8 or 16; measured equal within noise)
-void tensor_set_epi_warps(int n) { g_tensor_epi_warps = n == 8 ? 8 : 16; }
-
 template <int EW, bool QRES>
 static cudaError_t launch_kernel(bool pair, uint32_t units, size_t smem, cudaStream_t s, const CUtensorMap& tmQ,
                                  const CUtensorMap& tmE, const TensorParams& p) {
@@ -739,28 +736,23 @@ static cudaError_t launch_kernel(bool pair, uint32_t units, size_t smem, cudaStr
   return cudaLaunchKernelEx(&cfg, tensor_scan_kernel<true, EW, QRES>, tmQ, tmE, p);
 }
 
-static int g_tensor_pair = 0;  // 1 = two or more query tiles run as CTA pairs (cta_group::2); measured slower so far
-static int g_tensor_debug = 0; // measurement hook, see TensorParams::debug
-void tensor_set_pair(int on) { g_tensor_pair = on; }
-void tensor_set_debug(int mode) {
-  if (mode == -1) {  // report the effective SM clock of block 0 in the last debug-mode launch
-    unsigned long long c[2] = {0, 0};
-    cudaDeviceSynchronize();
-    if (cudaMemcpyFromSymbol(c, g_tensor_clock, sizeof c) == cudaSuccess && c[1])
-      fprintf(stderr, "[cortex_gpu] tensor_scan block 0: %llu cycles in %llu ns = %.0f MHz\n", c[0], c[1],
-              1e3 * (double)c[0] / (double)c[1]);
-    return;
-  }
-  g_tensor_debug = mode;
+// probe builds: report the effective SM clock of block 0 in the last debug-mode launch
+void tensor_report_clock() {
+  unsigned long long c[2] = {0, 0};
+  cudaDeviceSynchronize();
+  if (cudaMemcpyFromSymbol(c, g_tensor_clock, sizeof c) == cudaSuccess && c[1])
+    fprintf(stderr, "[cortex_gpu] tensor_scan block 0: %llu cycles in %llu ns = %.0f MHz\n", c[0], c[1],
+            1e3 * (double)c[0] / (double)c[1]);
 }
 
 static cudaError_t launch_mode(const StoreView& st, const void* Q16, uint32_t q0, uint32_t nq, const DevFilter& flt,
                                bool check_rows, const CandView& cv, uint64_t* lists, float* dump, uint32_t n_slots,
-                               uint32_t tile0, uint32_t mode, int sm_count, cudaStream_t s, bool static_tau = false) {
+                               uint32_t tile0, uint32_t mode, int sm_count, cudaStream_t s, const TensorTuning& tune,
+                               bool static_tau = false) {
   const uint32_t n_tiles_q = (nq + TC_BM - 1) / TC_BM;
   if (n_tiles_q > (uint32_t)sm_count) return cudaErrorInvalidValue;  // caller splits larger batches
   // two or more query tiles: CTA pairs (each pair = two query tiles walking the same rows)
-  const bool pair = g_tensor_pair && n_tiles_q >= 2 && sm_count >= 2;
+  const bool pair = tune.pair && n_tiles_q >= 2 && sm_count >= 2;
   uint32_t n_qt, n_es;  // query-tile groups (tiles, or pairs of tiles) x row splits
   if (pair) {
     n_qt = (n_tiles_q + 1) / 2;
@@ -786,7 +778,11 @@ static cudaError_t launch_mode(const StoreView& st, const void* Q16, uint32_t q0
   if (!p.stages) return cudaErrorInvalidConfiguration;
   p.mode = mode;
   p.check_rows = check_rows ? 1u : 0u;
-  p.debug = mode == TC_MODE_SCAN ? (uint32_t)g_tensor_debug : 0u;
+#ifdef CX_PROBE
+  p.debug = mode == TC_MODE_SCAN ? (uint32_t)tune.debug : 0u;
+#else
+  p.debug = 0u;  // the measurement hook exists in probe builds only
+#endif
   p.static_tau = static_tau ? 1u : 0u;
   p.KP = cv.KP;
   p.meta = st.meta;
@@ -805,18 +801,18 @@ static cudaError_t launch_mode(const StoreView& st, const void* Q16, uint32_t q0
   if (!encode_2d(&tmQ, qbase, st.ld16, (uint64_t)n_tiles_q * TC_BM, TC_BM)) return cudaErrorInvalidValue;
   if (!encode_2d(&tmE, st.E16, st.ld16, st.n_rows, pair ? TC_BN / 2 : TC_BN)) return cudaErrorInvalidValue;
   if (!tensor_q_resident(p.n_kc)) return launch_kernel<8, false>(pair, n_qt * n_es, smem, s, tmQ, tmE, p);
-  return g_tensor_epi_warps == 8 ? launch_kernel<8, true>(pair, n_qt * n_es, smem, s, tmQ, tmE, p)
-                                 : launch_kernel<16, true>(pair, n_qt * n_es, smem, s, tmQ, tmE, p);
+  return tune.epi_warps == 8 ? launch_kernel<8, true>(pair, n_qt * n_es, smem, s, tmQ, tmE, p)
+                             : launch_kernel<16, true>(pair, n_qt * n_es, smem, s, tmQ, tmE, p);
 }
 
 // Bootstrap: sample scores -> per-query cut-off in cv.gtau[q0 .. q0+nq).  dump holds
 // nq * n_slots * 256 floats.
 cudaError_t launch_tensor_bootstrap(const StoreView& st, const void* Q16, uint32_t q0, uint32_t nq,
                                     const DevFilter& flt, bool check_rows, const CandView& cv, float* dump,
-                                    uint32_t n_slots, int sm_count, cudaStream_t s) {
+                                    uint32_t n_slots, int sm_count, cudaStream_t s, const TensorTuning& tune) {
   if (!nq || !st.n_rows || !n_slots) return cudaSuccess;
   cudaError_t e =
-      launch_mode(st, Q16, q0, nq, flt, check_rows, cv, nullptr, dump, n_slots, 0, TC_MODE_DUMP, sm_count, s);
+      launch_mode(st, Q16, q0, nq, flt, check_rows, cv, nullptr, dump, n_slots, 0, TC_MODE_DUMP, sm_count, s, tune);
   if (e != cudaSuccess) return e;
   tau_select_kernel<<<nq, 256, 0, s>>>(dump, n_slots * TC_BN, cv.KP, cv.gtau + q0);
   return cudaGetLastError();
@@ -824,10 +820,11 @@ cudaError_t launch_tensor_bootstrap(const StoreView& st, const void* Q16, uint32
 
 cudaError_t launch_tensor_scan(const StoreView& st, const void* Q16, uint32_t q0, uint32_t nq,
                                const DevFilter& flt, bool check_rows, const CandView& cv, uint64_t* lists,
-                               uint32_t tile0, uint32_t n_tiles, int sm_count, cudaStream_t s, bool static_tau) {
+                               uint32_t tile0, uint32_t n_tiles, int sm_count, cudaStream_t s, const TensorTuning& tune,
+                               bool static_tau) {
   if (!nq || !st.n_rows || !n_tiles) return cudaSuccess;
   return launch_mode(st, Q16, q0, nq, flt, check_rows, cv, lists, nullptr, n_tiles, tile0, TC_MODE_SCAN, sm_count, s,
-                     static_tau);
+                     tune, static_tau);
 }
 
 // gtau[q] = the largest key below every key whose approximate cosine is thr_cos or more

@@ -77,7 +77,17 @@ class GpuVectorIndex final : public VectorIndex {
   explicit GpuVectorIndex(size_t dimension, int device = 0) {
     check(cx_index_create((uint32_t)dimension, device, &h_));
   }
+  // one index row-sharded over several GPUs of the box, driven from this process
+  GpuVectorIndex(size_t dimension, const std::vector<int>& devices) {
+    check(cx_index_create_sharded((uint32_t)dimension, devices.data(), (uint32_t)devices.size(), &h_));
+  }
   static GpuVectorIndex with_metadata(size_t dimension) { return GpuVectorIndex(dimension); }
+  static GpuVectorIndex load(const std::string& path, const std::vector<int>& devices) {
+    cx_index* h = nullptr;
+    check(cx_load_sharded(path.c_str(), devices.data(), (uint32_t)devices.size(), &h));
+    return GpuVectorIndex(h);
+  }
+  size_t shard_count() const { return cx_shard_count(h_); }
   static GpuVectorIndex load(const std::string& path, int device = 0) {
     cx_index* h = nullptr;
     check(cx_load(path.c_str(), device, &h));
@@ -126,16 +136,26 @@ class GpuVectorIndex final : public VectorIndex {
       const VectorFilter* f = nullptr) const override {
     std::unordered_map<NodeId, std::vector<SimilarityResult>, NodeIdHash> out;
     if (queries.empty()) return out;
-    const size_t B = queries.size(), dim = queries[0].second.size();
-    std::vector<float> flat(B * dim);
-    for (size_t b = 0; b < B; ++b) std::copy(queries[b].second.begin(), queries[b].second.end(), flat.begin() + b * dim);
-    std::vector<uint8_t> ids(16 * B * k);
-    std::vector<float> sc(B * k), di(B * k);
-    std::vector<uint64_t> n(B);
+    // the reference searches every query on its own (index.rs:397-403), so lengths may differ: one call
+    // per distinct length (normally exactly one), each over a flat buffer of that stride
+    k = std::max<size_t>(1, std::min(k, std::max<size_t>(1, len())));
+    std::unordered_map<size_t, std::vector<size_t>> by_len;
+    for (size_t i = 0; i < queries.size(); ++i) by_len[queries[i].second.size()].push_back(i);
     CFilter cf(f);
-    check(cx_search_batch(h_, flat.data(), B, (uint32_t)dim, k, cf.ptr(), ids.data(), sc.data(), di.data(), n.data()));
-    for (size_t b = 0; b < B; ++b)
-      out[queries[b].first] = collect(ids.data() + 16 * b * k, sc.data() + b * k, di.data() + b * k, n[b]);
+    for (auto& g : by_len) {
+      const size_t dim = g.first, B = g.second.size();
+      std::vector<float> flat(B * dim);
+      for (size_t b = 0; b < B; ++b) {
+        const Embedding& e = queries[g.second[b]].second;
+        std::copy(e.begin(), e.end(), flat.begin() + b * dim);
+      }
+      std::vector<uint8_t> ids(16 * B * k);
+      std::vector<float> sc(B * k), di(B * k);
+      std::vector<uint64_t> n(B);
+      check(cx_search_batch(h_, flat.data(), B, (uint32_t)dim, k, cf.ptr(), ids.data(), sc.data(), di.data(), n.data()));
+      for (size_t b = 0; b < B; ++b)
+        out[queries[g.second[b]].first] = collect(ids.data() + 16 * b * k, sc.data() + b * k, di.data() + b * k, n[b]);
+    }
     return out;
   }
   // The similarity step of DedupScanner::scan (linker/dedup.rs:65-127) as one self-join: every unordered

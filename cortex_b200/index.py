@@ -116,16 +116,30 @@ def _id16(node_id) -> np.ndarray:
 class GpuVectorIndex:
     """B200-resident exact-scan index behind the reference's VectorIndex surface."""
 
-    def __init__(self, dimension: int, device: int = 0, _handle: Optional[int] = None):
+    def __init__(self, dimension: int, device: int = 0, _handle: Optional[int] = None,
+                 devices: Optional[Sequence[int]] = None):
+        """device: one CUDA ordinal.  devices: a list of ordinals -- the index is row-sharded over them and
+        driven from this process (cx_index_create_sharded); queries / results of the device-resident calls
+        then live on devices[0]."""
         self._L = _capi.load()
         self.dimension = int(dimension)
-        self.device = device
-        if _handle is None:
+        self.devices = list(devices) if devices is not None else None
+        self.device = self.devices[0] if self.devices else device
+        if _handle is not None:
+            self._h = C.c_void_p(_handle)
+        elif self.devices is not None:
+            h = C.c_void_p()
+            arr = (C.c_int * len(self.devices))(*self.devices)
+            _check(self._L.cx_index_create_sharded(self.dimension, arr, len(self.devices), C.byref(h)))
+            self._h = h
+        else:
             h = C.c_void_p()
             _check(self._L.cx_index_create(self.dimension, device, C.byref(h)))
             self._h = h
-        else:
-            self._h = C.c_void_p(_handle)
+
+    @property
+    def shard_count(self) -> int:
+        return int(self._L.cx_shard_count(self._h))
 
     # HnswIndex::with_metadata (index.rs:214-216) is an alias of new()
     @classmethod
@@ -280,9 +294,10 @@ class GpuVectorIndex:
         return out
 
     def search_batch_device(self, d_queries, k: int, filter: Optional[VectorFilter] = None, stream: int = 0,
-                            out=None):
+                            out=None, ids_out=None):
         """Queries and results stay in HBM.  d_queries: torch.float32 CUDA tensor [B, dim].
-        Returns (rows int32 [B,k], score [B,k], distance [B,k], n int32 [B]) CUDA tensors."""
+        Returns (rows int32 [B,k], score [B,k], distance [B,k], n int32 [B]) CUDA tensors.
+        ids_out (optional): uint8 CUDA tensor [B,k,16] that receives the node ids."""
         import torch
 
         assert d_queries.is_cuda and d_queries.dtype == torch.float32 and d_queries.is_contiguous()
@@ -296,12 +311,13 @@ class GpuVectorIndex:
         rows, sc, di, n = out
         cf = _c_filter(filter)
         _check(self._L.cx_search_batch_device(self._h, d_queries.data_ptr(), B, int(k), cf.ptr if cf else None,
-                                              rows.data_ptr(), sc.data_ptr(), di.data_ptr(), None,
+                                              rows.data_ptr(), sc.data_ptr(), di.data_ptr(),
+                                              ids_out.data_ptr() if ids_out is not None else None,
                                               n.data_ptr(), C.c_void_p(stream)))
         return out
 
     def search_batch_device_begin(self, d_queries, k: int, filter: Optional[VectorFilter] = None, stream: int = 0,
-                                  out=None):
+                                  out=None, ids_out=None):
         """Enqueue a device-resident search without waiting (cx_search_batch_device_begin).  Returns
         (out, ticket): `stream` is ordered after the results; call search_batch_device_end(ticket)
         before the next mutation -- it reports how many queries had to be redone."""
@@ -319,7 +335,8 @@ class GpuVectorIndex:
         cf = _c_filter(filter)
         ticket = C.c_void_p()
         _check(self._L.cx_search_batch_device_begin(self._h, d_queries.data_ptr(), B, int(k), cf.ptr if cf else None,
-                                                    rows.data_ptr(), sc.data_ptr(), di.data_ptr(), None,
+                                                    rows.data_ptr(), sc.data_ptr(), di.data_ptr(),
+                                                    ids_out.data_ptr() if ids_out is not None else None,
                                                     n.data_ptr(), C.c_void_p(stream), C.byref(ticket)))
         return out, ticket
 
@@ -376,12 +393,16 @@ class GpuVectorIndex:
         _check(self._L.cx_save(self._h, str(path).encode()))
 
     @classmethod
-    def load(cls, path: str, device: int = 0) -> "GpuVectorIndex":
+    def load(cls, path: str, device: int = 0, devices: Optional[Sequence[int]] = None) -> "GpuVectorIndex":
         L = _capi.load()
         h = C.c_void_p()
-        _check(L.cx_load(str(path).encode(), device, C.byref(h)))
+        if devices is not None:
+            arr = (C.c_int * len(devices))(*devices)
+            _check(L.cx_load_sharded(str(path).encode(), arr, len(devices), C.byref(h)))
+        else:
+            _check(L.cx_load(str(path).encode(), device, C.byref(h)))
         dim = int(L.cx_dimension(h))
-        return cls(dim, device, _handle=h.value)
+        return cls(dim, device, _handle=h.value, devices=devices)
 
     # ---- instrumentation ------------------------------------------------------
     def stats(self) -> dict:

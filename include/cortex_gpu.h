@@ -66,10 +66,26 @@ typedef struct cx_stats {
   uint64_t d2h_bytes;
   uint64_t pass_kernel_ns;      /* with option "profile"=1: CUDA-event time of the scan-pass kernels */
   uint64_t pass_kernel_launches;/* ... and how many of them that time covers */
+  uint64_t graph_launches;      /* device-resident searches replayed as one CUDA graph launch */
+  uint64_t grow_events;         /* times the store was extended (in place: no copy) */
+  uint64_t irregular_rows;      /* live rows whose norm under- / overflows fp32: while > 0 every search takes the exact path */
+  uint64_t capacity_rows;       /* rows the mapped store can hold before it is extended again */
+  uint64_t in_place_growth;     /* 1 = the store grows in place (driver virtual-memory API), 0 = allocate-copy-free */
 } cx_stats;
 
 /* HnswIndex::new(dimension), index.rs:204-211.  device = CUDA ordinal. */
 cx_status cx_index_create(uint32_t dimension, int device, cx_index** out);
+/* The same index row-sharded over n_devices GPUs of one box, driven from this one process.
+ * The handle is used with every function below exactly like a single-device one: inserts are
+ * distributed so that the shards stay balanced, search / search_threshold / search_batch /
+ * autolink_batch / dedup_scan fan out to every device on its own streams and the per-device lists
+ * are merged on devices[0] (written there over NVLink by the producing GPUs).  Results, including the order
+ * of equal scores (global insertion order), are identical to a single-device index holding the same
+ * rows.  A device may be listed more than once (several shards on one GPU: how the single-GPU tests
+ * exercise this path). */
+cx_status cx_index_create_sharded(uint32_t dimension, const int* devices, uint32_t n_devices, cx_index** out);
+/* number of shards behind a handle (1 for cx_index_create) */
+uint32_t cx_shard_count(const cx_index* h);
 void cx_index_destroy(cx_index* h);
 
 /* VectorIndex::insert, index.rs:298-314.  len != dimension -> CX_ERR_VALIDATION
@@ -77,8 +93,9 @@ void cx_index_destroy(cx_index* h);
 cx_status cx_insert(cx_index* h, const uint8_t id[16], const float* embedding, uint32_t len);
 /* Bulk form of the startup loop serve.rs:111-117 / api.rs:55-69: n rows, row-major. */
 cx_status cx_insert_batch(cx_index* h, const uint8_t* ids, const float* rows, uint64_t n, uint32_t len);
-/* Same, for rows already resident in device memory ([n][len] f32, row-major); append only
- * (every id must be new).  ids stay host-side. */
+/* Same, for rows already resident in device memory ([n][len] f32, row-major; for a multi-device index:
+ * in the memory of devices[0]).  ids stay host-side.  Synchronises the device first (the buffer may
+ * have been produced on any stream). */
 cx_status cx_insert_batch_device(cx_index* h, const uint8_t* ids, const float* d_rows, uint64_t n, uint32_t len);
 /* VectorIndex::remove, index.rs:316-323.  Unknown id is not an error. */
 cx_status cx_remove(cx_index* h, const uint8_t id[16]);
@@ -88,10 +105,14 @@ cx_status cx_set_metadata(cx_index* h, const uint8_t id[16], const char* kind, c
 uint64_t cx_len(const cx_index* h);
 uint32_t cx_dimension(const cx_index* h);
 /* VectorIndex::rebuild, index.rs:416-435: there is no graph to build; this
- * compacts removed rows out of the device matrix (order preserving). */
+ * compacts removed rows out of the device matrix (order preserving, in place). */
 cx_status cx_rebuild(cx_index* h);
-/* Reserve capacity for n rows up front (no reference counterpart). */
+/* Map capacity for n rows up front (no reference counterpart; optional: the store grows in place). */
 cx_status cx_reserve(cx_index* h, uint64_t n_rows);
+
+/* insert / remove / set_metadata / rebuild enqueue their device work and return; the next search (or
+ * mutation, save, stats) on the handle waits for it.  All of them keep the host-side state unchanged
+ * when they fail. */
 
 /* VectorIndex::search, index.rs:325-374 (exact scan semantics of :259-294).
  * Outputs hold up to k entries; *out_n = number written.  qlen may differ from
@@ -114,7 +135,12 @@ cx_status cx_search_threshold_batch(cx_index* h, const float* queries, uint64_t 
  * once.  At most per_node_cap partners per node and max_pairs pairs are written (a-id, b-id,
  * score), ordered by (insertion order of a, score desc, insertion order of b) with a inserted
  * before b; *out_total = pairs that qualify.  Choosing merge / supersede / link for a pair
- * (determine_action, :130-171) needs graph degrees and stays with the caller. */
+ * (determine_action, :130-171) needs graph degrees and stays with the caller.
+ * Like the reference it always succeeds: the tcgen05 self-join serves thresholds >= 0.2 on indexes of
+ * 256+ regular rows; a node with more than 2 048 near-threshold partners (a large duplicate cluster),
+ * lower thresholds, tiny indexes and indexes holding rows with under- / overflowing norms are served
+ * per node by the exact path (reference arithmetic over every row + sort: correct, but milliseconds
+ * per node at a million rows).  Pairs are compacted on the device: the copy back is 12 bytes per pair. */
 cx_status cx_dedup_scan(cx_index* h, float threshold, uint32_t per_node_cap, uint64_t max_pairs,
                         uint8_t* out_a_ids, uint8_t* out_b_ids, float* out_score, uint64_t* out_n,
                         uint64_t* out_total);
@@ -190,20 +216,22 @@ cx_status cx_search_ticket_ok(void* ticket, const uint32_t** d_ok);
  * (HashMap<Uuid,Vec<f32>>, HashMap<Uuid,NodeMetadata>, usize). */
 cx_status cx_save(const cx_index* h, const char* path);
 cx_status cx_load(const char* path, int device, cx_index** out);
+cx_status cx_load_sharded(const char* path, const int* devices, uint32_t n_devices, cx_index** out);
 
 /* id of shard-local row r (16 bytes) -- used when merging device results */
 cx_status cx_row_id(const cx_index* h, uint32_t row, uint8_t out_id[16]);
 
 cx_status cx_get_stats(const cx_index* h, cx_stats* out);
-/* Tuning / test hooks.  Per index: "force_path" 0 auto, 1 stream (K1), 2 tensor (K2), 3 exact;
- * "tensor_min_batch" smallest query batch the tensor pass serves (default 5); "tensor_phase_growth"
- * growth factor of the scan phases (0/1 = one phase, default auto); "shadow" 0 = keep no bf16
- * copy (disables the tensor pass; before the first insert); "profile" 1 = bracket the scan-pass
- * kernels with CUDA events on their stream (cx_get_stats: pass_kernel_ns); "blocking_sync" 1 = search
- * calls sleep on an event instead of spinning while the GPU works.  Process-wide measurement hooks of
- * the tensor pass: "tensor_pair" 1 = CTA-pair (cta_group::2) form, "tensor_epi_warps" 8 | 16,
- * "tensor_debug" (results become wrong: 1 no epilogue work, 2 no hit handling, 4 no E traffic,
- * -1 print the effective SM clock of the last launch). */
+/* Tuning / test hooks, all per index; set them while no search is running on the handle.
+ * "force_path" 0 auto, 1 stream (K1), 2 tensor (K2), 3 exact; "tensor_min_batch" smallest query batch
+ * the tensor pass serves (default 5); "tensor_phase_growth" growth factor of the scan phases (0/1 = one
+ * phase, default auto); "shadow" 0 = keep no bf16 copy (disables the tensor pass; before the first
+ * insert); "profile" 1 = bracket the scan-pass kernels (bootstrap included) with CUDA events on their
+ * stream (cx_get_stats: pass_kernel_ns); "blocking_sync" 1 = search calls sleep on an event instead of
+ * spinning while the GPU works; "graphs" 0 = never replay repeated device-resident search shapes as a
+ * CUDA graph; "tensor_pair" 1 = CTA-pair (cta_group::2) form of the tensor pass; "tensor_epi_warps"
+ * 8 | 16.  Every option leaves results identical.  (The result-corrupting measurement hook
+ * "tensor_debug" exists only in -DCX_PROBE builds made by scripts/k2_probe.py, not in this library.) */
 cx_status cx_set_option(cx_index* h, const char* key, int64_t value);
 
 /* Test hook, needs no device: the tensor pass's launch plan -- queries per launch

@@ -29,12 +29,19 @@ pub struct cx_stats {
     pub d2h_bytes: u64,
     pub pass_kernel_ns: u64,
     pub pass_kernel_launches: u64,
+    pub graph_launches: u64,
+    pub grow_events: u64,
+    pub irregular_rows: u64,
+    pub capacity_rows: u64,
+    pub in_place_growth: u64,
 }
 
 pub const CX_OK: c_int = 0;
 
 extern "C" {
     pub fn cx_index_create(dimension: u32, device: c_int, out: *mut *mut cx_index) -> c_int;
+    pub fn cx_index_create_sharded(dimension: u32, devices: *const c_int, n_devices: u32, out: *mut *mut cx_index) -> c_int;
+    pub fn cx_shard_count(h: *const cx_index) -> u32;
     pub fn cx_index_destroy(h: *mut cx_index);
     pub fn cx_insert(h: *mut cx_index, id: *const u8, embedding: *const f32, len: u32) -> c_int;
     pub fn cx_insert_batch(h: *mut cx_index, ids: *const u8, rows: *const f32, n: u64, len: u32) -> c_int;
@@ -87,6 +94,7 @@ extern "C" {
                                 hits_per_kp: *mut f64) -> c_int;
     pub fn cx_save(h: *const cx_index, path: *const c_char) -> c_int;
     pub fn cx_load(path: *const c_char, device: c_int, out: *mut *mut cx_index) -> c_int;
+    pub fn cx_load_sharded(path: *const c_char, devices: *const c_int, n_devices: u32, out: *mut *mut cx_index) -> c_int;
     pub fn cx_row_id(h: *const cx_index, row: u32, out_id: *mut u8) -> c_int;
     pub fn cx_get_stats(h: *const cx_index, out: *mut cx_stats) -> c_int;
     pub fn cx_set_option(h: *mut cx_index, key: *const c_char, value: i64) -> c_int;

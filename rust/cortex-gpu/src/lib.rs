@@ -80,6 +80,11 @@ impl GpuVectorIndex {
             return Ok(Vec::new());
         }
         let (b, dim, me) = (nodes.len(), nodes[0].1.len(), max_edges as usize);
+        if let Some((_, e)) = nodes.iter().find(|(_, e)| e.len() != dim) {
+            // the flat buffer below has one stride: refuse mixed lengths instead of reading past it
+            return Err(CortexError::Validation(format!(
+                "Embedding dimension mismatch: expected {}, got {}", dim, e.len())));
+        }
         let ids: Vec<u8> = nodes.iter().flat_map(|(id, _)| id.as_bytes().to_vec()).collect();
         let flat: Vec<f32> = nodes.iter().flat_map(|(_, e)| e.iter().copied()).collect();
         let (mut to, mut sc, mut n) = (vec![0u8; 16 * b * me], vec![0f32; b * me], vec![0u32; b]);
@@ -101,6 +106,22 @@ impl GpuVectorIndex {
         let mut h = ptr::null_mut();
         check(unsafe { sys::cx_index_create(dimension as u32, device, &mut h) })?;
         Ok(Self { h })
+    }
+    /// One index row-sharded over several GPUs of the box, driven from this process: the same
+    /// `VectorIndex` object (`Arc<RwLock<GpuVectorIndex>>`, serve.rs:101) then spans all of them.
+    pub fn on_devices(dimension: usize, devices: &[i32]) -> Result<Self> {
+        let mut h = ptr::null_mut();
+        check(unsafe { sys::cx_index_create_sharded(dimension as u32, devices.as_ptr(), devices.len() as u32, &mut h) })?;
+        Ok(Self { h })
+    }
+    pub fn load_on_devices(path: &Path, devices: &[i32]) -> Result<Self> {
+        let p = CString::new(path.to_string_lossy().as_bytes()).unwrap();
+        let mut h = ptr::null_mut();
+        check(unsafe { sys::cx_load_sharded(p.as_ptr(), devices.as_ptr(), devices.len() as u32, &mut h) })?;
+        Ok(Self { h })
+    }
+    pub fn shard_count(&self) -> usize {
+        unsafe { sys::cx_shard_count(self.h) as usize }
     }
     /// HnswIndex::set_metadata, index.rs:219-222
     pub fn set_metadata(&mut self, id: NodeId, kind: NodeKind, source_agent: String) {
@@ -171,20 +192,29 @@ impl VectorIndex for GpuVectorIndex {
         if queries.is_empty() {
             return Ok(HashMap::new());
         }
-        let (b, dim) = (queries.len(), queries[0].1.len());
-        let flat: Vec<f32> = queries.iter().flat_map(|(_, e)| e.iter().copied()).collect();
-        let (mut ids, mut sc, mut di, mut n) =
-            (vec![0u8; 16 * b * k], vec![0f32; b * k], vec![0f32; b * k], vec![0u64; b]);
+        // the reference searches every query on its own (index.rs:397-403), so lengths may differ:
+        // one call per distinct length (normally exactly one), each over a flat buffer of that stride
+        let k = k.min(self.len()).max(1);
+        let mut by_len: HashMap<usize, Vec<usize>> = HashMap::new();
+        for (i, (_, e)) in queries.iter().enumerate() {
+            by_len.entry(e.len()).or_default().push(i);
+        }
         let cf = filter.map(c_filter);
-        check(unsafe {
-            sys::cx_search_batch(self.h, flat.as_ptr(), b as u64, dim as u32, k as u64,
-                                 cf.as_ref().map_or(ptr::null(), |c| &c.raw), ids.as_mut_ptr(),
-                                 sc.as_mut_ptr(), di.as_mut_ptr(), n.as_mut_ptr())
-        })?;
-        let mut map = HashMap::with_capacity(b);
-        for (i, (qid, _)) in queries.iter().enumerate() {
-            let r = Self::collect(&ids[16 * i * k..], &sc[i * k..], &di[i * k..], n[i] as usize);
-            map.insert(*qid, r);
+        let mut map = HashMap::with_capacity(queries.len());
+        for (dim, idx) in by_len {
+            let b = idx.len();
+            let flat: Vec<f32> = idx.iter().flat_map(|&i| queries[i].1.iter().copied()).collect();
+            let (mut ids, mut sc, mut di, mut n) =
+                (vec![0u8; 16 * b * k], vec![0f32; b * k], vec![0f32; b * k], vec![0u64; b]);
+            check(unsafe {
+                sys::cx_search_batch(self.h, flat.as_ptr(), b as u64, dim as u32, k as u64,
+                                     cf.as_ref().map_or(ptr::null(), |c| &c.raw), ids.as_mut_ptr(),
+                                     sc.as_mut_ptr(), di.as_mut_ptr(), n.as_mut_ptr())
+            })?;
+            for (j, &i) in idx.iter().enumerate() {
+                let r = Self::collect(&ids[16 * j * k..], &sc[j * k..], &di[j * k..], n[j] as usize);
+                map.insert(queries[i].0, r);
+            }
         }
         Ok(map)
     }

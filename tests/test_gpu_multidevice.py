@@ -1,0 +1,203 @@
+"""One index row-sharded over several devices behind the C ABI (cx_index_create_sharded), against the
+CPU oracle holding the same rows in ONE index: ids, score bits and the order of equal scores must be
+identical whatever the number of shards.  On a single-GPU box the shards are simulated by listing
+device 0 several times (same code path: per-shard streams, pack into the merge buffer, merge kernel);
+with two or more GPUs the real devices are used as well."""
+import os
+
+import numpy as np
+import pytest
+
+from cortex_b200 import GpuVectorIndex, SimilarityConfig, VectorFilter, synth
+from oracle.binding import Filter, OracleIndex
+
+from _util import assert_batch_equal, assert_dedup_equal, build_pair, check_threshold_batch, same_bits
+
+pytestmark = pytest.mark.gpu
+
+
+def device_sets():
+    import torch
+
+    sets = [[0, 0, 0], [0, 0, 0, 0, 0, 0, 0, 0]]
+    n = torch.cuda.device_count()
+    if n >= 2:
+        sets.append(list(range(min(n, 8))))
+    return sets
+
+
+@pytest.mark.parametrize("devs", device_sets(), ids=lambda d: "x".join(map(str, d)))
+def test_sharded_topk_matches_single_index_oracle(devs):
+    corpus = synth.make_corpus(30_000, 384, zero_row=True, dup_frac=0.03, seed=91)
+    g, o, ids = build_pair(corpus, devices=devs)
+    assert g.shard_count == len(devs) and len(g) == 30_000
+    for b, k in ((1, 10), (4, 50), (40, 10), (300, 100)):
+        Q = synth.make_queries(corpus, b, seed=b)
+        assert_batch_equal(g, o, Q, k)
+    # exact path on every shard gives the same answer
+    g.set_option("force_path", 3)
+    assert_batch_equal(g, o, synth.make_queries(corpus, 3, seed=5), 20)
+
+
+def test_sharded_ties_follow_global_insertion_order():
+    """Equal scores come out in insertion order of the single index even though consecutive rows live
+    on different devices."""
+    rng = np.random.default_rng(3)
+    base = rng.standard_normal((50, 64)).astype(np.float32)
+    corpus = np.concatenate([base[rng.integers(0, 50, 400)] for _ in range(10)])  # 4000 rows, 80 copies of each
+    ids = synth.make_ids(corpus.shape[0])
+    g = GpuVectorIndex(64, devices=[0, 0, 0, 0])
+    o = OracleIndex(64, faithful_copy=False)
+    # streaming appends of uneven sizes: every batch is dealt over the shards
+    at = 0
+    for step in (1, 7, 256, 33, 1000, 5, 2698):
+        g.insert_batch(ids[at:at + step], corpus[at:at + step])
+        o.insert_batch(ids[at:at + step], corpus[at:at + step])
+        at += step
+    assert at == corpus.shape[0]
+    Q = base[:9] + 0.0
+    assert_batch_equal(g, o, Q, 100)
+    assert_batch_equal(g, o, Q[:2], 3)
+    check_threshold_batch(g, o, Q[:3], 0.9, 500)
+
+
+def test_sharded_mutation_filters_rebuild_save_load(tmp_path):
+    corpus = synth.make_corpus(9000, 128, seed=17)
+    g, o, ids = build_pair(corpus, devices=[0, 0, 0])
+    for r in range(0, 9000, 3):
+        kind = "fact" if r % 2 else "event"
+        g.set_metadata(ids[r].tobytes(), kind, "agent-a")
+        o.set_metadata(ids[r].tobytes(), kind, "agent-a")
+    for r in range(5, 9000, 11):
+        g.remove(ids[r].tobytes())
+        o.remove(ids[r].tobytes())
+    # overwrite some rows in place (HashMap::insert, index.rs:307)
+    rng = np.random.default_rng(1)
+    for r in (1, 4000, 8999):
+        v = rng.standard_normal(128).astype(np.float32)
+        g.insert(ids[r].tobytes(), v)
+        o.insert(ids[r].tobytes(), v)
+    Q = synth.make_queries(corpus, 12, seed=2)
+    assert len(g) == len(o)
+    assert_batch_equal(g, o, Q, 10)
+    assert_batch_equal(g, o, Q, 10, VectorFilter().with_kinds(["fact"]), Filter(kinds=["fact"]))
+    ex = [ids[i].tobytes() for i in (0, 1, 2, 3000, 6000)]
+    assert_batch_equal(g, o, Q[:4], 10, VectorFilter().excluding(ex), Filter(exclude=ex))
+    g.rebuild()
+    assert_batch_equal(g, o, Q, 10)
+    check_threshold_batch(g, o, Q[:5], 0.75, 200)
+    # the file is the single-index file: a single-device index and the oracle read it back
+    p = str(tmp_path / "sharded.idx")
+    g.save(p)
+    g1 = GpuVectorIndex.load(p)
+    assert len(g1) == len(o)
+    assert_batch_equal(g1, o, Q, 10, VectorFilter().with_kinds(["event"]), Filter(kinds=["event"]))
+    g3 = GpuVectorIndex.load(p, devices=[0, 0])
+    assert g3.shard_count == 2
+    assert_batch_equal(g3, o, Q, 10)
+
+
+def test_sharded_threshold_scans():
+    corpus = synth.make_corpus(24_000, 384, zero_row=True, seed=8)
+    g, o, _ = build_pair(corpus, devices=[0, 0, 0, 0])
+    Q = synth.make_queries(corpus, 70, seed=3)
+    for thr in (0.92, 0.75):
+        check_threshold_batch(g, o, Q, thr, 256)
+    check_threshold_batch(g, o, Q[:3], 0.5, 2000)
+    check_threshold_batch(g, o, Q[:2], 0.1, 24_000)  # exact path on every shard
+    res = g.search_threshold(Q[0], 0.75)
+    exp = o.search_threshold(Q[0], 0.75)
+    assert [r.node_id for r in res] == [i.tobytes() for i in exp.ids]
+
+
+def test_sharded_dedup_scan_matches_reference_loop():
+    n, d = 6000, 96
+    corpus = synth.make_corpus(n, d, seed=77)
+    rng = np.random.default_rng(5)
+    near = rng.integers(0, n, 300)
+    corpus[near] = corpus[(near * 7 + 1) % n] + rng.normal(0, 0.004, (300, d)).astype(np.float32)
+    g, o, ids = build_pair(corpus, devices=[0, 0, 0])
+    dead = set(range(17, n, 97))
+    for r in dead:
+        g.remove(ids[r].tobytes())
+        o.remove(ids[r].tobytes())
+    exp = assert_dedup_equal(g, o, corpus, ids, 0.92, dead)
+    assert len(exp) > 50
+
+
+def test_sharded_autolink_matches_reference_loop():
+    from test_gpu_autolink import reference_cycle
+
+    cfg = SimilarityConfig()
+    n, b = 12_000, 60
+    corpus = synth.make_corpus(n, 384, n_clusters=60, dup_frac=0.02, seed=n)
+    g, o, ids = build_pair(corpus, devices=[0, 0, 0, 0])
+    rng = np.random.default_rng(n)
+    pick = rng.choice(n, size=b, replace=False)
+    new_nodes = []
+    for j, r in enumerate(pick):
+        if j % 2 == 0:
+            new_nodes.append((ids[r].tobytes(), corpus[r]))
+        else:
+            e = corpus[r] + rng.standard_normal(384).astype(np.float32) * 0.02
+            new_nodes.append((synth.make_ids(1, start=10_000_000 + j)[0].tobytes(), (e / np.linalg.norm(e)).astype(np.float32)))
+    got = g.autolink_batch(new_nodes, threshold=cfg.auto_link_threshold, k=100, max_edges_per_node=50)
+    exp = reference_cycle(o, new_nodes, cfg.auto_link_threshold, 100, 50)
+    n_links = 0
+    for nid in exp:
+        assert [t for t, _ in got[nid]] == [t for t, _ in exp[nid]]
+        assert same_bits([s for _, s in got[nid]], [s for _, s in exp[nid]])
+        n_links += len(exp[nid])
+    assert n_links > 0
+
+
+def test_sharded_device_resident_search_and_pipelining():
+    import torch
+
+    corpus = synth.make_corpus(40_000, 384, seed=4)
+    g, o, ids = build_pair(corpus, devices=[0, 0, 0, 0])
+    Q = synth.make_queries(corpus, 256, seed=9)
+    dq = torch.from_numpy(Q).cuda()
+    s = torch.cuda.current_stream().cuda_stream
+    ids_out = torch.zeros((256, 10, 16), dtype=torch.uint8, device="cuda")
+    out = None
+    for _ in range(4):  # repeated shape: later rounds replay recorded launch sequences on every shard
+        out = g.search_batch_device(dq, 10, stream=s, out=out, ids_out=ids_out)
+    torch.cuda.synchronize()
+    rows, sc, di, n = (t.cpu().numpy() for t in out)
+    oi, os_, od, _, on = o.search_batch(Q, 10)
+    assert np.array_equal(n, on)
+    assert np.array_equal(ids_out.cpu().numpy(), oi)
+    assert same_bits(sc, os_) and same_bits(di, od)
+    # two searches in flight
+    o2 = [None, None]
+    i2 = [torch.zeros_like(ids_out), torch.zeros_like(ids_out)]
+    pend = []
+    for step in range(6):
+        sl = step % 2
+        o2[sl], ticket = g.search_batch_device_begin(dq, 10, stream=s, out=o2[sl], ids_out=i2[sl])
+        pend.append((sl, ticket))
+        if len(pend) == 2:
+            sl0, t0 = pend.pop(0)
+            g.search_batch_device_end(t0)
+            torch.cuda.synchronize()
+            assert np.array_equal(i2[sl0].cpu().numpy(), oi)
+    for sl0, t0 in pend:
+        g.search_batch_device_end(t0)
+    assert g.stats()["graph_launches"] > 0
+
+
+@pytest.mark.skipif("CORTEX_TEST_MULTI" not in os.environ, reason="needs >= 2 GPUs (set CORTEX_TEST_MULTI=1)")
+def test_real_devices_bulk_device_insert():
+    """Rows resident on devices[0] are dealt to the other GPUs over NVLink."""
+    import torch
+
+    n_dev = torch.cuda.device_count()
+    assert n_dev >= 2
+    corpus = synth.make_corpus(50_000, 384, seed=12)
+    ids = synth.make_ids(50_000)
+    g = GpuVectorIndex(384, devices=list(range(n_dev)))
+    g.insert_batch_device(ids, torch.from_numpy(corpus).cuda(0))
+    o = OracleIndex(384, faithful_copy=False)
+    o.insert_batch(ids, corpus)
+    assert_batch_equal(g, o, synth.make_queries(corpus, 130, seed=1), 10)
