@@ -230,10 +230,11 @@ __global__ void shard_merge_kernel(const uint64_t* __restrict__ gathered, uint32
                                    uint64_t* __restrict__ out_seq, uint32_t* __restrict__ out_n,
                                    uint64_t* __restrict__ out_unverified) {
   const uint32_t b = blockIdx.x;
-  const size_t stride = (size_t)SLOT_WORDS * B * k + 1;  // words per shard (slots + trailer)
+  const size_t n_slot_words = (size_t)SLOT_WORDS * B * k;
+  const size_t stride = n_slot_words + SLOT_WORDS;  // words per shard: slots + trailer, 32 B aligned
   if (b == 0 && threadIdx.x == 0 && out_unverified) {
     uint64_t t = 0;
-    for (uint32_t w = 0; w < W; ++w) t += gathered[(size_t)w * stride + stride - 1];
+    for (uint32_t w = 0; w < W; ++w) t += gathered[(size_t)w * stride + n_slot_words];
     *out_unverified = t;
   }
   uint32_t valid = 0;
@@ -327,7 +328,8 @@ __global__ void shard_pair_write_kernel(const uint8_t* __restrict__ ids, const f
   }
 }
 
-size_t payload_words(uint64_t B, uint64_t k) { return (size_t)SLOT_WORDS * B * k + 1; }
+// slots + the trailer word, padded so that every shard's region starts 32 B aligned
+size_t payload_words(uint64_t B, uint64_t k) { return (size_t)SLOT_WORDS * B * k + SLOT_WORDS; }
 
 // Per-shard part of a fan-out: device buffers of the call on the shard's device, carved from the
 // aux block of a workspace leased from the shard.
@@ -374,7 +376,7 @@ cx_status shard_pack(ShardSet* S, uint32_t s, ShardCall& sc, MergeWs* mw, uint64
   const size_t words = payload_words(B, k);
   uint64_t* dst = gathered + (size_t)s * words;
   uint64_t* target = S->peer[s] ? dst : sc.payload;
-  CU(cudaMemsetAsync(target + words - 1, 0, 8, st));  // trailer
+  CU(cudaMemsetAsync(target + words - SLOT_WORDS, 0, 8 * SLOT_WORDS, st));  // trailer
   const uint64_t total = B * k;
   if (c->n_rows == 0) {
     CU(cudaMemsetAsync(target, 0, words * 8, st));
