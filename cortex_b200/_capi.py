@@ -91,6 +91,8 @@ SYMBOLS = {
                                       C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p]),
     "cx_merge_topk_device": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cx_autolink_filter_device": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64,
+                                            C.c_float, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cx_search_ticket_ok": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "cx_save": (C.c_int, [C.c_void_p, C.c_char_p]),
     "cx_load": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]),

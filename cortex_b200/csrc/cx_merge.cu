@@ -108,6 +108,30 @@ __global__ void autolink_filter_kernel(const uint32_t* __restrict__ rows, const 
   out_n[b] = m;
 }
 
+// the same post-pass on MERGED lists of a row-sharded search (global rows, int64; self < 0 = not in the index)
+__global__ void autolink_filter_global_kernel(const int64_t* __restrict__ rows, const float* __restrict__ score,
+                                              const uint32_t* __restrict__ n, const int64_t* __restrict__ self_rows,
+                                              uint32_t B, uint32_t k, float threshold, uint32_t max_edges,
+                                              int64_t* __restrict__ out_rows, float* __restrict__ out_score,
+                                              uint32_t* __restrict__ out_n) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int64_t self = self_rows ? self_rows[b] : -1;
+  const uint32_t nb = n[b] < k ? n[b] : k;
+  uint32_t m = 0;
+  for (uint32_t j = 0; j < nb && m < max_edges; ++j) {
+    const int64_t r = rows[(size_t)b * k + j];
+    const float s = score[(size_t)b * k + j];
+    if (r == self) continue;
+    if (!(s >= threshold)) continue;  // false for NaN
+    const size_t o = (size_t)b * max_edges + m;
+    out_rows[o] = r;
+    out_score[o] = s;
+    ++m;
+  }
+  out_n[b] = m;
+}
+
 void launch_autolink_filter(const uint32_t* rows, const float* score, const uint32_t* n, const uint32_t* self_rows,
                             const uint8_t* ids, uint32_t B, uint32_t k, float threshold, uint32_t max_edges,
                             uint32_t* out_rows, float* out_score, uint8_t* out_ids, uint32_t* out_n,
@@ -228,6 +252,22 @@ extern "C" cx_status cx_merge_topk_device(const uint64_t* d_gathered, uint32_t w
   merge_topk_kernel<<<(unsigned)B, 128, smem, (cudaStream_t)stream>>>(d_gathered, world, (uint32_t)B, (uint32_t)k,
                                                                       d_out_rows, d_out_score, d_out_distance, d_out_n,
                                                                       d_out_unverified);
+  CU(cudaGetLastError());
+  return CX_OK;
+}
+
+// AutoLinker::run_cycle's candidate post-pass (linker/auto_linker.rs:224-264, rules.rs:42-62) on the merged
+// lists of a row-sharded search: skip self, keep score >= threshold, at most max_edges per node.
+extern "C" cx_status cx_autolink_filter_device(const int64_t* d_rows, const float* d_score, const uint32_t* d_n,
+                                               const int64_t* d_self_rows, uint64_t B, uint64_t k, float threshold,
+                                               uint32_t max_edges_per_node, int64_t* d_out_rows, float* d_out_score,
+                                               uint32_t* d_out_n, void* stream) {
+  if (!d_rows || !d_score || !d_n || !d_out_rows || !d_out_score || !d_out_n)
+    return fail(CX_ERR_VALIDATION, "null device buffer");
+  if (!B) return CX_OK;
+  autolink_filter_global_kernel<<<(unsigned)((B + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      d_rows, d_score, d_n, d_self_rows, (uint32_t)B, (uint32_t)k, threshold, max_edges_per_node, d_out_rows, d_out_score,
+      d_out_n);
   CU(cudaGetLastError());
   return CX_OK;
 }

@@ -383,6 +383,28 @@ class GpuVectorIndex:
         return {bytes(nid): [(to[b, j].tobytes(), float(sc[b, j])) for j in range(int(n[b]))]
                 for b, (nid, _) in enumerate(new_nodes)}
 
+    def autolink_batch_device(self, d_embeddings, k: int = 100, threshold: float = 0.75,
+                              max_edges_per_node: int = 50, d_self_rows=None, stream: int = 0, bufs=None):
+        """cx_autolink_batch_device: the auto-link scan step with new-node embeddings [B, dim] and results in
+        HBM (single-device index).  Returns ((rows int32 [B,me], score [B,me], n int32 [B]), bufs); pass
+        `bufs` back in to reuse the scratch and output buffers."""
+        import torch
+
+        assert d_embeddings.is_cuda and d_embeddings.dtype == torch.float32 and d_embeddings.is_contiguous()
+        B, me, dev = d_embeddings.shape[0], int(max_edges_per_node), d_embeddings.device
+        kk = min(int(k), max(1, len(self)))
+        if bufs is None:
+            bufs = (torch.empty((B, kk), dtype=torch.int32, device=dev), torch.empty((B, kk), dtype=torch.float32, device=dev),
+                    torch.empty((B, kk), dtype=torch.float32, device=dev), torch.empty((B,), dtype=torch.int32, device=dev),
+                    torch.empty((B, me), dtype=torch.int32, device=dev), torch.empty((B, me), dtype=torch.float32, device=dev),
+                    torch.empty((B,), dtype=torch.int32, device=dev))
+        sr, ss, sd, sn, orow, osc, on = bufs
+        _check(self._L.cx_autolink_batch_device(self._h, d_embeddings.data_ptr(), B, kk, C.c_float(threshold), me,
+                                                d_self_rows.data_ptr() if d_self_rows is not None else None,
+                                                sr.data_ptr(), ss.data_ptr(), sd.data_ptr(), sn.data_ptr(),
+                                                orow.data_ptr(), osc.data_ptr(), None, on.data_ptr(), C.c_void_p(stream)))
+        return (orow, osc, on), bufs
+
     def row_id(self, row: int) -> bytes:
         buf = np.zeros(16, np.uint8)
         _check(self._L.cx_row_id(self._h, int(row), buf.ctypes.data))

@@ -186,13 +186,39 @@ class ShardedSearch:
         identical on every rank."""
         grow, score, _, n = self.search(new_embeddings, k)
         B = grow.shape[0]
+        me = min(int(max_edges_per_node), grow.shape[1])
+        if grow.is_cuda:
+            # one CUDA kernel on the merged lists (cx_merge.cu), behind the sharded search on the same stream
+            import ctypes as C
+
+            from . import _capi
+            L = _capi.load()
+            dev = grow.device
+            key = ("al", B, k, me, str(dev))
+            buf = self._bufs.get(key)
+            if buf is None:
+                buf = (torch.empty((B, me), dtype=torch.int64, device=dev),
+                       torch.empty((B, me), dtype=torch.float32, device=dev),
+                       torch.empty((B,), dtype=torch.int32, device=dev))
+                self._bufs[key] = buf
+            out_rows, out_score, out_n = buf
+            selfp = None
+            if self_global_rows is not None:
+                self_dev = self_global_rows.to(dev).to(torch.int64).contiguous()
+                selfp = self_dev.data_ptr()
+            st = L.cx_autolink_filter_device(grow.data_ptr(), score.data_ptr(), n.data_ptr(), selfp, B, grow.shape[1],
+                                             C.c_float(threshold), me, out_rows.data_ptr(), out_score.data_ptr(),
+                                             out_n.data_ptr(), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+            if st != 0:
+                raise RuntimeError(L.cx_last_error().decode())
+            return out_rows, out_score, out_n
+        # CPU tensors (the gloo tests of the host logic): the same rule in torch
         idx = torch.arange(grow.shape[1], device=grow.device)[None, :]
         keep = (idx < n.to(torch.int64)[:, None]) & (score >= threshold)        # NaN >= t is False
         if self_global_rows is not None:
             keep &= grow != self_global_rows.to(grow.device).to(torch.int64)[:, None]
         # stable compaction of the kept entries to the front (they are already best first)
         order = torch.argsort((~keep).to(torch.int8), dim=1, stable=True)
-        me = min(int(max_edges_per_node), grow.shape[1])
         out_rows = torch.gather(grow, 1, order)[:, :me]
         out_score = torch.gather(score, 1, order)[:, :me]
         out_n = keep.sum(dim=1).clamp(max=me).to(torch.int32)

@@ -209,6 +209,13 @@ cx_status cx_pack_topk_device(const uint32_t* d_rows, const float* d_score, cons
 cx_status cx_merge_topk_device(const uint64_t* d_gathered, uint32_t world, uint64_t B, uint64_t k,
                                int64_t* d_out_rows, float* d_out_score, float* d_out_distance,
                                uint32_t* d_out_n, uint64_t* d_out_unverified, void* stream);
+/* The auto-link candidate post-pass (linker/auto_linker.rs:224-264, rules.rs:42-62) on the MERGED lists of
+ * a process-per-GPU sharded search (global rows): skip the node itself (d_self_rows [B], < 0 = not in the
+ * index; may be NULL), keep score >= threshold, at most max_edges_per_node.  Outputs [B][max_edges_per_node]. */
+cx_status cx_autolink_filter_device(const int64_t* d_rows, const float* d_score, const uint32_t* d_n,
+                                    const int64_t* d_self_rows, uint64_t B, uint64_t k, float threshold,
+                                    uint32_t max_edges_per_node, int64_t* d_out_rows, float* d_out_score,
+                                    uint32_t* d_out_n, void* stream);
 /* device pointer to the verification flags [B] of a search in flight (NULL ticket -> NULL) */
 cx_status cx_search_ticket_ok(void* ticket, const uint32_t** d_ok);
 

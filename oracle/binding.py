@@ -61,6 +61,8 @@ def lib():
     L.cxo_set_faithful_copy.argtypes = [C.c_void_p, C.c_int]
     L.cxo_insert.restype = C.c_int
     L.cxo_insert.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    L.cxo_insert_batch.restype = C.c_int
+    L.cxo_insert_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]
     L.cxo_remove.restype = C.c_int
     L.cxo_remove.argtypes = [C.c_void_p, C.c_void_p]
     L.cxo_set_metadata.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_char_p]
@@ -142,10 +144,11 @@ class OracleIndex:
     def insert_batch(self, ids: np.ndarray, rows: np.ndarray) -> None:
         rows = np.ascontiguousarray(rows, dtype=np.float32)
         ids = np.ascontiguousarray(ids, dtype=np.uint8).reshape(-1, 16)
-        for i in range(rows.shape[0]):
-            rc = self._L.cxo_insert(self._h, ids[i].ctypes.data, rows[i].ctypes.data, rows.shape[1])
-            if rc != 0:
-                raise ValueError("Embedding dimension mismatch")
+        if rows.shape[0] == 0:
+            return
+        rc = self._L.cxo_insert_batch(self._h, ids.ctypes.data, rows.ctypes.data, rows.shape[0], rows.shape[1])
+        if rc != 0:
+            raise ValueError("Embedding dimension mismatch")
 
     def remove(self, node_id) -> None:
         self._L.cxo_remove(self._h, _id(node_id).ctypes.data)
@@ -236,7 +239,12 @@ class OracleIndex:
 
 
 def max_threads() -> int:
-    return int(lib().cxo_max_threads())
+    """Host threads the CPU legs use: every core this process may run on.  (Not omp_get_max_threads():
+    torchrun exports OMP_NUM_THREADS=1, which would silently shrink the baseline to one core.)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
 class OracleHnsw:
@@ -245,10 +253,11 @@ class OracleHnsw:
     the reference's approximate path as recall@k against the exact scan."""
 
     def __init__(self, vectors: np.ndarray, M: int = 32, ef_construction: int = 100, ef_search: int = 100,
-                 seed: int = 1):
+                 seed: int = 1, n_threads: int = 1):
         L = lib()
-        L.cxo_hnsw_build.restype = C.c_void_p
-        L.cxo_hnsw_build.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_uint64]
+        L.cxo_hnsw_build_mt.restype = C.c_void_p
+        L.cxo_hnsw_build_mt.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_uint64,
+                                        C.c_int]
         L.cxo_hnsw_search.restype = C.c_size_t
         L.cxo_hnsw_search.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]
         L.cxo_hnsw_distance_evals.restype = C.c_uint64
@@ -256,9 +265,9 @@ class OracleHnsw:
         L.cxo_hnsw_free.argtypes = [C.c_void_p]
         self._L = L
         self._v = np.ascontiguousarray(vectors, dtype=np.float32)  # borrowed by the C side
-        self.ef_search = ef_search
-        self._h = L.cxo_hnsw_build(self._v.ctypes.data, self._v.shape[0], self._v.shape[1], M, ef_construction,
-                                   ef_search, seed)
+        self.M, self.ef_construction, self.ef_search = M, ef_construction, ef_search
+        self._h = L.cxo_hnsw_build_mt(self._v.ctypes.data, self._v.shape[0], self._v.shape[1], M, ef_construction,
+                                      ef_search, seed, n_threads)
 
     def __del__(self):
         if getattr(self, "_h", None):

@@ -237,6 +237,15 @@ int cxo_insert(cxo_index *ix, const uint8_t *id, const float *v, size_t len) {
   return CXO_OK;
 }
 
+/* the startup loop serve.rs:111-117 / api.rs:55-69: one insert per row, in order */
+int cxo_insert_batch(cxo_index *ix, const uint8_t *ids, const float *rows, size_t n, size_t len) {
+  for (size_t i = 0; i < n; ++i) {
+    int rc = cxo_insert(ix, ids + 16 * i, rows + i * len, len);
+    if (rc != CXO_OK) return rc;
+  }
+  return CXO_OK;
+}
+
 /* vector/index.rs:316-323: drop vector and metadata; never an error. */
 int cxo_remove(cxo_index *ix, const uint8_t *id) {
   long r = find_row(ix, id);

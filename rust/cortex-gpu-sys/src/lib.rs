@@ -89,6 +89,9 @@ extern "C" {
     pub fn cx_merge_topk_device(d_gathered: *const u64, world: u32, b: u64, k: u64, d_out_rows: *mut i64,
                                 d_out_score: *mut f32, d_out_distance: *mut f32, d_out_n: *mut u32,
                                 d_out_unverified: *mut u64, stream: *mut c_void) -> c_int;
+    pub fn cx_autolink_filter_device(d_rows: *const i64, d_score: *const f32, d_n: *const u32, d_self_rows: *const i64,
+                                     b: u64, k: u64, threshold: f32, max_edges_per_node: u32, d_out_rows: *mut i64,
+                                     d_out_score: *mut f32, d_out_n: *mut u32, stream: *mut c_void) -> c_int;
     pub fn cx_debug_tensor_plan(n_queries: u64, n_rows: u64, sm_count: c_int, sample_tiles: u32, growth: u32,
                                 groups: *mut u32, groups_n: *mut u32, phases: *mut u32, phases_n: *mut u32,
                                 hits_per_kp: *mut f64) -> c_int;
