@@ -11,7 +11,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcortex_gpu.so")
+# CORTEX_GPU_LIB: load another build of the same sources (the -DCX_PROBE measurement build of scripts/k2_probe.py)
+LIB_PATH = os.environ.get("CORTEX_GPU_LIB") or os.path.join(_HERE, "libcortex_gpu.so")
 
 CX_OK, CX_ERR_VALIDATION, CX_ERR_CUDA, CX_ERR_NCCL, CX_ERR_IO = 0, 1, 2, 3, 4
 
@@ -27,6 +28,11 @@ class CxFilter(C.Structure):
         ("has_source_agent", C.c_int32),
         ("source_agent", C.c_char_p),
     ]
+
+
+class CxDecayConfig(C.Structure):
+    _fields_ = [("enabled", C.c_int32), ("max_age_days", C.c_double), ("min_factor", C.c_double),
+                ("echo_weight", C.c_double), ("echo_cap", C.c_double)]
 
 
 class CxStats(C.Structure):
@@ -98,6 +104,11 @@ SYMBOLS = {
     "cx_load": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(C.c_void_p)]),
     "cx_load_sharded": (C.c_int, [C.c_char_p, C.POINTER(C.c_int), C.c_uint32, C.POINTER(C.c_void_p)]),
     "cx_row_id": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p]),
+    "cx_extract_embeddings": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "cx_load_nodes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "cx_apply_score_decay": (C.c_int, [C.c_void_p, C.POINTER(CxDecayConfig), C.c_float, C.c_uint64, C.c_uint32,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "cx_get_stats": (C.c_int, [C.c_void_p, C.POINTER(CxStats)]),
     "cx_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "cx_debug_tensor_plan": (C.c_int, [C.c_uint64, C.c_uint64, C.c_int, C.c_uint32, C.c_uint32, C.c_void_p,

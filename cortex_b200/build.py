@@ -18,6 +18,10 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libcortex_gpu.so")
 STAMP = os.path.join(HERE, ".libcortex_gpu.stamp")
+# measurement build for scripts/k2_probe.py only (-DCX_PROBE: the result-corrupting "tensor_debug" hook exists);
+# never loaded by the package unless CORTEX_GPU_LIB points at it
+PROBE_LIB = os.path.join(HERE, "libcortex_gpu_probe.so")
+PROBE_STAMP = os.path.join(HERE, ".libcortex_gpu_probe.stamp")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -51,12 +55,13 @@ def _digest() -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, probe: bool = False) -> str:
     dig = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(STAMP):
-        if open(STAMP).read().strip() == dig:
-            return LIB
-    cmd = [_nvcc(), *NVCC_FLAGS, "-I", INCLUDE, "-I", CSRC, "-o", LIB, *sources()]
+    lib, stamp = (PROBE_LIB, PROBE_STAMP) if probe else (LIB, STAMP)
+    if not force and os.path.exists(lib) and os.path.exists(stamp):
+        if open(stamp).read().strip() == dig:
+            return lib
+    cmd = [_nvcc(), *NVCC_FLAGS, *(["-DCX_PROBE"] if probe else []), "-I", INCLUDE, "-I", CSRC, "-o", lib, *sources()]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
@@ -69,10 +74,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
         print(r.stderr, file=sys.stderr)
     if r.returncode != 0:
         raise RuntimeError(f"nvcc failed:\n{r.stdout}\n{r.stderr}")
-    with open(STAMP, "w") as fp:
+    with open(stamp, "w") as fp:
         fp.write(dig)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, probe="--probe" in sys.argv))

@@ -113,6 +113,23 @@ def _id16(node_id) -> np.ndarray:
     return a.copy()
 
 
+def extract_embeddings(blob: np.ndarray, offsets: np.ndarray, dim: int, device: int = 0):
+    """cx_extract_embeddings: walk the raw `nodes` table values on the GPU.  Returns a dict with status [n],
+    ids [n,16], rows [n,dim] (valid where status == 0), created_ns, last_accessed_ns, access_count."""
+    L = _capi.load()
+    blob = np.ascontiguousarray(blob, np.uint8)
+    offsets = np.ascontiguousarray(offsets, np.uint64)
+    n = offsets.size - 1
+    out = {"status": np.zeros(n, np.uint8), "ids": np.zeros((n, 16), np.uint8), "rows": np.zeros((n, dim), np.float32),
+           "created_ns": np.zeros(n, np.int64), "last_accessed_ns": np.zeros(n, np.int64),
+           "access_count": np.zeros(n, np.uint64)}
+    _check(L.cx_extract_embeddings(blob.ctypes.data, offsets.ctypes.data, n, dim, device, out["ids"].ctypes.data,
+                                   out["rows"].ctypes.data, out["created_ns"].ctypes.data,
+                                   out["last_accessed_ns"].ctypes.data, out["access_count"].ctypes.data,
+                                   out["status"].ctypes.data))
+    return out
+
+
 class GpuVectorIndex:
     """B200-resident exact-scan index behind the reference's VectorIndex surface."""
 
@@ -404,6 +421,37 @@ class GpuVectorIndex:
                                                 sr.data_ptr(), ss.data_ptr(), sd.data_ptr(), sn.data_ptr(),
                                                 orow.data_ptr(), osc.data_ptr(), None, on.data_ptr(), C.c_void_p(stream)))
         return (orow, osc, on), bufs
+
+    # ---- the callers' data formats either side of the scan -------------------------
+    def load_nodes(self, blob: np.ndarray, offsets: np.ndarray):
+        """The start-up loop (serve.rs:105-123) in one call: raw values of the redb `nodes` table in, every live
+        node with an embedding inserted newest first.  Returns (status uint8 [n], counts [6])."""
+        blob = np.ascontiguousarray(blob, np.uint8)
+        offsets = np.ascontiguousarray(offsets, np.uint64)
+        n = offsets.size - 1
+        status = np.zeros(max(1, n), np.uint8)
+        counts = np.zeros(6, np.uint64)
+        _check(self._L.cx_load_nodes(self._h, blob.ctypes.data, offsets.ctypes.data, n, status.ctypes.data,
+                                     counts.ctypes.data))
+        return status[:n], counts
+
+    def apply_score_decay(self, raw_score, idle_seconds, access_count, kind_rate, recency_bias: float = 0.15,
+                          seg_len: int = 0, enabled: bool = True, max_age_days: float = 365.0, min_factor: float = 0.1,
+                          echo_weight: float = 0.05, echo_cap: float = 2.0, rerank: bool = False):
+        """apply_score_decay (vector/scoring.rs:84-114) for n candidates (defaults = ScoreDecayConfig::default()).
+        Returns the decayed scores and, with rerank=True, the per-segment order (routes.rs:945-949)."""
+        raw = np.ascontiguousarray(raw_score, np.float32)
+        idle = np.ascontiguousarray(idle_seconds, np.int64)
+        acc = np.ascontiguousarray(access_count, np.uint64)
+        rate = np.ascontiguousarray(kind_rate, np.float64)
+        n = raw.size
+        out = np.zeros(n, np.float32)
+        order = np.zeros(n, np.uint32) if rerank else None
+        cfg = _capi.CxDecayConfig(int(enabled), max_age_days, min_factor, echo_weight, echo_cap)
+        _check(self._L.cx_apply_score_decay(self._h, C.byref(cfg), C.c_float(recency_bias), n, int(seg_len),
+                                            raw.ctypes.data, idle.ctypes.data, acc.ctypes.data, rate.ctypes.data,
+                                            out.ctypes.data, order.ctypes.data if rerank else None))
+        return (out, order) if rerank else out
 
     def row_id(self, row: int) -> bytes:
         buf = np.zeros(16, np.uint8)

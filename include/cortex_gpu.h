@@ -228,6 +228,49 @@ cx_status cx_load_sharded(const char* path, const int* devices, uint32_t n_devic
 /* id of shard-local row r (16 bytes) -- used when merging device results */
 cx_status cx_row_id(const cx_index* h, uint32_t row, uint8_t out_id[16]);
 
+/* ---- the callers' data formats either side of the scan ---------------------- */
+
+/* What the node walk decided for a node of the redb `nodes` table. */
+typedef enum cx_node_status {
+  CX_NODE_OK = 0,               /* live node with an embedding of the right dimension: extracted / inserted */
+  CX_NODE_NO_EMBEDDING = 1,     /* embedding: None (serve.rs:111 skips it) */
+  CX_NODE_DELETED = 2,          /* tombstone: list_nodes(NodeFilter::new()) leaves it out (redb_storage.rs:347) */
+  CX_NODE_DIM_MISMATCH = 3,     /* insert() is Err, the start-up loop moves on (serve.rs:112-114) */
+  CX_NODE_NEEDS_HOST_DECODE = 4,/* non-empty `metadata` (bincode does not describe serde_json::Value, types.rs:142)
+                                   or a timestamp form the walk does not parse: decode it with the caller's own
+                                   deserializer and insert it through cx_insert */
+  CX_NODE_CORRUPT = 5           /* the reference's deserializer fails too and skips the record (redb_storage.rs:707-710) */
+} cx_node_status;
+
+/* Embedding extractor for the start-up loop (serve.rs:105-123, api.rs:55-69): `values` holds the n raw values
+ * of the `nodes` table back to back (bincode 1.3 of `Node`, types.rs:26-68; layout pinned by the golden bytes
+ * of storage/redb_storage.rs:1834-1856), value i = values[offsets[i] .. offsets[i+1]).  One GPU thread per node
+ * walks the variable-length fields; out_status[i] says what it found, out_ids [n][16], out_created_ns /
+ * out_last_accessed_ns [n] (nanoseconds since the epoch), out_access_count [n] and out_rows [n][dim] (written
+ * for CX_NODE_OK nodes only) are optional. */
+cx_status cx_extract_embeddings(const uint8_t* values, const uint64_t* offsets, uint64_t n, uint32_t dim, int device,
+                                uint8_t* out_ids, float* out_rows, int64_t* out_created_ns,
+                                int64_t* out_last_accessed_ns, uint64_t* out_access_count, uint8_t* out_status);
+/* The whole start-up loop in one call: every CX_NODE_OK node is inserted in the reference's order (newest
+ * created_at first, ties in table order: redb_storage.rs:728); the embeddings move from the uploaded blob into
+ * the store on the device.  out_status [n] and out_counts [6] (nodes per cx_node_status) are optional. */
+cx_status cx_load_nodes(cx_index* h, const uint8_t* values, const uint64_t* offsets, uint64_t n, uint8_t* out_status,
+                        uint64_t out_counts[6]);
+
+/* ScoreDecayConfig (vector/scoring.rs:20-76) without the by_kind table: the caller resolves
+ * `by_kind.get(kind).unwrap_or(daily_rate)` per candidate and passes it as kind_rate. */
+typedef struct cx_decay_config {
+  int32_t enabled;
+  double max_age_days, min_factor, echo_weight, echo_cap;
+} cx_decay_config;
+/* apply_score_decay (vector/scoring.rs:84-114) for n search candidates at once, seg_len per query (0 = one
+ * segment): idle_seconds = (now - last_accessed_at).num_seconds().  out_order (optional, [n]): per segment the
+ * candidates' positions re-ranked by decayed score, best first, equal scores in candidate order -- the
+ * re-rank of the search handler (http/routes.rs:945-949). */
+cx_status cx_apply_score_decay(cx_index* h, const cx_decay_config* cfg, float recency_bias, uint64_t n, uint32_t seg_len,
+                               const float* raw_score, const int64_t* idle_seconds, const uint64_t* access_count,
+                               const double* kind_rate, float* out_score, uint32_t* out_order);
+
 cx_status cx_get_stats(const cx_index* h, cx_stats* out);
 /* Tuning / test hooks, all per index; set them while no search is running on the handle.
  * "force_path" 0 auto, 1 stream (K1), 2 tensor (K2), 3 exact; "tensor_min_batch" smallest query batch

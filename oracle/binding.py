@@ -20,7 +20,7 @@ _LIB_PATH = os.path.join(_HERE, "libcortex_oracle.so")
 
 def build(force: bool = False) -> str:
     """Compile the oracle with the committed Makefile (gcc, -ffp-contract=off)."""
-    srcs = [os.path.join(_HERE, f) for f in ("cortex_oracle.c", "hnsw_oracle.c", "cpu_fast.c", "Makefile")]
+    srcs = [os.path.join(_HERE, f) for f in ("cortex_oracle.c", "hnsw_oracle.c", "aux_oracle.c", "cpu_fast.c", "Makefile")]
     fast = os.path.join(_HERE, "libcortex_cpufast_v3.so")
     stale = not os.path.exists(_LIB_PATH) or not os.path.exists(fast) or any(
         os.path.getmtime(s) > min(os.path.getmtime(_LIB_PATH), os.path.getmtime(fast)) for s in srcs
@@ -236,6 +236,30 @@ class OracleIndex:
         L.cxo_dim.restype = C.c_size_t
         L.cxo_dim.argtypes = [C.c_void_p]
         return cls(int(L.cxo_dim(h)), _handle=h)
+
+
+def walk_node(value: bytes, dim: int):
+    """aux_oracle.c cxo_walk_node: (status, id bytes, embedding or None, created_ns, last_accessed_ns, access_count)."""
+    L = lib()
+    L.cxo_walk_node.restype = C.c_int
+    L.cxo_walk_node.argtypes = [C.c_char_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64),
+                                C.POINTER(C.c_int64), C.POINTER(C.c_uint64)]
+    idb = np.zeros(16, np.uint8)
+    row = np.zeros(max(1, dim), np.float32)
+    cr, la, ac = C.c_int64(0), C.c_int64(0), C.c_uint64(0)
+    st = L.cxo_walk_node(value, len(value), dim, idb.ctypes.data, row.ctypes.data, C.byref(cr), C.byref(la), C.byref(ac))
+    return st, idb.tobytes(), (row[:dim].copy() if st == 0 else None), cr.value, la.value, ac.value
+
+
+def apply_score_decay(raw, idle_seconds, access_count, kind_rate, enabled=True, max_age_days=365.0, min_factor=0.1,
+                      echo_weight=0.05, echo_cap=2.0, recency_bias=0.15) -> float:
+    """aux_oracle.c cxo_apply_score_decay (vector/scoring.rs:84-114); defaults = ScoreDecayConfig::default()."""
+    L = lib()
+    L.cxo_apply_score_decay.restype = C.c_float
+    L.cxo_apply_score_decay.argtypes = [C.c_float, C.c_int64, C.c_uint64, C.c_double, C.c_int, C.c_double, C.c_double,
+                                        C.c_double, C.c_double, C.c_float]
+    return float(L.cxo_apply_score_decay(raw, int(idle_seconds), int(access_count), kind_rate, int(enabled), max_age_days,
+                                         min_factor, echo_weight, echo_cap, recency_bias))
 
 
 def max_threads() -> int:

@@ -36,6 +36,16 @@ pub struct cx_stats {
     pub in_place_growth: u64,
 }
 
+#[repr(C)]
+#[derive(Debug, Clone, Copy)]
+pub struct cx_decay_config {
+    pub enabled: i32,
+    pub max_age_days: f64,
+    pub min_factor: f64,
+    pub echo_weight: f64,
+    pub echo_cap: f64,
+}
+
 pub const CX_OK: c_int = 0;
 
 extern "C" {
@@ -99,6 +109,14 @@ extern "C" {
     pub fn cx_load(path: *const c_char, device: c_int, out: *mut *mut cx_index) -> c_int;
     pub fn cx_load_sharded(path: *const c_char, devices: *const c_int, n_devices: u32, out: *mut *mut cx_index) -> c_int;
     pub fn cx_row_id(h: *const cx_index, row: u32, out_id: *mut u8) -> c_int;
+    pub fn cx_extract_embeddings(values: *const u8, offsets: *const u64, n: u64, dim: u32, device: c_int,
+                                 out_ids: *mut u8, out_rows: *mut f32, out_created_ns: *mut i64,
+                                 out_last_accessed_ns: *mut i64, out_access_count: *mut u64, out_status: *mut u8) -> c_int;
+    pub fn cx_load_nodes(h: *mut cx_index, values: *const u8, offsets: *const u64, n: u64, out_status: *mut u8,
+                         out_counts: *mut u64) -> c_int;
+    pub fn cx_apply_score_decay(h: *mut cx_index, cfg: *const cx_decay_config, recency_bias: f32, n: u64, seg_len: u32,
+                                raw_score: *const f32, idle_seconds: *const i64, access_count: *const u64,
+                                kind_rate: *const f64, out_score: *mut f32, out_order: *mut u32) -> c_int;
     pub fn cx_get_stats(h: *const cx_index, out: *mut cx_stats) -> c_int;
     pub fn cx_set_option(h: *mut cx_index, key: *const c_char, value: i64) -> c_int;
     pub fn cx_last_error() -> *const c_char;

@@ -10,7 +10,10 @@ import sys
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+# the measurement hook "tensor_debug" exists only in the -DCX_PROBE build (python -m cortex_b200.build --probe)
+os.environ.setdefault("CORTEX_GPU_LIB", os.path.join(ROOT, "cortex_b200", "libcortex_gpu_probe.so"))
 import bench  # noqa: E402
 from cortex_b200 import GpuVectorIndex  # noqa: E402
 
