@@ -1005,6 +1005,11 @@ cx_status cx::index_set_option(cx_index* h, const char* key, int64_t value) {
     h->tensor_phase_growth = (uint32_t)value;
     return CX_OK;
   }
+  if (!strcmp(key, "tensor_sample_tiles")) {
+    if (value < 0 || value > 4096) return fail(CX_ERR_VALIDATION, "tensor_sample_tiles must be 0..4096");
+    h->tensor_sample_tiles = (uint32_t)value;
+    return CX_OK;
+  }
   if (!strcmp(key, "blocking_sync")) {
     h->blocking_sync = value != 0;
     return CX_OK;

@@ -170,6 +170,7 @@ struct cx_index {
   uint32_t tensor_min_batch = 5;   // query groups at least this large go to the tensor pass
   uint32_t tensor_phase_growth = 0xFFFFFFFFu; // tensor pass: each scan phase covers this many times the rows seen before
                                               // (0/1 = one phase; 0xFFFFFFFF = auto: one phase for B <= 256 and k <= 16, else 8 for k <= 16, 4 above)
+  uint32_t tensor_sample_tiles = 0;  // row tiles sampled for the cut-off bootstrap (0 = auto)
   int profile = 0;
   bool blocking_sync = false;      // search calls sleep on an event instead of spinning while the GPU works
   bool use_graphs = true;          // replay repeated device-resident search shapes as one CUDA graph launch

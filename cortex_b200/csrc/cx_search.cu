@@ -278,6 +278,7 @@ Plan make_plan(const cx_index* h, uint64_t B, uint32_t qlen, uint32_t ldq, uint3
     // twice that plus slack (excess is detected by the select kernel and sent to a fallback,
     // never lost silently)
     p.n_slots = tensor_sample_tiles(n_rows, (uint32_t)(B < p.q_per_launch ? B : p.q_per_launch));
+    if (h->tensor_sample_tiles) p.n_slots = std::min<uint32_t>(h->tensor_sample_tiles, tensor_tiles(n_rows));
     double hits_per_kp = 0.0;
     // auto: up to two query tiles with a short keep list the pass is HBM-bound and the epilogue has
     // slack, so one phase (no refine launches) is fastest; otherwise grow x8 (k <= 16) or x4
@@ -1105,7 +1106,8 @@ cx_status cx::index_search_device(cx_index* h, const float* d_queries, uint32_t 
                                (uint64_t)(uintptr_t)d_out_n,       (uint64_t)(uintptr_t)ws->hp,
                                (uint64_t)h->force_path,            (uint64_t)h->tensor_min_batch,
                                (uint64_t)h->tensor_phase_growth,   (uint64_t)h->profile,
-                               (uint64_t)(h->tensor_tune.pair * 64 + h->tensor_tune.epi_warps + 1024 * h->tensor_tune.debug),
+                               (uint64_t)(h->tensor_tune.pair * 64 + h->tensor_tune.epi_warps + 1024 * h->tensor_tune.debug) +
+                                   ((uint64_t)h->tensor_sample_tiles << 32),
                                (uint64_t)t->fh.excl_rows.size()};
     hs = fnv(hs, misc, sizeof misc);
     gk.w[0] = B;
