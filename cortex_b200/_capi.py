@@ -51,6 +51,9 @@ class CxStats(C.Structure):
         ("irregular_rows", C.c_uint64),
         ("capacity_rows", C.c_uint64),
         ("in_place_growth", C.c_uint64),
+        ("grow_ns", C.c_uint64),
+        ("grow_ns_max", C.c_uint64),
+        ("grow_waits", C.c_uint64),
     ]
 
 

@@ -374,19 +374,8 @@ static cx_status reserve_store(cx_index* h, size_t total_mem) {
   return CX_OK;
 }
 
-static cx_status grow(cx_index* h, uint64_t need, bool exact = false) {
-  if (need <= h->cap) return CX_OK;
-  if (need > 0x7FFFFF00ull) return fail(CX_ERR_VALIDATION, "index shard limited to 2^31 rows");
-  const bool vmm = h->aE.vmm;
-  uint64_t ncap = need;
-  if (!exact) {
-    // in-place growth is cheap: a quarter more at a time bounds the unused tail to 25 %; the
-    // copying fallback doubles
-    const uint64_t step = vmm ? (h->cap / 4 > 4096 ? h->cap / 4 : 4096) : (h->cap > 1024 ? h->cap : 1024);
-    if (h->cap + step > ncap) ncap = h->cap + step;
-  }
-  if (vmm && ncap > h->max_rows) ncap = need;
-  cudaStream_t s = h->mut_stream;
+// map every array up to ncap rows (no copy in vmm mode; the fallback copies the rows in use on s)
+static cx_status map_store(cx_index* h, uint64_t ncap, cudaStream_t s) {
   const uint64_t u = h->n_rows;
   cx_status st;
   if ((st = h->aE.ensure(ncap * h->ld * 4, u * h->ld * 4, s)) != CX_OK) return st;
@@ -397,6 +386,43 @@ static cx_status grow(cx_index* h, uint64_t need, bool exact = false) {
   if ((st = h->aIds.ensure(ncap * 16, u * 16, s)) != CX_OK) return st;
   if (h->want_shadow && (st = h->aE16.ensure(ncap * h->ld16 * 2, u * h->ld16 * 2, s)) != CX_OK) return st;
   if (h->with_seq && (st = h->aSeq.ensure(ncap * 8, u * 8, s)) != CX_OK) return st;
+  return CX_OK;
+}
+
+static void join_grower(cx_index* h) {
+  if (h->grow_thread.joinable()) h->grow_thread.join();
+}
+
+static uint64_t now_ns() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (uint64_t)ts.tv_sec * 1000000000ull + (uint64_t)ts.tv_nsec;
+}
+
+static cx_status grow(cx_index* h, uint64_t need, bool exact = false) {
+  if (need <= h->cap.load()) return CX_OK;
+  if (need > 0x7FFFFF00ull) return fail(CX_ERR_VALIDATION, "index shard limited to 2^31 rows");
+  if (h->grow_thread.joinable()) {  // an extension is already on its way: it normally covers the need
+    h->grow_waits += 1;
+    join_grower(h);
+    if (need <= h->cap.load()) return CX_OK;
+  }
+  const bool vmm = h->aE.vmm;
+  const uint64_t cap = h->cap.load();
+  uint64_t ncap = need;
+  if (!exact) {
+    // in-place growth is cheap: a quarter more at a time bounds the unused tail to 25 %; the
+    // copying fallback doubles
+    const uint64_t step = vmm ? (cap / 4 > 4096 ? cap / 4 : 4096) : (cap > 1024 ? cap : 1024);
+    if (cap + step > ncap) ncap = cap + step;
+  }
+  if (vmm && ncap > h->max_rows) ncap = need;
+  const uint64_t t0 = now_ns();
+  cx_status st = map_store(h, ncap, h->mut_stream);
+  if (st != CX_OK) return st;
+  const uint64_t dt = now_ns() - t0;
+  h->grow_ns += dt;
+  if (dt > h->grow_ns_max.load()) h->grow_ns_max = dt;
   refresh_ptrs(h);
   h->cap = ncap;
   h->grow_events += 1;
@@ -406,6 +432,32 @@ static cx_status grow(cx_index* h, uint64_t need, bool exact = false) {
     for (Workspace* w : h->ws_free) w->drop_graph();
   }
   return CX_OK;
+}
+
+// Called at the end of an insert: when the mapped store is nearly used up, map the next extension on a helper
+// thread.  Only in vmm mode (pointers never move; mapping new pages does not touch pages in use).
+static void grow_ahead(cx_index* h) {
+  if (!h->aE.vmm || h->grow_thread.joinable()) return;
+  const uint64_t cap = h->cap.load();
+  if (h->n_rows + cap / 8 + 1024 < cap) return;  // more than an eighth of the capacity is still free
+  uint64_t ncap = cap + (cap / 4 > 4096 ? cap / 4 : 4096);
+  if (ncap > h->max_rows) ncap = h->max_rows;
+  if (ncap <= cap) return;
+  h->grow_thread = std::thread([h, ncap] {
+    cudaSetDevice(h->device);
+    const uint64_t t0 = now_ns();
+    const cx_status st = map_store(h, ncap, nullptr);
+    const uint64_t dt = now_ns() - t0;
+    h->grow_status = st;
+    if (st != CX_OK) {
+      h->grow_error = last_error();
+      return;  // the next insert that needs the room maps it itself and reports the error
+    }
+    h->grow_ns += dt;
+    if (dt > h->grow_ns_max.load()) h->grow_ns_max = dt;
+    h->grow_events += 1;
+    h->cap = ncap;
+  });
 }
 
 static uint32_t meta_word(bool has, uint32_t kind) { return has ? (META_HAS | (kind & META_KIND_MASK)) : 0u; }
@@ -458,6 +510,7 @@ extern "C" void cx_index_destroy(cx_index* h) {
     return;
   }
   cudaSetDevice(h->device);
+  join_grower(h);
   if (h->mut_stream) cudaStreamSynchronize(h->mut_stream);
   for (Workspace* w : h->ws_free) delete w;
   free_store(h);
@@ -476,6 +529,7 @@ extern "C" cx_status cx_reserve(cx_index* h, uint64_t n_rows) {
   cx_status st = settle(h);
   if (st != CX_OK) return st;
   if (!h->store_ready && (st = index_prepare_store(h)) != CX_OK) return st;
+  join_grower(h);
   return grow(h, n_rows, /*exact=*/true);
 }
 
@@ -609,6 +663,7 @@ cx_status cx::index_insert(cx_index* h, const uint8_t* ids, const float* rows, u
     }
     h->n_rows += n_new;
     h->n_live += n_new;
+    grow_ahead(h);
   }
   return mutation_done(h);
 }
@@ -707,6 +762,7 @@ cx_status cx::index_rebuild(cx_index* h) {
   CU(cudaSetDevice(h->device));
   cx_status st = settle(h);
   if (st != CX_OK) return st;
+  join_grower(h);
   cudaStream_t s = h->mut_stream;
   std::vector<uint32_t> live;
   live.reserve(h->n_live);
@@ -967,7 +1023,10 @@ void cx::index_add_stats(const cx_index* h, cx_stats* out) {
   out->graph_launches += h->graph_launches.load();
   out->grow_events += h->grow_events.load();
   out->irregular_rows += h->n_irregular();
-  out->capacity_rows += h->cap;
+  out->capacity_rows += h->cap.load();
+  out->grow_ns += h->grow_ns.load();
+  if (h->grow_ns_max.load() > out->grow_ns_max) out->grow_ns_max = h->grow_ns_max.load();
+  out->grow_waits += h->grow_waits.load();
   out->in_place_growth = h->aE.vmm ? 1 : 0;
 }
 

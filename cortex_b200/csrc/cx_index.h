@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstring>
 #include <mutex>
+#include <thread>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -134,7 +135,14 @@ struct cx_index {
   int device = 0;
   int sm_count = 148;
   uint32_t dim = 0, ld = 0, ld16 = 0;
-  uint64_t n_rows = 0, n_live = 0, cap = 0;
+  uint64_t n_rows = 0, n_live = 0;
+  std::atomic<uint64_t> cap{0};    // rows the mapped store can hold
+  // in-place growth runs AHEAD of need on a helper thread (mapping a gigabyte takes the driver a few hundred
+  // milliseconds; no insert should ever wait for that)
+  std::thread grow_thread;
+  cx_status grow_status = CX_OK;
+  std::string grow_error;
+  std::atomic<uint64_t> grow_ns{0}, grow_ns_max{0}, grow_waits{0};
   // the store: growable device arrays and the raw pointers into them
   cx::VmArray aE, aNorm, aRnorm, aMeta, aAgent, aIds, aE16, aSeq;
   float* dE = nullptr;
@@ -169,7 +177,7 @@ struct cx_index {
   int force_path = 0;
   uint32_t tensor_min_batch = 5;   // query groups at least this large go to the tensor pass
   uint32_t tensor_phase_growth = 0xFFFFFFFFu; // tensor pass: each scan phase covers this many times the rows seen before
-                                              // (0/1 = one phase; 0xFFFFFFFF = auto: one phase for B <= 256 and k <= 16, else 8 for k <= 16, 4 above)
+                                              // (0/1 = one phase; 0xFFFFFFFF = auto: one phase for B <= 256 and k <= 16, else 8 for k <= 16, 6 above)
   uint32_t tensor_sample_tiles = 0;  // row tiles sampled for the cut-off bootstrap (0 = auto)
   int profile = 0;
   bool blocking_sync = false;      // search calls sleep on an event instead of spinning while the GPU works

@@ -278,13 +278,16 @@ Plan make_plan(const cx_index* h, uint64_t B, uint32_t qlen, uint32_t ldq, uint3
     // twice that plus slack (excess is detected by the select kernel and sent to a fallback,
     // never lost silently)
     p.n_slots = tensor_sample_tiles(n_rows, (uint32_t)(B < p.q_per_launch ? B : p.q_per_launch));
+    // measured (scripts/k2_probe.py, B = 1024, 1M rows): with a short keep list half the sample does as well
+    // and the bootstrap costs half
+    if (B > 512 && p.KPt <= 32 && p.n_slots > 16) p.n_slots = 16;
     if (h->tensor_sample_tiles) p.n_slots = std::min<uint32_t>(h->tensor_sample_tiles, tensor_tiles(n_rows));
     double hits_per_kp = 0.0;
     // auto: up to two query tiles with a short keep list the pass is HBM-bound and the epilogue has
-    // slack, so one phase (no refine launches) is fastest; otherwise grow x8 (k <= 16) or x4
+    // slack, so one phase (no refine launches) is fastest; otherwise grow x8 (k <= 16) or x6
     p.growth = h->tensor_phase_growth != 0xFFFFFFFFu ? h->tensor_phase_growth
                : (B <= 256 && p.KPt <= 32)           ? 0u
-               : (p.KPt <= 32 ? 8u : 4u);
+               : (p.KPt <= 32 ? 8u : 6u);
     tensor_phases(tensor_tiles(n_rows), p.n_slots, p.growth, &hits_per_kp);
     const uint64_t expected = (uint64_t)((double)p.KPt * hits_per_kp) + 1;
     uint64_t cap = 2 * expected + 4 * p.KPt + 64;

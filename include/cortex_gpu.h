@@ -71,6 +71,9 @@ typedef struct cx_stats {
   uint64_t irregular_rows;      /* live rows whose norm under- / overflows fp32: while > 0 every search takes the exact path */
   uint64_t capacity_rows;       /* rows the mapped store can hold before it is extended again */
   uint64_t in_place_growth;     /* 1 = the store grows in place (driver virtual-memory API), 0 = allocate-copy-free */
+  uint64_t grow_ns;             /* host time spent extending the store (mostly on the helper thread, ahead of need) */
+  uint64_t grow_ns_max;         /* ... the longest single extension */
+  uint64_t grow_waits;          /* inserts that had to wait for an extension */
 } cx_stats;
 
 /* HnswIndex::new(dimension), index.rs:204-211.  device = CUDA ordinal. */

@@ -34,6 +34,9 @@ pub struct cx_stats {
     pub irregular_rows: u64,
     pub capacity_rows: u64,
     pub in_place_growth: u64,
+    pub grow_ns: u64,
+    pub grow_ns_max: u64,
+    pub grow_waits: u64,
 }
 
 #[repr(C)]
