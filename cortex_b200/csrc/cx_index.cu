@@ -568,10 +568,9 @@ cx_status cx::index_insert(cx_index* h, const uint8_t* ids, const float* rows, u
     if (n > 1) fresh.reserve(n);
     for (uint64_t i = 0; i < n; ++i) {
       const Id128 key = load_id(ids + 16 * i);
-      auto it = h->id2row.find(key);
-      if (it != h->id2row.end()) {
-        tgt[i] = it->second;
-        overwritten.push_back(it->second);
+      if (const uint32_t* row = h->id2row.find(key)) {
+        tgt[i] = *row;
+        overwritten.push_back(*row);
         continue;
       }
       if (n > 1) {
@@ -691,13 +690,13 @@ extern "C" cx_status cx_insert(cx_index* h, const uint8_t id[16], const float* e
 cx_status cx::index_remove(cx_index* h, const uint8_t id[16]) {
   Id128 key = load_id(id);
   h->orphan_meta.erase(key);
-  auto it = h->id2row.find(key);
-  if (it == h->id2row.end()) return CX_OK;  // index.rs:316-323: never an error
+  const uint32_t* found = h->id2row.find(key);
+  if (!found) return CX_OK;  // index.rs:316-323: never an error
   CU(cudaSetDevice(h->device));
   cx_status st = settle(h);
   if (st != CX_OK) return st;
-  uint32_t r = it->second;
-  h->id2row.erase(it);
+  uint32_t r = *found;
+  h->id2row.erase(key);
   launch_count_irregular(h->dRnorm, h->dMeta, r, 1, -1, h->d_irr, h->mut_stream);  // while the row still counts as live
   h->h_meta[r] |= META_DEAD;
   h->n_live--;
@@ -720,15 +719,15 @@ cx_status cx::index_set_metadata(cx_index* h, const uint8_t id[16], const char* 
   if (k > META_KIND_MASK) return fail(CX_ERR_VALIDATION, "more than 256 distinct node kinds");
   uint32_t a = h->agents.intern(agent);
   Id128 key = load_id(id);
-  auto it = h->id2row.find(key);
-  if (it == h->id2row.end()) {  // the metadata map is independent of the vector map (index.rs:219-222)
+  const uint32_t* found = h->id2row.find(key);
+  if (!found) {  // the metadata map is independent of the vector map (index.rs:219-222)
     h->orphan_meta[key] = {k, a};
     return CX_OK;
   }
   CU(cudaSetDevice(h->device));
   cx_status st = settle(h);
   if (st != CX_OK) return st;
-  uint32_t r = it->second;
+  uint32_t r = *found;
   h->h_meta[r] = meta_word(true, k) | (h->h_meta[r] & META_DEAD);
   h->h_agent[r] = a;
   st = stage(h, 8);

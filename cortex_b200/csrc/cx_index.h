@@ -46,6 +46,37 @@ inline Id128 load_id(const uint8_t* p) {
   return k;
 }
 
+// id -> row.  256 independent tables picked by the hash, so that a table never rehashes more than 1/256th of
+// the ids at once (one big table stalls an insert for ~0.2 s when it rehashes at a few million rows).
+class IdMap {
+ public:
+  uint32_t* find(const Id128& k) {
+    auto& m = sub_[slot(k)];
+    auto it = m.find(k);
+    return it == m.end() ? nullptr : &it->second;
+  }
+  const uint32_t* find(const Id128& k) const {
+    const auto& m = sub_[slot(k)];
+    auto it = m.find(k);
+    return it == m.end() ? nullptr : &it->second;
+  }
+  bool count(const Id128& k) const { return find(k) != nullptr; }
+  bool emplace(const Id128& k, uint32_t row) { return sub_[slot(k)].emplace(k, row).second; }
+  void erase(const Id128& k) { sub_[slot(k)].erase(k); }
+  void clear() {
+    for (auto& m : sub_) m.clear();
+  }
+  size_t size() const {
+    size_t n = 0;
+    for (const auto& m : sub_) n += m.size();
+    return n;
+  }
+
+ private:
+  static size_t slot(const Id128& k) { return (Id128Hash()(k) >> 24) & 255u; }
+  std::unordered_map<Id128, uint32_t, Id128Hash> sub_[256];
+};
+
 struct Interner {
   std::vector<std::string> strs;
   std::unordered_map<std::string, uint32_t> map;
@@ -165,7 +196,7 @@ struct cx_index {
   std::vector<uint8_t> h_ids;
   std::vector<uint32_t> h_meta, h_agent;
   std::vector<uint64_t> h_seq;
-  std::unordered_map<cx::Id128, uint32_t, cx::Id128Hash> id2row;
+  cx::IdMap id2row;
   std::unordered_map<cx::Id128, std::pair<uint32_t, uint32_t>, cx::Id128Hash> orphan_meta;
   cx::Interner kinds, agents;
   cudaStream_t mut_stream = nullptr;

@@ -45,8 +45,7 @@ void build_filter(const cx_index* h, const cx_filter* f, FilterHost* out) {
   }
   if (f->has_exclude && f->exclude_ids) {
     for (uint32_t i = 0; i < f->n_exclude; ++i) {
-      auto it = h->id2row.find(load_id(f->exclude_ids + 16 * i));
-      if (it != h->id2row.end()) out->excl_rows.push_back(it->second);
+      if (const uint32_t* row = h->id2row.find(load_id(f->exclude_ids + 16 * i))) out->excl_rows.push_back(*row);
     }
   }
 }
@@ -1250,8 +1249,7 @@ extern "C" cx_status cx_autolink_batch(cx_index* h, const uint8_t* new_ids, cons
   for (uint64_t b = 0; b < B; ++b) self[b] = 0xFFFFFFFFu;
   if (new_ids)
     for (uint64_t b = 0; b < B; ++b) {
-      auto it = h->id2row.find(load_id(new_ids + 16 * b));
-      if (it != h->id2row.end()) self[b] = it->second;
+      if (const uint32_t* row = h->id2row.find(load_id(new_ids + 16 * b))) self[b] = *row;
     }
   cudaStream_t s = wo->stream;
   CU(cudaMemcpyAsync(d + o_q, embeddings, B * h->dim * 4, cudaMemcpyHostToDevice, s));

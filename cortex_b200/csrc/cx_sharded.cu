@@ -82,7 +82,7 @@ struct ShardSet {
   std::vector<char> peer;  // shard s can store into the merge device's memory
   int merge_dev = 0;
   uint64_t next_seq = 0;
-  std::unordered_map<Id128, uint16_t, Id128Hash> id2shard;
+  IdMap id2shard;
   std::vector<std::unique_ptr<Worker>> workers;
   std::mutex mu;
   std::vector<MergeWs*> free_ws;
@@ -496,9 +496,8 @@ cx_status shard_insert(cx_index* h, const uint8_t* ids, const float* rows, uint6
     std::vector<uint64_t> dup_of(n, ~0ull);
     for (uint64_t i = 0; i < n; ++i) {
       const Id128 key = load_id(ids + 16 * i);
-      auto it = S->id2shard.find(key);
-      if (it != S->id2shard.end()) {
-        where[i] = it->second;
+      if (const uint32_t* sh_of = S->id2shard.find(key)) {
+        where[i] = (uint16_t)*sh_of;
         continue;
       }
       auto f = seen.find(key);
@@ -566,7 +565,7 @@ cx_status shard_insert(cx_index* h, const uint8_t* ids, const float* rows, uint6
   for (uint64_t i = 0; i < n; ++i) {
     const Id128 key = load_id(ids + 16 * i);
     if (st != CX_OK && !S->sh[where[i]]->id2row.count(key)) continue;
-    if (S->id2shard.emplace(key, where[i]).second)
+    if (S->id2shard.emplace(key, where[i]))
       for (uint32_t s = 0; s < W; ++s)  // metadata that waited for this id was applied by the receiving shard
         if (s != where[i] && !S->sh[s]->orphan_meta.empty()) S->sh[s]->orphan_meta.erase(key);
   }
@@ -577,20 +576,19 @@ cx_status shard_insert(cx_index* h, const uint8_t* ids, const float* rows, uint6
 cx_status shard_remove(cx_index* h, const uint8_t id[16]) {
   ShardSet* S = h->shards;
   const Id128 key = load_id(id);
-  auto it = S->id2shard.find(key);
-  if (it == S->id2shard.end()) {
+  const uint32_t* sh_of = S->id2shard.find(key);
+  if (!sh_of) {
     for (cx_index* c : S->sh) c->orphan_meta.erase(key);
     return CX_OK;
   }
-  cx_status st = index_remove(S->sh[it->second], id);
-  if (st == CX_OK) S->id2shard.erase(it);
+  cx_status st = index_remove(S->sh[*sh_of], id);
+  if (st == CX_OK) S->id2shard.erase(key);
   return st;
 }
 
 cx_status shard_set_metadata(cx_index* h, const uint8_t id[16], const char* kind, const char* agent) {
   ShardSet* S = h->shards;
-  auto it = S->id2shard.find(load_id(id));
-  if (it != S->id2shard.end()) return index_set_metadata(S->sh[it->second], id, kind, agent);
+  if (const uint32_t* sh_of = S->id2shard.find(load_id(id))) return index_set_metadata(S->sh[*sh_of], id, kind, agent);
   // metadata for an id that has no vector (yet): every shard remembers it, whichever receives the row
   // later applies it.  Kind / agent strings are interned per shard, filters are built per shard.
   for (cx_index* c : S->sh) {
@@ -941,11 +939,10 @@ cx_status shard_autolink_batch(cx_index* h, const uint8_t* new_ids, const float*
     self[b] = ~0ull;
     if (!new_ids) continue;
     const Id128 key = load_id(new_ids + 16 * b);
-    auto it = S->id2shard.find(key);
-    if (it == S->id2shard.end()) continue;
-    cx_index* c = S->sh[it->second];
-    auto r = c->id2row.find(key);
-    if (r != c->id2row.end()) self[b] = c->h_seq[r->second];
+    const uint32_t* sh_of = S->id2shard.find(key);
+    if (!sh_of) continue;
+    cx_index* c = S->sh[*sh_of];
+    if (const uint32_t* row = c->id2row.find(key)) self[b] = c->h_seq[*row];
   }
   CU(cudaMemcpyAsync(d + o_self, self, B * 8, cudaMemcpyHostToDevice, mw->stream));
   shard_autolink_kernel<<<(unsigned)((B + 127) / 128), 128, 0, mw->stream>>>(
