@@ -26,19 +26,13 @@
 namespace cx {
 
 constexpr int SEL_THREADS = 512;
-constexpr int SEL_MAX_BATCH = 32;         // rows rescored per staging round (fewer for long rows)
+constexpr int SEL_PAR = 128;              // rows rescored side by side (one thread per row)
+constexpr uint32_t SEL_STAGE_FLOATS = 128 * 65;  // [rows][W + 1]: 128 x 64, 64 x 128 or 32 x 256 floats per chunk
 constexpr int SEL_MAX_KS = 256;
 constexpr uint32_t SEL_K2 = 1024;         // survivors that can be ordered
 constexpr uint32_t SEL_STAGE = 2048;      // radix-select staging words
 constexpr uint32_t SEL_RANK_MAX = 256;    // up to this many survivors are ordered by rank counting (no barriers)
 constexpr double SCORE_QUANTUM_MARGIN = 1.1920928955078125e-7;  // 2^-23: twice the score quantum below 0.5
-
-// rows per staging round: as many as fit 64 KB of shared memory, a power of two <= 32
-__host__ __device__ inline uint32_t select_batch(uint32_t ld) {
-  uint32_t b = SEL_MAX_BATCH;
-  while (b > 4 && (size_t)b * (ld + 1) * 4 > 64 * 1024) b >>= 1;
-  return b;
-}
 
 struct SelectParams {
   StoreView st;
@@ -70,7 +64,7 @@ __host__ __device__ inline SelectLayout select_layout(uint32_t ld) {
   L.q = o;
   o += (size_t)ld * 4;
   L.stage = o;
-  o += (size_t)select_batch(ld) * (ld + 1) * 4;
+  o += (size_t)SEL_STAGE_FLOATS * 4;
   o = (o + 7) & ~(size_t)7;
   L.e = o;
   o += (size_t)SEL_MAX_KS * (8 + 4 + 4 + 4);
@@ -174,44 +168,71 @@ __global__ void __launch_bounds__(SEL_THREADS) select_rescore_kernel(const Selec
   const float na = s_na;
   uint32_t KS = min(min(M, p.KP), (uint32_t)SEL_MAX_KS);
 
-  // ---- 2. exact rescore of keys[lo, hi), SEL_BATCH rows per round ---------------------
-  const uint32_t warp = tid >> 5, lane = tid & 31, nwarps = SEL_THREADS / 32;
-  const uint32_t sstride = ld + 1;
+  // ---- 2. exact rescore of keys[lo, hi) ----------------------------------------------------------------
+  // Up to SEL_PAR rows at a time, ALL of them in parallel: the rows are staged into shared memory in
+  // column chunks of W dimensions ([rows][W], W = 256 / 128 / 64 for <= 32 / 64 / 128 rows), one thread per
+  // row carries that row's strict left-to-right fold (index.rs:172) across the chunks, and the next chunk is
+  // already on its way from HBM (in registers) while the current one is folded.  The order of operations
+  // inside a row is exactly the reference's; only independent rows run side by side.
   auto rescore = [&](uint32_t lo, uint32_t hi) {
-    const uint32_t batch = select_batch(ld);
-    for (uint32_t base = lo; base < hi; base += batch) {
-      const uint32_t nb = min(batch, hi - base);
-      for (uint32_t j = warp; j < nb; j += nwarps) {
-        const uint32_t row = key_row(keys[base + j]);
-        const float* g = p.st.E + (size_t)row * ld;
-        uint32_t d = lane;
-        for (; d + 7 * 32 < ld; d += 8 * 32) {  // eight loads in flight per lane
-          float x[8];
+    const uint32_t n_dims = p.qlen < dim ? p.qlen : dim;
+    for (uint32_t base = lo; base < hi; base += SEL_PAR) {
+      const uint32_t nb = min((uint32_t)SEL_PAR, hi - base);
+      const uint32_t W = nb <= 32 ? 256u : nb <= 64 ? 128u : 64u;   // floats per row per chunk
+      const uint32_t W4 = W >> 2, sstride = W + 1;
+      const uint32_t n_chunks = (ld + W - 1) / W;
+      // element e of a chunk = (row e / W4, float4 e % W4); thread tid owns e = tid + i * SEL_THREADS, i < 4
+      float4 nxt[4];
+      auto fetch = [&](uint32_t c) {
+        const uint32_t w4 = min(W4, (ld - c * W) >> 2);
 #pragma unroll
-          for (int u = 0; u < 8; ++u) x[u] = __ldg(g + d + u * 32);
-#pragma unroll
-          for (int u = 0; u < 8; ++u) stage[j * sstride + d + u * 32] = x[u];
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t e = tid + i * SEL_THREADS, r = e / W4, f = e % W4;
+          if (r < nb && f < w4) {
+            const uint32_t row = key_row(keys[base + r]);
+            nxt[i] = __ldg(reinterpret_cast<const float4*>(p.st.E + (size_t)row * ld + c * W) + f);
+          }
         }
-        for (; d < ld; d += 32) stage[j * sstride + d] = __ldg(g + d);
+      };
+      float dot = 0.0f;
+      fetch(0);
+      for (uint32_t c = 0; c < n_chunks; ++c) {
+        const uint32_t w4 = min(W4, (ld - c * W) >> 2);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t e = tid + i * SEL_THREADS, r = e / W4, f = e % W4;
+          if (r < nb && f < w4) {
+            float* d = stage + r * sstride + 4 * f;
+            d[0] = nxt[i].x;
+            d[1] = nxt[i].y;
+            d[2] = nxt[i].z;
+            d[3] = nxt[i].w;
+          }
+        }
+        __syncthreads();
+        if (c + 1 < n_chunks) fetch(c + 1);  // in flight while this chunk is folded
+        if (tid < nb) {
+          const float* r = stage + tid * sstride;
+          const float* qq = q_s + c * W;
+          const uint32_t d0 = c * W;
+          const uint32_t n = n_dims > d0 ? min(W, n_dims - d0) : 0u;
+          uint32_t d = 0;
+          for (; d + 8 <= n; d += 8) {
+            float a[8], b[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              a[j] = qq[d + j];
+              b[j] = r[d + j];
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dot = ref_fold(dot, a[j], b[j]);
+          }
+          for (; d < n; ++d) dot = ref_fold(dot, qq[d], r[d]);
+        }
+        __syncthreads();
       }
-      __syncthreads();
       if (tid < nb) {
         const uint32_t row = key_row(keys[base + tid]);
-        const float* r = stage + tid * sstride;
-        const uint32_t n = p.qlen < dim ? p.qlen : dim;
-        float dot = 0.0f;
-        uint32_t d = 0;
-        for (; d + 8 <= n; d += 8) {
-          float a[8], b[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            a[j] = q_s[d + j];
-            b[j] = r[d + j];
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j) dot = ref_fold(dot, a[j], b[j]);
-        }
-        for (; d < n; ++d) dot = ref_fold(dot, q_s[d], r[d]);
         const float nbm = __ldg(p.st.norm + row);
         const float sim = __fdiv_rn(dot, __fmul_rn(na, nbm));
         const float dist = __fsub_rn(1.0f, sim);
