@@ -98,6 +98,38 @@ impl GpuVectorIndex {
         }).collect()).collect())
     }
 
+    /// The start-up loop (serve.rs:105-123 / api.rs:55-69) in one call: `values` = the raw values of the
+    /// redb `nodes` table back to back, `offsets[i]..offsets[i+1]` = value i.  Every live node with an
+    /// embedding is inserted newest first; the returned status per node tells the caller which nodes
+    /// (non-empty metadata) it has to decode itself (4 = CX_NODE_NEEDS_HOST_DECODE).
+    pub fn load_nodes(&mut self, values: &[u8], offsets: &[u64]) -> Result<(Vec<u8>, [u64; 6])> {
+        let n = offsets.len().saturating_sub(1);
+        let (mut status, mut counts) = (vec![0u8; n], [0u64; 6]);
+        check(unsafe {
+            sys::cx_load_nodes(self.h, values.as_ptr(), offsets.as_ptr(), n as u64, status.as_mut_ptr(),
+                               counts.as_mut_ptr())
+        })?;
+        Ok((status, counts))
+    }
+
+    /// apply_score_decay (vector/scoring.rs:84-114) for the candidates of one query, plus the re-rank of
+    /// the search handler (http/routes.rs:945-949): returns (decayed scores, order best first).
+    /// `idle_seconds[i]` = (now - node.last_accessed_at).num_seconds(), `kind_rate[i]` =
+    /// config.by_kind.get(kind).unwrap_or(config.daily_rate).
+    pub fn apply_score_decay(&self, cfg: &sys::cx_decay_config, recency_bias: f32, raw: &[f32], idle_seconds: &[i64],
+                             access_count: &[u64], kind_rate: &[f64]) -> Result<(Vec<f32>, Vec<u32>)> {
+        let n = raw.len();
+        if idle_seconds.len() != n || access_count.len() != n || kind_rate.len() != n {
+            return Err(CortexError::Validation("apply_score_decay: array lengths differ".into()));
+        }
+        let (mut out, mut order) = (vec![0f32; n], vec![0u32; n]);
+        check(unsafe {
+            sys::cx_apply_score_decay(self.h, cfg, recency_bias, n as u64, n as u32, raw.as_ptr(), idle_seconds.as_ptr(),
+                                      access_count.as_ptr(), kind_rate.as_ptr(), out.as_mut_ptr(), order.as_mut_ptr())
+        })?;
+        Ok((out, order))
+    }
+
     /// HnswIndex::new(dimension), index.rs:204-211
     pub fn new(dimension: usize) -> Result<Self> {
         Self::on_device(dimension, 0)
