@@ -121,30 +121,36 @@ cx_status VmArray::ensure(size_t bytes, size_t used, cudaStream_t s) {
     const size_t upto = align_up(bytes, g);
     if (upto > reserved)
       return fail(CX_ERR_CUDA, "embedding store: %zu bytes exceed the %zu reserved for this device", upto, reserved);
-    const size_t add = upto - mapped;
+    // slices of at most 256 MB: the driver holds its lock while it maps, and kernel launches of
+    // concurrent searches wait for that lock -- short holds keep them flowing
+    const size_t slice = align_up((size_t)256 << 20, g);
     const CUmemAllocationProp prop = vm_prop(device);
-    CUmemGenericAllocationHandle hd = 0;
-    CUresult r = vm_api().create(&hd, add, &prop, 0);
-    if (r != CUDA_SUCCESS) return fail(CX_ERR_CUDA, "cuMemCreate(%zu bytes) failed (%d): out of device memory", add, (int)r);
-    const CUdeviceptr at = reinterpret_cast<CUdeviceptr>(p) + mapped;
-    r = vm_api().map(at, add, 0, hd, 0);
-    if (r != CUDA_SUCCESS) {
-      vm_api().release(hd);
-      return fail(CX_ERR_CUDA, "cuMemMap failed (%d)", (int)r);
+    while (mapped < upto) {
+      const size_t add = upto - mapped < slice ? upto - mapped : slice;
+      CUmemGenericAllocationHandle hd = 0;
+      CUresult r = vm_api().create(&hd, add, &prop, 0);
+      if (r != CUDA_SUCCESS)
+        return fail(CX_ERR_CUDA, "cuMemCreate(%zu bytes) failed (%d): out of device memory", add, (int)r);
+      const CUdeviceptr at = reinterpret_cast<CUdeviceptr>(p) + mapped;
+      r = vm_api().map(at, add, 0, hd, 0);
+      if (r != CUDA_SUCCESS) {
+        vm_api().release(hd);
+        return fail(CX_ERR_CUDA, "cuMemMap failed (%d)", (int)r);
+      }
+      CUmemAccessDesc acc;
+      memset(&acc, 0, sizeof acc);
+      acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+      acc.location.id = device;
+      acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+      r = vm_api().set_access(at, add, &acc, 1);
+      if (r != CUDA_SUCCESS) {
+        vm_api().unmap(at, add);
+        vm_api().release(hd);
+        return fail(CX_ERR_CUDA, "cuMemSetAccess failed (%d)", (int)r);
+      }
+      chunks.push_back({(unsigned long long)hd, mapped, add});
+      mapped += add;
     }
-    CUmemAccessDesc acc;
-    memset(&acc, 0, sizeof acc);
-    acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
-    acc.location.id = device;
-    acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
-    r = vm_api().set_access(at, add, &acc, 1);
-    if (r != CUDA_SUCCESS) {
-      vm_api().unmap(at, add);
-      vm_api().release(hd);
-      return fail(CX_ERR_CUDA, "cuMemSetAccess failed (%d)", (int)r);
-    }
-    chunks.push_back({(unsigned long long)hd, mapped, add});
-    mapped = upto;
     return CX_OK;
   }
   // fallback: allocate, copy what is in use, free
@@ -436,10 +442,14 @@ static cx_status grow(cx_index* h, uint64_t need, bool exact = false) {
 
 // Called at the end of an insert: when the mapped store is nearly used up, map the next extension on a helper
 // thread.  Only in vmm mode (pointers never move; mapping new pages does not touch pages in use).
-static void grow_ahead(cx_index* h) {
+static void grow_ahead(cx_index* h, uint64_t n_new) {
   if (!h->aE.vmm || h->grow_thread.joinable()) return;
   const uint64_t cap = h->cap.load();
   if (h->n_rows + cap / 8 + 1024 < cap) return;  // more than an eighth of the capacity is still free
+  // only streaming ingest is worth running ahead of: a bulk load that just filled what the caller reserved
+  // says nothing about what comes next, and mapping gigabytes behind its back would compete with the
+  // searches that follow
+  if (n_new > cap / 64 + 4096) return;
   uint64_t ncap = cap + (cap / 4 > 4096 ? cap / 4 : 4096);
   if (ncap > h->max_rows) ncap = h->max_rows;
   if (ncap <= cap) return;
@@ -662,7 +672,7 @@ cx_status cx::index_insert(cx_index* h, const uint8_t* ids, const float* rows, u
     }
     h->n_rows += n_new;
     h->n_live += n_new;
-    grow_ahead(h);
+    grow_ahead(h, n_new);
   }
   return mutation_done(h);
 }

@@ -30,12 +30,21 @@ __global__ void pack_topk_kernel(const uint32_t* __restrict__ rows, const float*
   payload[2 * (size_t)i + 1] = w1;
 }
 
-// one CTA per query; W*k candidates ranked by counting (all (ord,row) pairs are distinct)
+// Does slot (x0, x1) come before (ord, row) in the merged order?  (empty slots never do)
+__device__ __forceinline__ bool slot_before(uint64_t x0, uint64_t x1, uint32_t ord, uint64_t row) {
+  if (x0 == 0) return false;
+  const uint32_t xo = (uint32_t)(x0 >> 32);
+  return xo > ord || (xo == ord && x1 < row);
+}
+
+// One CTA per query.  Every rank's list is already in merged order (score desc, NaN last, row asc) with its
+// valid slots first, so the rank of a slot is its own position plus, for every other rank, the number of that
+// rank's slots that come before it: one binary search per (slot, other rank) -- O(W k W log k) per query
+// instead of the (W k)^2 of rank counting, which matters at k = 100 on 8 GPUs.  No shared memory, any k.
 __global__ void merge_topk_kernel(const uint64_t* __restrict__ gathered, uint32_t W, uint32_t B, uint32_t k,
                                   int64_t* __restrict__ out_rows, float* __restrict__ out_score,
                                   float* __restrict__ out_dist, uint32_t* __restrict__ out_n,
                                   uint64_t* __restrict__ out_unverified) {
-  extern __shared__ uint64_t sm[];  // [W*k][2]
   const uint32_t b = blockIdx.x, tid = threadIdx.x, n = W * k;
   const size_t stride = 2 * (size_t)B * k + 2;  // words per rank: slots + trailer
   __shared__ uint32_t s_valid;
@@ -45,25 +54,26 @@ __global__ void merge_topk_kernel(const uint64_t* __restrict__ gathered, uint32_
     for (uint32_t w = 0; w < W; ++w) t += gathered[(size_t)w * stride + stride - 2];
     *out_unverified = t;
   }
-  for (uint32_t i = tid; i < n; i += blockDim.x) {
-    const uint32_t w = i / k, j = i % k;
-    const uint64_t* src = gathered + (size_t)w * stride + 2 * ((size_t)b * k + j);
-    sm[2 * i] = src[0];
-    sm[2 * i + 1] = src[1];
-  }
   __syncthreads();
   uint32_t valid = 0;
   for (uint32_t i = tid; i < n; i += blockDim.x) {
-    const uint64_t w0 = sm[2 * i], w1 = sm[2 * i + 1];
+    const uint32_t w = i / k, j = i % k;
+    const uint64_t* src = gathered + (size_t)w * stride + 2 * ((size_t)b * k + j);
+    const uint64_t w0 = src[0], w1 = src[1];
     if (w0 == 0) continue;
     ++valid;
     const uint32_t ord = (uint32_t)(w0 >> 32);
-    uint32_t rank = 0;
-    for (uint32_t j = 0; j < n; ++j) {
-      const uint64_t x0 = sm[2 * j];
-      if (x0 == 0) continue;
-      const uint32_t xo = (uint32_t)(x0 >> 32);
-      rank += (xo > ord) || (xo == ord && sm[2 * j + 1] < w1);
+    uint32_t rank = j;
+    for (uint32_t x = 0; x < W; ++x) {
+      if (x == w) continue;
+      const uint64_t* L = gathered + (size_t)x * stride + 2 * (size_t)b * k;
+      uint32_t lo = 0, hi = k;  // first slot of rank x that does NOT come before mine
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (slot_before(L[2 * mid], L[2 * mid + 1], ord, w1)) lo = mid + 1;
+        else hi = mid;
+      }
+      rank += lo;
     }
     if (rank < k) {
       const size_t o = (size_t)b * k + rank;
@@ -246,10 +256,8 @@ extern "C" cx_status cx_merge_topk_device(const uint64_t* d_gathered, uint32_t w
   if (!d_gathered || !d_out_rows || !d_out_score || !d_out_distance || !d_out_n)
     return fail(CX_ERR_VALIDATION, "null device buffer");
   if (!B || !k || !world) return CX_OK;
-  const size_t smem = (size_t)world * k * 16;
-  if (smem > 200 * 1024) return fail(CX_ERR_VALIDATION, "world * k too large for the merge kernel");
-  CU(cudaFuncSetAttribute(merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  merge_topk_kernel<<<(unsigned)B, 128, smem, (cudaStream_t)stream>>>(d_gathered, world, (uint32_t)B, (uint32_t)k,
+  const unsigned threads = world * k >= 256 ? 256u : 128u;
+  merge_topk_kernel<<<(unsigned)B, threads, 0, (cudaStream_t)stream>>>(d_gathered, world, (uint32_t)B, (uint32_t)k,
                                                                       d_out_rows, d_out_score, d_out_distance, d_out_n,
                                                                       d_out_unverified);
   CU(cudaGetLastError());

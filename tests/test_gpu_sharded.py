@@ -77,7 +77,8 @@ def test_cuda_merge_equals_torch_merge_with_ties_nan_and_short_lists():
         dist[torch.rand(B, k) < 0.1] = float("nan")
         dist, _ = torch.sort(dist, dim=1)
         score = (1.0 - dist).clamp(0, 1)
-        rows = torch.stack([torch.randperm(1000)[:k] for _ in range(B)]).int()
+        # a rank's list is in merged order: score descending, NaN last, equal scores by ascending row
+        rows = torch.stack([torch.sort(torch.randperm(1000)[:k]).values for _ in range(B)]).int()
         n = torch.randint(0, k + 1, (B,)).int()
         r, s, dd, nn = rows.cuda(), score.cuda(), dist.cuda(), n.cuda()
         payloads.append(cuda_pack(L, r, s, dd, nn, w * 1000))
