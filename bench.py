@@ -117,13 +117,20 @@ def ids_for(n, start=0):
 # ----------------------------------------------------------------------------------
 # synthetic data (clustered unit-norm rows), generated with torch so
 # that 1M x 384 takes a fraction of a second on the GPU and a few seconds on CPU.
-def make_corpus_torch(n, d, seed, device):
+def make_corpus_torch(n, d, seed, device, cluster_seed=None, n_clusters=None):
+    """n clustered unit-norm rows.  cluster_seed / n_clusters: draw the centroids from their own seed, so that
+    several calls (the shards of one corpus, the chunks of a big one) sample the SAME clusters with different
+    noise -- a row-partitioned corpus, not unrelated corpora side by side."""
     import torch
 
     g = torch.Generator(device=device)
     g.manual_seed(seed)
-    n_clusters = max(1, n // 64)
-    cent = torch.randn((n_clusters, d), generator=g, device=device, dtype=torch.float32)
+    n_clusters = max(1, n // 64) if n_clusters is None else max(1, int(n_clusters))
+    gc = g
+    if cluster_seed is not None:
+        gc = torch.Generator(device=device)
+        gc.manual_seed(cluster_seed)
+    cent = torch.randn((n_clusters, d), generator=gc, device=device, dtype=torch.float32)
     cent /= cent.norm(dim=1, keepdim=True)
     out = torch.empty((n, d), device=device, dtype=torch.float32)
     chunk = 1 << 18
@@ -420,7 +427,12 @@ def main():
     pk = peaks()
 
     # ---- data: this rank's shard + the (shared) query batch ---------------------
-    corpus = make_corpus_torch(a.rows, a.dim, SEED + 7919 * rank, dev)
+    # one clustered corpus, row-partitioned: every rank draws from the same clusters (its own noise), so a
+    # query has near neighbours in every shard, as it would in a corpus dealt out row by row
+    def shard_corpus(r):
+        return make_corpus_torch(a.rows, a.dim, SEED + 7919 * r, dev, cluster_seed=SEED, n_clusters=a.rows // 64)
+
+    corpus = shard_corpus(rank)
     q_all = make_queries_torch(corpus, max(256, a.batch), SEED)
     if world > 1:
         dist.broadcast(q_all, src=0)
@@ -659,7 +671,7 @@ def main():
         o_ix = OracleIndex(a.dim, faithful_copy=True)
         o_ix.insert_batch(ids_for(a.rows), corpus_np)
         for r in range(1, world):  # the other ranks' shards, regenerated from their seeds
-            c_r = make_corpus_torch(a.rows, a.dim, SEED + 7919 * r, dev).cpu().numpy()
+            c_r = shard_corpus(r).cpu().numpy()
             o_ix.insert_batch(ids_for(a.rows, r * a.rows), c_r)
             del c_r
         q_np = q_all.cpu().numpy()
@@ -699,11 +711,13 @@ def main():
         rows_s = a.strong_rows // world
         ixs = GpuVectorIndex(a.dim, device=local_rank)
         ixs.reserve(rows_s)
-        chunk = 2_000_000
+        chunk = 250_000  # the corpus is the same 250k-row chunks whatever N is: rank r holds chunks r*rows_s/chunk ...
         q_src = None
         for s0 in range(0, rows_s, chunk):
             n = min(chunk, rows_s - s0)
-            c = make_corpus_torch(n, a.dim, SEED + 31 * (s0 // chunk) + 104729 * rank, dev)
+            g_chunk = (rank * rows_s + s0) // chunk
+            c = make_corpus_torch(n, a.dim, SEED + 31 * g_chunk + 104729, dev, cluster_seed=SEED + 3,
+                                  n_clusters=a.strong_rows // 64)
             ixs.insert_batch_device(ids_for(n, rank * rows_s + s0), c)
             if s0 == 0 and rank == 0:
                 q_src = c[:min(n, 65536)].clone()
@@ -764,7 +778,8 @@ def main():
         q4 = None
         for s0 in range(0, rows4, 625_000):
             n = min(625_000, rows4 - s0)
-            c = make_corpus_torch(n, d4, SEED + 17 * (s0 // 625_000) + 7919 * rank, dev)
+            c = make_corpus_torch(n, d4, SEED + 17 * (s0 // 625_000) + 7919 * rank, dev, cluster_seed=SEED + 4,
+                                  n_clusters=50_000_000 // 64)
             c = c.to(torch.bfloat16).to(torch.float32)  # the corpus is bf16: rows hold bf16 values
             ix4.insert_batch_device(ids_for(n, rank * rows4 + s0), c)
             if s0 == 0:
@@ -794,13 +809,19 @@ def main():
         n4 = 20
         e40.record()
         pend = []
+        t_b = t_e = 0.0
         for i in range(n4):
+            tb = time.perf_counter()
             pend.append(sh4.search_begin(q4, k4, slot=i % 2))
+            t_b += time.perf_counter() - tb
             if len(pend) >= 2:
+                te = time.perf_counter()
                 sh4.search_end(pend.pop(0))
+                t_e += time.perf_counter() - te
         while pend:
             sh4.search_end(pend.pop(0))
         e41.record()
+        print(f"[cfg4 rank {rank}] host ms per step: begin {1e3 * t_b / n4:.3f} end {1e3 * t_e / n4:.3f}", file=sys.stderr)
         barrier()
         s41 = ix4.stats()
         ms4 = max_over_ranks(e40.elapsed_time(e41)) / n4
@@ -825,7 +846,7 @@ def main():
             try:
                 ixm = GpuVectorIndex(a.dim, devices=list(range(world)))
                 for r in range(world):
-                    c_r = make_corpus_torch(a.rows, a.dim, SEED + 7919 * r, dev)
+                    c_r = shard_corpus(r)
                     ixm.insert_batch_device(ids_for(a.rows, r * a.rows), c_r)
                     del c_r
                 torch.cuda.empty_cache()
