@@ -716,8 +716,9 @@ def main():
         for s0 in range(0, rows_s, chunk):
             n = min(chunk, rows_s - s0)
             g_chunk = (rank * rows_s + s0) // chunk
+            # clusters of ~1024 rows: every shard of an 8-GPU run still holds more than k = 100 members of each
             c = make_corpus_torch(n, a.dim, SEED + 31 * g_chunk + 104729, dev, cluster_seed=SEED + 3,
-                                  n_clusters=a.strong_rows // 64)
+                                  n_clusters=a.strong_rows // 1024)
             ixs.insert_batch_device(ids_for(n, rank * rows_s + s0), c)
             if s0 == 0 and rank == 0:
                 q_src = c[:min(n, 65536)].clone()
@@ -779,7 +780,7 @@ def main():
         for s0 in range(0, rows4, 625_000):
             n = min(625_000, rows4 - s0)
             c = make_corpus_torch(n, d4, SEED + 17 * (s0 // 625_000) + 7919 * rank, dev, cluster_seed=SEED + 4,
-                                  n_clusters=50_000_000 // 64)
+                                  n_clusters=50_000_000 // 1024)
             c = c.to(torch.bfloat16).to(torch.float32)  # the corpus is bf16: rows hold bf16 values
             ix4.insert_batch_device(ids_for(n, rank * rows4 + s0), c)
             if s0 == 0:

@@ -633,8 +633,11 @@ cx_status run_search(cx_index* h, Workspace* ws, const FilterHost& fh, const Sea
       for (size_t c0 = 0; c0 < redo.size(); c0 += RETRY_CHUNK) {
         const uint32_t nc = (uint32_t)std::min<size_t>(RETRY_CHUNK, redo.size() - c0);
         CU(cudaMemcpyAsync(sb.qmap, redo.data() + c0, nc * 4, cudaMemcpyHostToDevice, s));
-        for (uint32_t g0 = 0; g0 < nc; g0 += 4) {
-          const uint32_t ng = nc - g0 < 4 ? nc - g0 : 4;
+        // queries per pass over the matrix: eight with the normal keep count, four with the wide one (its lists
+        // are four times as long and share the same shared memory)
+        const uint32_t per_pass = (tier == 0 && stream_scan_smem(h->ld, 8, KPr) != 0) ? 8u : 4u;
+        for (uint32_t g0 = 0; g0 < nc; g0 += per_pass) {
+          const uint32_t ng = nc - g0 < per_pass ? nc - g0 : per_pass;
           cr.keys = sb.retry_keys + (size_t)g0 * cr.cap;
           CU(launch_stream_scan(st, qv, 0, ng, flt, cr, h->sm_count, s, sb.qmap + g0));
           h->launches += 1;

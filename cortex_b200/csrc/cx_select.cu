@@ -28,10 +28,10 @@ namespace cx {
 constexpr int SEL_THREADS = 512;
 constexpr int SEL_PAR = 128;              // rows rescored side by side (one thread per row)
 constexpr uint32_t SEL_STAGE_FLOATS = 128 * 65;  // [rows][W + 1]: 128 x 64, 64 x 128 or 32 x 256 floats per chunk
-constexpr int SEL_MAX_KS = 256;
+constexpr int SEL_MAX_KS = 512;            // rows that can be rescored for one query (head + the +-eps band)
 constexpr uint32_t SEL_K2 = 1024;         // survivors that can be ordered
 constexpr uint32_t SEL_STAGE = 2048;      // radix-select staging words
-constexpr uint32_t SEL_RANK_MAX = 256;    // up to this many survivors are ordered by rank counting (no barriers)
+constexpr uint32_t SEL_RANK_MAX = 512;    // up to this many survivors are ordered by rank counting (no barriers)
 constexpr double SCORE_QUANTUM_MARGIN = 1.1920928955078125e-7;  // 2^-23: twice the score quantum below 0.5
 
 struct SelectParams {
@@ -121,12 +121,12 @@ __global__ void __launch_bounds__(SEL_THREADS) select_rescore_kernel(const Selec
   }
 
   // ---- 1. survivors -> keys[0..M), ordered ---------------------------------------------
-  // Only the best n_keep candidates can matter: the KS = KP that are rescored plus as many
+  // Only the best n_keep candidates can matter: the KS = KP that are rescored plus up to three times as many
   // again for the +-eps band around the k-th result (step 3).  A radix select finds that cut;
   // what it leaves behind is bounded by `cut` and enters U.
   unsigned long long U = gt;
   uint32_t cut = 0;  // radix cut (score ord); 0 = none
-  const uint32_t n_keep = min(min(2 * p.KP, (uint32_t)SEL_MAX_KS), n_src);
+  const uint32_t n_keep = min(min(4 * p.KP, (uint32_t)SEL_MAX_KS), n_src);
   if (n_src > n_keep) {
     auto get = [&](uint32_t i) {
       const uint64_t key = src[i];
