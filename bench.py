@@ -137,7 +137,8 @@ def make_corpus_torch(n, d, seed, device, cluster_seed=None, n_clusters=None):
     for s in range(0, n, chunk):
         e = min(n, s + chunk)
         which = torch.randint(0, n_clusters, (e - s,), generator=g, device=device)
-        scale = 0.035 * (0.3 + 1.3 * torch.rand((e - s, 1), generator=g, device=device))
+        # noise per coordinate scaled so that the intra-cluster cosines (0.7 .. 0.99) do not depend on the dimension
+        scale = 0.035 * (384.0 / d) ** 0.5 * (0.3 + 1.3 * torch.rand((e - s, 1), generator=g, device=device))
         x = torch.randn((e - s, d), generator=g, device=device, dtype=torch.float32) * scale + cent[which]
         x /= x.norm(dim=1, keepdim=True)
         out[s:e] = x
