@@ -563,9 +563,34 @@ def main():
         return a.batch * world * n / dt, res
 
     e2e_value, e2e_res = time_e2e(step_e2e, a.steps)
-    e2e_pageable = None
+    e2e_single, e2e_pageable, e2e_callers = e2e_value, None, 1
     if world == 1:
         e2e_pageable, _ = time_e2e(lambda: step_e2e(h_q_pageable), a.steps)
+        # the reference serves searches from many threads under read guards (serve.rs:101, routes.rs:906); the
+        # library is re-entrant, so two callers overlap one call's copies and select step with the other's scan
+        # -- the host-side counterpart of the two searches in flight of `value`
+        e2e_callers = 2
+        per = max(1, a.steps // e2e_callers)
+        start = threading.Barrier(e2e_callers + 1)
+        done = []
+
+        def caller(i):
+            torch.cuda.set_device(local_rank)
+            q_i = h_q_np if i == 0 else np.array(h_q_np, copy=True)
+            for _ in range(3):
+                ix.search_batch_arrays(q_i, a.k)
+            start.wait()
+            for _ in range(per):
+                ix.search_batch_arrays(q_i, a.k)
+            done.append(time.perf_counter())
+        ths = [threading.Thread(target=caller, args=(i,)) for i in range(e2e_callers)]
+        for t in ths:
+            t.start()
+        start.wait()
+        t0 = time.perf_counter()
+        for t in ths:
+            t.join()
+        e2e_value = a.batch * per * e2e_callers / (max(done) - t0)
     clk = clocks.stop() if rank == 0 else None
     h2d = a.batch * a.dim * 4
     d2h = a.batch * a.k * (16 + 4 + 4) + a.batch * 4
@@ -738,14 +763,40 @@ def main():
             dist.broadcast(q_new, src=0)
         # the cycle in batches of one tensor-pass launch group (148 x 128 new nodes)
         QB = 148 * 128
-        cyc = [autolink_cycle_fn(ixs, rows_s, q_new[s0:s0 + QB].contiguous()) for s0 in range(0, nq_s, QB)]
+        chunks = [q_new[s0:s0 + QB].contiguous() for s0 in range(0, nq_s, QB)]
         ixs.set_option("profile", 1)
+        if world == 1:
+            cyc = [autolink_cycle_fn(ixs, rows_s, qc) for qc in chunks]
 
-        def cycle_all():
-            res = None
-            for c in cyc:
-                res = c()
-            return res
+            def cycle_all():
+                res = None
+                for c in cyc:
+                    res = c()
+                return res
+        else:
+            # two batches in flight: the exchange + merge + post-pass of one overlaps the scan of the next
+            outs_s = {}
+
+            def ls(q, k):
+                outs_s[(0, q.shape[0])] = ixs.search_batch_device(q, k, stream=stream.cuda_stream, out=outs_s.get((0, q.shape[0])))
+                return outs_s[(0, q.shape[0])]
+
+            def lsb(q, k, slot=0):
+                key = (slot, q.shape[0])
+                outs_s[key], t = ixs.search_batch_device_begin(q, k, stream=stream.cuda_stream, out=outs_s.get(key))
+                return outs_s[key], t
+
+            sh_s = ShardedSearch(ls, row_offset=rank * rows_s, local_begin=lsb, local_end=ixs.search_batch_device_end,
+                                 ticket_ok_ptr=ixs.ticket_ok_ptr)
+
+            def cycle_all():
+                pend, res = None, None
+                for i, qc in enumerate(chunks):
+                    p = sh_s.autolink_begin(qc, 100, slot=i % 2)
+                    if pend is not None:
+                        res = sh_s.autolink_end(pend, None, 0.75, 50)
+                    pend = p
+                return sh_s.autolink_end(pend, None, 0.75, 50)
         res = cycle_all()
         barrier()
         ss0 = ixs.stats()
@@ -768,7 +819,7 @@ def main():
                   "tflops_per_gpu_whole_cycle": tf, "frac_of_sustained_bf16_whole_cycle": tf / pk["bf16_tflops_sustained"],
                   "scan_ms_per_cycle": scan_ms, "scan_share_of_cycle": scan_ms / ms_c,
                   "fallbacks": ss1["fallbacks"] - ss0["fallbacks"]}
-        del ixs, cyc
+        del ixs
         torch.cuda.empty_cache()
 
     # ---- configs[3] as named: 50M x 1024-d bf16-valued corpus over 8 GPUs, B = 256, top-100 ----------------
@@ -946,7 +997,8 @@ def main():
         "roofline": roof, "small_batch": small, "autolink": autolink, "strong_scaling": strong, "cfg4": cfg4,
         "single_process": single, "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "buffers": "pinned host memory", "pageable_value": e2e_pageable},
+                "buffers": "pinned host memory" if e2e_callers == 1 else "caller 0 pinned, caller 1 pageable",
+                "concurrent_callers": e2e_callers, "single_caller_value": e2e_single, "pageable_value": e2e_pageable},
         "gpu_launches": st1["kernel_launches"] - st0["kernel_launches"],
         "graph_launches": st1["graph_launches"] - st0["graph_launches"],
         "per_rank": per_rank, "host_cpus": os.cpu_count(),

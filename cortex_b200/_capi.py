@@ -54,6 +54,9 @@ class CxStats(C.Structure):
         ("grow_ns", C.c_uint64),
         ("grow_ns_max", C.c_uint64),
         ("grow_waits", C.c_uint64),
+        ("unverified_overflow", C.c_uint64),
+        ("unverified_near_ties", C.c_uint64),
+        ("unverified_other", C.c_uint64),
     ]
 
 

@@ -1047,6 +1047,12 @@ extern "C" cx_status cx_get_stats(const cx_index* hc, cx_stats* out) {
   cx_status st = settle(h);  // the irregular-row count of the last mutation
   if (st != CX_OK) return st;
   index_add_stats(h, out);
+  CU(cudaSetDevice(h->device));
+  uint64_t why[3];
+  select_why_read(why);
+  out->unverified_overflow = why[0];
+  out->unverified_near_ties = why[1];
+  out->unverified_other = why[2];
   return CX_OK;
 }
 

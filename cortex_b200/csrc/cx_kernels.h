@@ -75,6 +75,9 @@ cudaError_t launch_stream_scan(const StoreView& st, const QueryView& qv, uint32_
 // It also computes the query norms (qv.qnorm / qv.rqnorm are written) and re-zeroes cv.cnt / cv.gtau.
 // scale_by_rqn: the pass's keys are cosine * |q| (streaming pass) instead of cosine.
 size_t select_smem(uint32_t cap, uint32_t ld);
+// diagnostics: queries that failed verification on the current device since process start, by reason
+// ([0] list overflow, [1] near-ties denser than the rescored band, [2] other)
+void select_why_read(uint64_t out[3]);
 cudaError_t launch_select_rescore(const StoreView& st, const QueryView& qv, uint32_t q0, uint32_t nq,
                                   const CandView& cv, const ResultView& rv, float eps_cos, int scale_by_rqn,
                                   cudaStream_t s, const uint32_t* qmap = nullptr);

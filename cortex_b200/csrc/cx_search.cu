@@ -274,8 +274,8 @@ Plan make_plan(const cx_index* h, uint64_t B, uint32_t qlen, uint32_t ldq, uint3
     p.groups = tensor_groups(B, h->sm_count);
     p.q_per_launch = *std::max_element(p.groups.begin(), p.groups.end());
     // the cut-off comes from a sample of S rows, so about KPt * rows / S keys per query clear it;
-    // twice that plus slack (excess is detected by the select kernel and sent to a fallback,
-    // never lost silently)
+    // the list capacity is a multiple of that (below; excess is detected by the select kernel and sent to a
+    // fallback, never lost silently)
     p.n_slots = tensor_sample_tiles(n_rows, (uint32_t)(B < p.q_per_launch ? B : p.q_per_launch));
     // measured (scripts/k2_probe.py, B = 1024, 1M rows): with a short keep list half the sample does as well
     // and the bootstrap costs half
@@ -289,7 +289,10 @@ Plan make_plan(const cx_index* h, uint64_t B, uint32_t qlen, uint32_t ldq, uint3
                : (p.KPt <= 32 ? 8u : 6u);
     tensor_phases(tensor_tiles(n_rows), p.n_slots, p.growth, &hits_per_kp);
     const uint64_t expected = (uint64_t)((double)p.KPt * hits_per_kp) + 1;
-    uint64_t cap = 2 * expected + 4 * p.KPt + 64;
+    // four times the expectation: when a query's KP-th neighbour sits in the dense background of unrelated
+    // rows, the 2 * eps the refined cut-off is lowered by admits two to three times the rows the plain
+    // order-statistics estimate predicts (measured on 1024-d shards: lists of 2x overflowed for 3 % of queries)
+    uint64_t cap = 4 * expected + 4 * p.KPt + 64;
     if (cap > 16384) cap = 16384;
     p.cap = (uint32_t)cap;
   }

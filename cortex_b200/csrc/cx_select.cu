@@ -72,6 +72,19 @@ __host__ __device__ inline SelectLayout select_layout(uint32_t ld) {
   return L;
 }
 
+// why queries fail verification (diagnostics, per device since process start): [0] candidate list overflowed
+// or was truncated, [1] the margin test failed (near-ties around rank k denser than the rescored band),
+// [2] everything else (too few candidates, degenerate query norm, NaN / zero k-th score)
+__device__ unsigned long long g_select_why[4];
+
+void select_why_read(uint64_t out[3]) {
+  unsigned long long v[4] = {0, 0, 0, 0};
+  if (cudaMemcpyFromSymbol(v, g_select_why, sizeof v) != cudaSuccess) (void)cudaGetLastError();
+  out[0] = v[0];
+  out[1] = v[1];
+  out[2] = v[2];
+}
+
 __global__ void __launch_bounds__(SEL_THREADS) select_rescore_kernel(const SelectParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const SelectLayout L = select_layout(p.st.ld);
@@ -298,10 +311,12 @@ __global__ void __launch_bounds__(SEL_THREADS) select_rescore_kernel(const Selec
   if (tid == 0) {
     p.rv.n[q] = min(k, KS);
     bool ok = KS >= k && !overflow && !truncated && na >= NORM_REGULAR_MIN && na <= NORM_REGULAR_MAX;
+    int why = (overflow || truncated) ? 0 : 2;
     if (ok) {
       const float sk = s_scorek, simk = s_simk;
       if (sk != sk) ok = false;
       else if (U != 0ull) {
+        why = sk > 0.0f ? 1 : 2;
         float u = float_from_ord(key_ord(U));
         if (p.scale_by_rqn) u = u * __frcp_rn(na);
         // every row that was not rescored has a reference cosine <= u + eps.  Its SCORE must be strictly
@@ -312,6 +327,7 @@ __global__ void __launch_bounds__(SEL_THREADS) select_rescore_kernel(const Selec
       }
     }
     p.rv.ok[q] = ok ? 1u : 0u;
+    if (!ok) atomicAdd(&g_select_why[why], 1ull);
     p.cnt[q] = 0;   // leave the workspace ready for the next pass
     p.gtau[q] = 0ull;
   }

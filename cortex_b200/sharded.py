@@ -185,7 +185,22 @@ class ShardedSearch:
         max_edges_per_node per node (:261).  Returns (global_rows [B,me] int64, score [B,me], n [B]);
         identical on every rank."""
         grow, score, _, n = self.search(new_embeddings, k)
-        B = grow.shape[0]
+        return self._autolink_filter(grow, score, n, self_global_rows, threshold, max_edges_per_node, 0)
+
+    def autolink_begin(self, new_embeddings: torch.Tensor, k: int = 100, slot: int = 0):
+        """Pipelined form for a cycle that runs in several batches: enqueue the sharded search of this batch and
+        return; autolink_end finishes it.  With alternating slots the exchange + merge of one batch overlaps
+        the scan of the next."""
+        return self.search_begin(new_embeddings, k, slot), slot
+
+    def autolink_end(self, pending, self_global_rows: Optional[torch.Tensor] = None, threshold: float = 0.75,
+                     max_edges_per_node: int = 50):
+        pend, slot = pending
+        grow, score, _, n = self.search_end(pend)
+        return self._autolink_filter(grow, score, n, self_global_rows, threshold, max_edges_per_node, slot)
+
+    def _autolink_filter(self, grow, score, n, self_global_rows, threshold, max_edges_per_node, slot):
+        B, k = grow.shape[0], grow.shape[1]
         me = min(int(max_edges_per_node), grow.shape[1])
         if grow.is_cuda:
             # one CUDA kernel on the merged lists (cx_merge.cu), behind the sharded search on the same stream
@@ -194,7 +209,7 @@ class ShardedSearch:
             from . import _capi
             L = _capi.load()
             dev = grow.device
-            key = ("al", B, k, me, str(dev))
+            key = ("al", B, k, me, str(dev), slot)
             buf = self._bufs.get(key)
             if buf is None:
                 buf = (torch.empty((B, me), dtype=torch.int64, device=dev),

@@ -74,6 +74,9 @@ typedef struct cx_stats {
   uint64_t grow_ns;             /* host time spent extending the store (mostly on the helper thread, ahead of need) */
   uint64_t grow_ns_max;         /* ... the longest single extension */
   uint64_t grow_waits;          /* inserts that had to wait for an extension */
+  /* why fast-pass results failed verification (and were redone on a tighter path), on this device since
+   * process start: candidate list overflow / near-ties around rank k denser than the rescored band / other */
+  uint64_t unverified_overflow, unverified_near_ties, unverified_other;
 } cx_stats;
 
 /* HnswIndex::new(dimension), index.rs:204-211.  device = CUDA ordinal. */

@@ -37,6 +37,9 @@ pub struct cx_stats {
     pub grow_ns: u64,
     pub grow_ns_max: u64,
     pub grow_waits: u64,
+    pub unverified_overflow: u64,
+    pub unverified_near_ties: u64,
+    pub unverified_other: u64,
 }
 
 #[repr(C)]

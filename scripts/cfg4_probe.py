@@ -1,45 +1,49 @@
-import sys, time, json, torch
-sys.path.insert(0, "/root/repo")
-import bench
-from cortex_b200 import GpuVectorIndex
+#!/usr/bin/env python
+"""configs[3] shard shape (1024-d bf16-valued rows, B=256, top-100): which path answers, how many queries need a
+retry, what a step costs.  usage: python scripts/cfg4_probe.py [rows]"""
+import json
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, __file__.rsplit("/", 2)[0])
+import bench  # noqa: E402
+from cortex_b200 import GpuVectorIndex  # noqa: E402
+
 dev = torch.device("cuda", 0)
-rows, d, B, k = 1_000_000, 1024, 256, 100
+rows = int(sys.argv[1]) if len(sys.argv) > 1 else 6_250_000
+d, B, k = 1024, 256, 100
 ix = GpuVectorIndex(d)
+ix.reserve(rows)
 q = None
-for s0 in range(0, rows, 500_000):
-    c = bench.make_corpus_torch(500_000, d, 5 + s0, dev).to(torch.bfloat16).to(torch.float32)
-    ix.insert_batch_device(bench.ids_for(500_000, s0), c)
+for s0 in range(0, rows, 625_000):
+    n = min(625_000, rows - s0)
+    c = bench.make_corpus_torch(n, d, bench.SEED + 17 * (s0 // 625_000), dev, cluster_seed=bench.SEED + 4,
+                                n_clusters=50_000_000 // 1024)
+    c = c.to(torch.bfloat16).to(torch.float32)
+    ix.insert_batch_device(bench.ids_for(n, s0), c)
     if q is None:
-        q = bench.make_queries_torch(c, B, 3)
+        q = bench.make_queries_torch(c, B, bench.SEED)
     del c
 s = torch.cuda.current_stream().cuda_stream
 ix.set_option("profile", 1)
-for graphs in (1, 0):
-    ix.set_option("graphs", graphs)
+for force in (0, 1):
+    if force:
+        ix.set_option("force_path", 1)
     out = None
+    for _ in range(2):
+        out = ix.search_batch_device(q, k, stream=s, out=out)
+    torch.cuda.synchronize()
+    st0 = ix.stats()
+    t0 = time.perf_counter()
     for _ in range(3):
         out = ix.search_batch_device(q, k, stream=s, out=out)
     torch.cuda.synchronize()
-    st0 = ix.stats(); t0 = time.perf_counter()
-    for _ in range(10):
-        out = ix.search_batch_device(q, k, stream=s, out=out)
-    torch.cuda.synchronize()
-    dt = (time.perf_counter() - t0) / 10 * 1e3
+    dt = (time.perf_counter() - t0) / 3 * 1e3
     st1 = ix.stats()
-    print(json.dumps({"mode": "one-call", "graphs": graphs, "ms": dt, "scan_ms": (st1["pass_kernel_ns"] - st0["pass_kernel_ns"]) / 10e6,
-                      "fallbacks": st1["fallbacks"] - st0["fallbacks"], "stream": st1["queries_stream"] - st0["queries_stream"], "exact": st1["queries_exact"] - st0["queries_exact"], "launches": (st1["kernel_launches"] - st0["kernel_launches"]) / 10}), flush=True)
-    outs = [None, None]
-    pend = []
-    torch.cuda.synchronize(); st0 = ix.stats(); t0 = time.perf_counter()
-    for i in range(10):
-        outs[i % 2], t = ix.search_batch_device_begin(q, k, stream=s, out=outs[i % 2])
-        pend.append(t)
-        if len(pend) >= 2:
-            ix.search_batch_device_end(pend.pop(0))
-    while pend:
-        ix.search_batch_device_end(pend.pop(0))
-    torch.cuda.synchronize()
-    dt = (time.perf_counter() - t0) / 10 * 1e3
-    st1 = ix.stats()
-    print(json.dumps({"mode": "begin/end", "graphs": graphs, "ms": dt, "scan_ms": (st1["pass_kernel_ns"] - st0["pass_kernel_ns"]) / 10e6,
-                      "fallbacks": st1["fallbacks"] - st0["fallbacks"], "stream": st1["queries_stream"] - st0["queries_stream"]}), flush=True)
+    print(json.dumps({"force_path": force, "ms": dt, **{kk: (st1[kk] - st0[kk]) / 3 for kk in
+                      ("fallbacks", "queries_stream", "queries_tensor", "queries_exact", "kernel_launches")},
+                      "why": [st1[w] - st0[w] for w in ("unverified_overflow", "unverified_near_ties", "unverified_other")]}), flush=True)
+    sc = out[1].cpu().numpy()
+    print("score range of the 100 results, first 6 queries:", [(float(sc[i, 0]), float(sc[i, 99])) for i in range(6)])
