@@ -46,7 +46,8 @@ for pair, growth, epi, sample in [(int(p), int(g), int(e), int(sm)) for p in a.p
         ix.set_option("tensor_phase_growth", growth)
         ix.set_option("tensor_epi_warps", epi)
         ix.set_option("tensor_sample_tiles", sample)
-        ix.set_option("tensor_debug", dbg)
+        if dbg or a.debug_modes != "0":
+            ix.set_option("tensor_debug", dbg)   # exists in the -DCX_PROBE build only
         reps = a.reps if dbg == 0 else 2
         out = ix.search_batch_device(q, a.k, out=out)
         torch.cuda.synchronize()
@@ -66,5 +67,6 @@ for pair, growth, epi, sample in [(int(p), int(g), int(e), int(sm)) for p in a.p
             ix.set_option("tensor_debug", -1)  # prints the effective SM clock of the last launch to stderr
         print(json.dumps({"call_us": call_us, "sample": sample, "epi": epi, "pair": pair, "growth": growth, "debug": dbg, "fallbacks": s1["fallbacks"] - s0["fallbacks"], "us_per_launch": us, "tflops": tf, "launches": n,
                           "batch": a.batch, "k": a.k}), flush=True)
-ix.set_option("tensor_debug", 0)
+if a.debug_modes != "0":
+    ix.set_option("tensor_debug", 0)
 ix.set_option("tensor_pair", 0)
