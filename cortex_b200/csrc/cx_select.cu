@@ -25,14 +25,22 @@
 
 namespace cx {
 
-constexpr int SEL_THREADS = 512;
-constexpr int SEL_PAR = 128;              // rows rescored side by side (one thread per row)
-constexpr uint32_t SEL_STAGE_FLOATS = 128 * 65;  // [rows][W + 1]: 128 x 64, 64 x 128 or 32 x 256 floats per chunk
 constexpr int SEL_MAX_KS = 512;            // rows that can be rescored for one query (head + the +-eps band)
-constexpr uint32_t SEL_K2 = 1024;         // survivors that can be ordered
 constexpr uint32_t SEL_STAGE = 2048;      // radix-select staging words
-constexpr uint32_t SEL_RANK_MAX = 512;    // up to this many survivors are ordered by rank counting (no barriers)
 constexpr double SCORE_QUANTUM_MARGIN = 1.1920928955078125e-7;  // 2^-23: twice the score quantum below 0.5
+
+// Two launch shapes.  SMALL (keep count <= 32, i.e. k <= 16: interactive searches, search_batch top-10):
+// 256 threads, rows rescored 32 at a time in chunks of 128 dimensions, ~31 KB of shared memory -- seven
+// queries share an SM, so a batch of 1024 is resident at once and the kernel takes about as long as ONE
+// query's chain of dependent steps.  LARGE (k = 100 auto-link scans, wide retries): 512 threads, 128 rows at
+// a time.
+template <bool SMALL>
+struct SelShape {
+  static constexpr int T = SMALL ? 256 : 512;
+  static constexpr int PAR = SMALL ? 32 : 128;                        // rows rescored side by side
+  static constexpr uint32_t STAGE_FLOATS = SMALL ? 32 * 129 : 128 * 65;  // [rows][W + 1]
+};
+__host__ __device__ inline bool select_small(uint32_t KP) { return KP <= 32; }
 
 struct SelectParams {
   StoreView st;
@@ -52,22 +60,27 @@ struct SelectParams {
 
 struct SelectLayout {
   size_t keys, rstage, q, stage, e, total;
+  uint32_t n_keep_max, keys_cap;
 };
 
-__host__ __device__ inline SelectLayout select_layout(uint32_t ld) {
+__host__ __device__ inline SelectLayout select_layout(uint32_t ld, uint32_t KP) {
   SelectLayout L;
+  L.n_keep_max = 4 * KP < (uint32_t)SEL_MAX_KS ? 4 * KP : (uint32_t)SEL_MAX_KS;  // head + band
+  L.keys_cap = 256;  // survivors incl. ties at the cut: a power of two (the bitonic fallback pads to one)
+  while (L.keys_cap < 2 * L.n_keep_max) L.keys_cap <<= 1;
   size_t o = 0;
   L.keys = o;
-  o += (size_t)SEL_K2 * 8;
+  o += (size_t)L.keys_cap * 8;
   L.rstage = o;
   o += (size_t)SEL_STAGE * 4;
   L.q = o;
   o += (size_t)ld * 4;
+  o = (o + 15) & ~(size_t)15;
   L.stage = o;
-  o += (size_t)SEL_STAGE_FLOATS * 4;
+  o += (size_t)(select_small(KP) ? SelShape<true>::STAGE_FLOATS : SelShape<false>::STAGE_FLOATS) * 4;
   o = (o + 7) & ~(size_t)7;
   L.e = o;
-  o += (size_t)SEL_MAX_KS * (8 + 4 + 4 + 4);
+  o += (size_t)L.n_keep_max * (8 + 4 + 4 + 4);
   L.total = o;
   return L;
 }
@@ -85,17 +98,21 @@ void select_why_read(uint64_t out[3]) {
   out[2] = v[2];
 }
 
-__global__ void __launch_bounds__(SEL_THREADS) select_rescore_kernel(const SelectParams p) {
+template <bool SMALL>
+__global__ void __launch_bounds__(SelShape<SMALL>::T, SMALL ? 5 : 2) select_rescore_kernel(const SelectParams p) {
+  constexpr int SEL_THREADS = SelShape<SMALL>::T;
+  constexpr int SEL_PAR = SelShape<SMALL>::PAR;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const SelectLayout L = select_layout(p.st.ld);
+  const SelectLayout L = select_layout(p.st.ld, p.KP);
+  const uint32_t SEL_K2 = L.keys_cap;
   uint64_t* keys = reinterpret_cast<uint64_t*>(smem_raw + L.keys);
   uint32_t* rstage = reinterpret_cast<uint32_t*>(smem_raw + L.rstage);
   float* q_s = reinterpret_cast<float*>(smem_raw + L.q);
   float* stage = reinterpret_cast<float*>(smem_raw + L.stage);
   uint64_t* ekey = reinterpret_cast<uint64_t*>(smem_raw + L.e);
-  float* esim = reinterpret_cast<float*>(ekey + SEL_MAX_KS);
-  float* edist = esim + SEL_MAX_KS;
-  float* escore = edist + SEL_MAX_KS;
+  float* esim = reinterpret_cast<float*>(ekey + L.n_keep_max);
+  float* edist = esim + L.n_keep_max;
+  float* escore = edist + L.n_keep_max;
   __shared__ float s_na, s_simk, s_scorek;
   __shared__ uint32_t scratch[260];
   __shared__ uint32_t s_m;
@@ -139,7 +156,7 @@ __global__ void __launch_bounds__(SEL_THREADS) select_rescore_kernel(const Selec
   // what it leaves behind is bounded by `cut` and enters U.
   unsigned long long U = gt;
   uint32_t cut = 0;  // radix cut (score ord); 0 = none
-  const uint32_t n_keep = min(min(4 * p.KP, (uint32_t)SEL_MAX_KS), n_src);
+  const uint32_t n_keep = min(L.n_keep_max, n_src);
   if (n_src > n_keep) {
     auto get = [&](uint32_t i) {
       const uint64_t key = src[i];
@@ -159,7 +176,7 @@ __global__ void __launch_bounds__(SEL_THREADS) select_rescore_kernel(const Selec
   __syncthreads();
   const uint32_t M = min(s_m, SEL_K2);
   const bool truncated = s_m > SEL_K2;
-  if (M <= SEL_RANK_MAX) {
+  if (M <= (uint32_t)SEL_THREADS) {
     // rank counting (keys are distinct): no barriers inside, every thread reads the same key at a time
     uint64_t mine = 0ull;
     uint32_t rank = 0;
@@ -179,11 +196,12 @@ __global__ void __launch_bounds__(SEL_THREADS) select_rescore_kernel(const Selec
     __syncthreads();
   }
   const float na = s_na;
-  uint32_t KS = min(min(M, p.KP), (uint32_t)SEL_MAX_KS);
+  uint32_t KS = min(min(M, p.KP), L.n_keep_max);
 
   // ---- 2. exact rescore of keys[lo, hi) ----------------------------------------------------------------
   // Up to SEL_PAR rows at a time, ALL of them in parallel: the rows are staged into shared memory in
-  // column chunks of W dimensions ([rows][W], W = 256 / 128 / 64 for <= 32 / 64 / 128 rows), one thread per
+  // column chunks of W dimensions ([rows][W]; LARGE: W = 256 / 128 / 64 for <= 32 / 64 / 128 rows, SMALL: 32 rows
+  // x 128), one thread per
   // row carries that row's strict left-to-right fold (index.rs:172) across the chunks, and the next chunk is
   // already on its way from HBM (in registers) while the current one is folded.  The order of operations
   // inside a row is exactly the reference's; only independent rows run side by side.
@@ -191,7 +209,7 @@ __global__ void __launch_bounds__(SEL_THREADS) select_rescore_kernel(const Selec
     const uint32_t n_dims = p.qlen < dim ? p.qlen : dim;
     for (uint32_t base = lo; base < hi; base += SEL_PAR) {
       const uint32_t nb = min((uint32_t)SEL_PAR, hi - base);
-      const uint32_t W = nb <= 32 ? 256u : nb <= 64 ? 128u : 64u;   // floats per row per chunk
+      const uint32_t W = SMALL ? 128u : (nb <= 32 ? 256u : nb <= 64 ? 128u : 64u);   // floats per row per chunk
       const uint32_t W4 = W >> 2, sstride = W + 1;
       const uint32_t n_chunks = (ld + W - 1) / W;
       // element e of a chunk = (row e / W4, float4 e % W4); thread tid owns e = tid + i * SEL_THREADS, i < 4
@@ -297,7 +315,7 @@ __global__ void __launch_bounds__(SEL_THREADS) select_rescore_kernel(const Selec
       float band = simk - p.eps - 2.0f * (float)SCORE_QUANTUM_MARGIN;  // cosine units; covers the verify margin
       if (p.scale_by_rqn) band = band * na;      // streaming-pass keys are cosine * |q|
       uint32_t KS1 = KS;
-      while (KS1 < M && KS1 < (uint32_t)SEL_MAX_KS && float_from_ord(key_ord(keys[KS1])) >= band) ++KS1;
+      while (KS1 < M && KS1 < L.n_keep_max && float_from_ord(key_ord(keys[KS1])) >= band) ++KS1;
       if (KS1 > KS) {
         rescore(KS, KS1);
         KS = KS1;
@@ -560,7 +578,7 @@ size_t threshold_rescore_smem(uint32_t ld) { return threshold_layout(ld).total; 
 
 size_t select_smem(uint32_t cap, uint32_t ld) {
   (void)cap;
-  return select_layout(ld).total + 2048;
+  return select_layout(ld, 128).total + 2048;  // the larger of the two launch shapes
 }
 
 cudaError_t launch_select_rescore(const StoreView& st, const QueryView& qv, uint32_t q0, uint32_t nq,
@@ -590,12 +608,20 @@ cudaError_t launch_select_rescore(const StoreView& st, const QueryView& qv, uint
   p.rv.ok += q0;
   p.eps = eps_cos;
   p.scale_by_rqn = scale_by_rqn;
-  const size_t smem = select_layout(st.ld).total;
+  const size_t smem = select_layout(st.ld, cv.KP).total;
   if (smem > 200 * 1024 || cv.KP > SEL_MAX_KS) return cudaErrorInvalidConfiguration;
-  cudaError_t e =
-      cudaFuncSetAttribute(select_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-  select_rescore_kernel<<<nq, SEL_THREADS, smem, s>>>(p);
+  if (select_small(cv.KP)) {
+    cudaError_t e = cudaFuncSetAttribute(select_rescore_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    // ask for the largest shared-memory carve-out: the point of the small shape is seven queries per SM
+    (void)cudaFuncSetAttribute(select_rescore_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    select_rescore_kernel<true><<<nq, SelShape<true>::T, smem, s>>>(p);
+  } else {
+    cudaError_t e = cudaFuncSetAttribute(select_rescore_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    (void)cudaFuncSetAttribute(select_rescore_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+    select_rescore_kernel<false><<<nq, SelShape<false>::T, smem, s>>>(p);
+  }
   return cudaGetLastError();
 }
 
