@@ -1208,7 +1208,11 @@ extern "C" cx_status cx_autolink_batch_device(cx_index* h, const float* d_embedd
     CU(cudaMemsetAsync(d_out_n, 0, B * 4, (cudaStream_t)stream));
     return CX_OK;
   }
-  const uint64_t kk = k < h->n_rows ? k : h->n_rows;
+  // Only the first max_edges + 1 neighbours can become links: the list is walked best first, the node itself
+  // is skipped (at most one entry), the walk stops at the first score below the threshold or at the cap
+  // (linker/auto_linker.rs:224-264).  Searching for min(k, max_edges + 1) is therefore exact and cheaper.
+  uint64_t kk = k < h->n_rows ? k : h->n_rows;
+  if (kk > (uint64_t)max_edges_per_node + 1) kk = (uint64_t)max_edges_per_node + 1;
   cx_status st = cx_search_batch_device(h, d_embeddings, B, kk, nullptr, d_scratch_rows, d_scratch_score,
                                         d_scratch_distance, nullptr, d_scratch_n, stream);
   if (st != CX_OK) return st;

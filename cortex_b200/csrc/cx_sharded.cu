@@ -910,8 +910,9 @@ cx_status shard_autolink_batch(cx_index* h, const uint8_t* new_ids, const float*
   if (!B || shard_len(h) == 0 || !max_edges_per_node || !k) return CX_OK;
   uint64_t n_rows = 0;
   for (cx_index* c : S->sh) n_rows += c->n_rows;
-  const uint64_t kk = k < n_rows ? k : n_rows;
   const uint32_t me = max_edges_per_node;
+  uint64_t kk = k < n_rows ? k : n_rows;
+  if (kk > (uint64_t)me + 1) kk = (uint64_t)me + 1;  // only the first me + 1 neighbours can become links (exact)
   FanOut f(S);
   cx_status st = fan_topk_begin(h, f, embeddings, nullptr, nullptr, B, h->dim, kk, nullptr);
   if (st != CX_OK) return st;

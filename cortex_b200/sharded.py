@@ -184,14 +184,16 @@ class ShardedSearch:
         -1 = not in the index), keep `score >= threshold` (linker/rules.rs:50), at most
         max_edges_per_node per node (:261).  Returns (global_rows [B,me] int64, score [B,me], n [B]);
         identical on every rank."""
-        grow, score, _, n = self.search(new_embeddings, k)
+        # only the first max_edges + 1 neighbours can become links (best first, self skipped at most once, the
+        # walk stops below the threshold or at the cap): exchanging lists of that length is exact
+        grow, score, _, n = self.search(new_embeddings, min(int(k), int(max_edges_per_node) + 1))
         return self._autolink_filter(grow, score, n, self_global_rows, threshold, max_edges_per_node, 0)
 
-    def autolink_begin(self, new_embeddings: torch.Tensor, k: int = 100, slot: int = 0):
+    def autolink_begin(self, new_embeddings: torch.Tensor, k: int = 100, slot: int = 0, max_edges_per_node: int = 50):
         """Pipelined form for a cycle that runs in several batches: enqueue the sharded search of this batch and
         return; autolink_end finishes it.  With alternating slots the exchange + merge of one batch overlaps
         the scan of the next."""
-        return self.search_begin(new_embeddings, k, slot), slot
+        return self.search_begin(new_embeddings, min(int(k), int(max_edges_per_node) + 1), slot), slot
 
     def autolink_end(self, pending, self_global_rows: Optional[torch.Tensor] = None, threshold: float = 0.75,
                      max_edges_per_node: int = 50):
