@@ -360,7 +360,8 @@ __global__ void __launch_bounds__(SelShape<SMALL>::T, SMALL ? 5 : 2) select_resc
 // result is exact with no verification step; the only failure is a list that overflowed
 // (ok = 0 -> the host reruns that query on the exact path).
 constexpr int THR_THREADS = 512;
-constexpr int THR_BATCH = 16;
+constexpr int THR_PAR = 128;                       // nominees rescored side by side
+constexpr uint32_t THR_STAGE_FLOATS = 128 * 65;    // [rows][W + 1]: 128 x 64, 64 x 128 or 32 x 256 floats per chunk
 constexpr uint32_t THR_MAX = 2048;  // survivors that can be ordered in shared memory
 
 struct ThresholdParams {
@@ -389,8 +390,9 @@ __host__ __device__ inline ThresholdLayout threshold_layout(uint32_t ld) {
   size_t o = 0;
   L.q = o;
   o += (size_t)ld * 4;
+  o = (o + 15) & ~(size_t)15;
   L.stage = o;
-  o += (size_t)THR_BATCH * (ld + 1) * 4;
+  o += (size_t)THR_STAGE_FLOATS * 4;
   o = (o + 7) & ~(size_t)7;
   L.ekey = o;
   o += (size_t)THR_MAX * 8;
@@ -427,44 +429,68 @@ __global__ void __launch_bounds__(THR_THREADS) threshold_rescore_kernel(const Th
   for (uint32_t d = tid; d < ld; d += THR_THREADS) q_s[d] = d < p.qlen ? p.Q[(size_t)q * p.ldq + d] : 0.0f;
   __syncthreads();
   const float na = p.qnorm[q];
-  const uint32_t warp = tid >> 5, lane = tid & 31, nwarps = THR_THREADS / 32;
-  const uint32_t sstride = ld + 1;
-
-  for (uint32_t base = 0; base < n_src; base += THR_BATCH) {
-    const uint32_t nb = min((uint32_t)THR_BATCH, n_src - base);
-    for (uint32_t j = warp; j < nb; j += nwarps) {
-      const uint32_t row = key_row(src[base + j]);
-      const float* g = p.st.E + (size_t)row * ld;
-      uint32_t d = lane;
-      for (; d + 7 * 32 < ld; d += 8 * 32) {
-        float x[8];
+  // All nominees are rescored, THR_PAR rows side by side: the rows are staged in column chunks of W dimensions,
+  // one thread per row carries its strict left-to-right fold (index.rs:172) across the chunks while the next
+  // chunk is already in flight (the scheme of the select kernel above).
+  const uint32_t n_dims = p.qlen < dim ? p.qlen : dim;
+  for (uint32_t base = 0; base < n_src; base += THR_PAR) {
+    const uint32_t nb = min((uint32_t)THR_PAR, n_src - base);
+    const uint32_t W = nb <= 32 ? 256u : nb <= 64 ? 128u : 64u;
+    const uint32_t W4 = W >> 2, sstride = W + 1;
+    const uint32_t n_chunks = (ld + W - 1) / W;
+    float4 nxt[4];
+    auto fetch = [&](uint32_t c) {
+      const uint32_t w4 = min(W4, (ld - c * W) >> 2);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) x[u] = __ldg(g + d + u * 32);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) stage[j * sstride + d + u * 32] = x[u];
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t e = tid + i * THR_THREADS, r = e / W4, f = e % W4;
+        if (r < nb && f < w4) {
+          const uint32_t row = key_row(src[base + r]);
+          nxt[i] = __ldg(reinterpret_cast<const float4*>(p.st.E + (size_t)row * ld + c * W) + f);
+        }
       }
-      for (; d < ld; d += 32) stage[j * sstride + d] = __ldg(g + d);
-    }
-    __syncthreads();
-    if (tid < nb) {
-      const uint32_t row = key_row(src[base + tid]);
-      const bool wanted = by_seq ? __ldg(p.row_seq + row) > my_seq : (row != self && !(p.upper_only && row < self));
-      if (wanted) {
+    };
+    float dot = 0.0f;
+    fetch(0);
+    for (uint32_t c = 0; c < n_chunks; ++c) {
+      const uint32_t w4 = min(W4, (ld - c * W) >> 2);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t e = tid + i * THR_THREADS, r = e / W4, f = e % W4;
+        if (r < nb && f < w4) {
+          float* d = stage + r * sstride + 4 * f;
+          d[0] = nxt[i].x;
+          d[1] = nxt[i].y;
+          d[2] = nxt[i].z;
+          d[3] = nxt[i].w;
+        }
+      }
+      __syncthreads();
+      if (c + 1 < n_chunks) fetch(c + 1);
+      if (tid < nb) {
         const float* r = stage + tid * sstride;
-        const uint32_t n = p.qlen < dim ? p.qlen : dim;
-        float dot = 0.0f;
+        const float* qq = q_s + c * W;
+        const uint32_t d0 = c * W;
+        const uint32_t n = n_dims > d0 ? min(W, n_dims - d0) : 0u;
         uint32_t d = 0;
         for (; d + 8 <= n; d += 8) {
           float a[8], b[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            a[j] = q_s[d + j];
+            a[j] = qq[d + j];
             b[j] = r[d + j];
           }
 #pragma unroll
           for (int j = 0; j < 8; ++j) dot = ref_fold(dot, a[j], b[j]);
         }
-        for (; d < n; ++d) dot = ref_fold(dot, q_s[d], r[d]);
+        for (; d < n; ++d) dot = ref_fold(dot, qq[d], r[d]);
+      }
+      __syncthreads();
+    }
+    if (tid < nb) {
+      const uint32_t row = key_row(src[base + tid]);
+      const bool wanted = by_seq ? __ldg(p.row_seq + row) > my_seq : (row != self && !(p.upper_only && row < self));
+      if (wanted) {
         const float nbm = __ldg(p.st.norm + row);
         const float sim = __fdiv_rn(dot, __fmul_rn(na, nbm));
         const float dist = __fsub_rn(1.0f, sim);

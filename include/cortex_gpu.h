@@ -187,7 +187,9 @@ cx_status cx_search_batch_device_end(cx_index* h, void* ticket, uint64_t* n_redo
  * `score >= threshold` (SimilarityLinkRule, linker/rules.rs:50) in best-first order, at most
  * max_edges_per_node per node (:261).  Outputs are [B][max_edges_per_node]; out_n[b] = links
  * proposed for node b (to-id, score = edge weight).  Storage lookups, structural rules and
- * de-duplication against existing edges stay with the caller. */
+ * de-duplication against existing edges stay with the caller.  (Internally the search asks for
+ * min(k, max_edges_per_node + 1) neighbours: the walk over the best-first list skips at most one entry --
+ * the node itself -- and stops at the cap, so nothing further down can ever become a link.) */
 cx_status cx_autolink_batch(cx_index* h, const uint8_t* new_ids, const float* embeddings, uint64_t B,
                             uint32_t len, uint64_t k, float threshold, uint32_t max_edges_per_node,
                             uint8_t* out_to_ids, float* out_score, uint32_t* out_n);
