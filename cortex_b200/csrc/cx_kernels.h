@@ -3,9 +3,33 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
+#include <mutex>
+
 #include "cx_common.cuh"
 
 namespace cx {
+
+// The opt-in dynamic shared memory limit of a kernel is a per-device function attribute shared by every host thread:
+// it is only ever RAISED (under a lock), so a thread that launches with less can never find it lowered under its feet
+// by a concurrent caller (or a recorded graph find it lowered at replay).  The common case is one relaxed load.
+template <auto Fn>
+cudaError_t raise_dynamic_smem(size_t smem, bool prefer_smem_carveout = false) {
+  static std::atomic<size_t> allowed[64];
+  static std::mutex mu;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return cudaErrorInvalidDevice;
+  if (allowed[dev].load(std::memory_order_acquire) >= smem && smem != 0) return cudaSuccess;
+  std::lock_guard<std::mutex> lk(mu);
+  if (allowed[dev].load(std::memory_order_relaxed) >= smem && smem != 0) return cudaSuccess;
+  e = cudaFuncSetAttribute(Fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  if (prefer_smem_carveout) (void)cudaFuncSetAttribute(Fn, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  allowed[dev].store(smem, std::memory_order_release);
+  return cudaSuccess;
+}
 
 // Device view of the embedding store.
 struct StoreView {

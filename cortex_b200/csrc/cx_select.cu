@@ -594,8 +594,7 @@ cudaError_t launch_threshold_rescore(const StoreView& st, const QueryView& qv, u
   p.total = total ? total + q0 : nullptr;
   const size_t smem = threshold_layout(st.ld).total;
   if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
-  cudaError_t e =
-      cudaFuncSetAttribute(threshold_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = raise_dynamic_smem<threshold_rescore_kernel>(smem);
   if (e != cudaSuccess) return e;
   threshold_rescore_kernel<<<nq, THR_THREADS, smem, s>>>(p);
   return cudaGetLastError();
@@ -637,15 +636,13 @@ cudaError_t launch_select_rescore(const StoreView& st, const QueryView& qv, uint
   const size_t smem = select_layout(st.ld, cv.KP).total;
   if (smem > 200 * 1024 || cv.KP > SEL_MAX_KS) return cudaErrorInvalidConfiguration;
   if (select_small(cv.KP)) {
-    cudaError_t e = cudaFuncSetAttribute(select_rescore_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    // with the largest shared-memory carve-out: the point of the small shape is several queries per SM
+    cudaError_t e = raise_dynamic_smem<select_rescore_kernel<true>>(smem, true);
     if (e != cudaSuccess) return e;
-    // ask for the largest shared-memory carve-out: the point of the small shape is seven queries per SM
-    (void)cudaFuncSetAttribute(select_rescore_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     select_rescore_kernel<true><<<nq, SelShape<true>::T, smem, s>>>(p);
   } else {
-    cudaError_t e = cudaFuncSetAttribute(select_rescore_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = raise_dynamic_smem<select_rescore_kernel<false>>(smem, true);
     if (e != cudaSuccess) return e;
-    (void)cudaFuncSetAttribute(select_rescore_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     select_rescore_kernel<false><<<nq, SelShape<false>::T, smem, s>>>(p);
   }
   return cudaGetLastError();

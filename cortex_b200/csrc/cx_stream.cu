@@ -440,8 +440,7 @@ size_t stream_scan_smem(uint32_t ld, uint32_t nq_pass, uint32_t KP) {
 
 template <int NQ, int KC>
 static cudaError_t launch_one(const StreamParams& p, size_t smem, cudaStream_t s) {
-  cudaError_t e = cudaFuncSetAttribute(stream_scan_kernel<NQ, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem);
+  cudaError_t e = raise_dynamic_smem<stream_scan_kernel<NQ, KC>>(smem);
   if (e != cudaSuccess) return e;
   stream_scan_kernel<NQ, KC><<<p.G, SC_THREADS, smem, s>>>(p);
   return cudaGetLastError();

@@ -712,14 +712,12 @@ static cudaError_t launch_kernel(bool pair, uint32_t units, size_t smem, cudaStr
                                  const CUtensorMap& tmE, const TensorParams& p) {
   constexpr uint32_t threads = (TC_CTRL_WARPS + EW) * 32;
   if (!pair) {
-    cudaError_t e = cudaFuncSetAttribute(tensor_scan_kernel<false, EW, QRES>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = raise_dynamic_smem<tensor_scan_kernel<false, EW, QRES>>(smem);
     if (e != cudaSuccess) return e;
     tensor_scan_kernel<false, EW, QRES><<<units, threads, smem, s>>>(tmQ, tmE, p);
     return cudaGetLastError();
   }
-  cudaError_t e = cudaFuncSetAttribute(tensor_scan_kernel<true, EW, QRES>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = raise_dynamic_smem<tensor_scan_kernel<true, EW, QRES>>(smem);
   if (e != cudaSuccess) return e;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(2 * units, 1, 1);

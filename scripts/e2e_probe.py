@@ -12,12 +12,14 @@ q_all = bench.make_queries_torch(corpus, 1024, bench.SEED)
 ids = np.zeros((rows, 16), np.uint8)
 ids[:, 8:] = np.arange(rows, dtype=np.uint64).astype(">u8").view(np.uint8).reshape(-1, 8)
 ix = GpuVectorIndex(384); ix.reserve(rows); ix.insert_batch_device(ids, corpus)
+graphs = int(os.environ.get("CX_GRAPHS", "1"))
+ix.set_option("graphs", graphs)
 for B in (1, 2, 4, 8, 64, 1024):
     hq = q_all[:B].cpu().numpy()
     hp = torch.empty((B, 384), dtype=torch.float32).pin_memory(); hp.copy_(q_all[:B]); hpn = hp.numpy()
     for name, buf in (("pageable", hq), ("pinned", hpn)):
         for _ in range(3): ix.search_batch_arrays(buf, 10)
-        t0 = time.perf_counter(); n = 30
+        t0 = time.perf_counter(); n = 200 if B <= 64 else 50
         for _ in range(n): ix.search_batch_arrays(buf, 10)
         dt = (time.perf_counter() - t0) / n
-        print(json.dumps({"B": B, "buf": name, "ms": dt * 1e3, "qps": B / dt}), flush=True)
+        print(json.dumps({"graphs": graphs, "B": B, "buf": name, "ms": dt * 1e3, "qps": B / dt}), flush=True)

@@ -43,7 +43,8 @@ for pair, growth, epi, sample in [(int(p), int(g), int(e), int(sm)) for p in a.p
                                   for g in a.growth.split(",") for e in a.epi.split(",") for sm in a.sample.split(",")]:
     for dbg in [int(x) for x in a.debug_modes.split(",")]:
         ix.set_option("tensor_pair", pair)
-        ix.set_option("tensor_phase_growth", growth)
+        if growth >= 0:
+            ix.set_option("tensor_phase_growth", growth)   # < 0: leave the automatic choice
         ix.set_option("tensor_epi_warps", epi)
         ix.set_option("tensor_sample_tiles", sample)
         if dbg or a.debug_modes != "0":
