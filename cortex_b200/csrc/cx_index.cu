@@ -1074,6 +1074,10 @@ cx_status cx::index_set_option(cx_index* h, const char* key, int64_t value) {
     h->tensor_tune.pair = value != 0;
     return CX_OK;
   }
+  if (!strcmp(key, "tensor_leftover_sms")) {  // 0: only the regular (query tiles x row splits) grid of CTAs
+    h->tensor_tune.use_leftover_sms = value != 0;
+    return CX_OK;
+  }
   if (!strcmp(key, "tensor_phase_growth")) {
     if (value < 0 || value > 1024) return fail(CX_ERR_VALIDATION, "tensor_phase_growth must be 0..1024");
     h->tensor_phase_growth = (uint32_t)value;

@@ -131,6 +131,7 @@ struct TensorTuning {
   int pair = 0;
   int epi_warps = 8;
   int debug = 0;
+  int use_leftover_sms = 1;  // give the SMs the (query tiles x row splits) grid leaves over a share of the rows
 };
 void tensor_report_clock();  // CX_PROBE builds: print the effective SM clock of block 0 in the last debug-mode launch
 size_t tensor_scratch_bytes(int sm_count);

@@ -895,7 +895,8 @@ cx_status search_host(cx_index* h, const float* queries, uint64_t B, uint32_t ql
     hs = fnv(hs, &f.has_agent, sizeof f.has_agent);
     const uint64_t misc[8] = {(uint64_t)(uintptr_t)h_block,  (uint64_t)h->force_path,      (uint64_t)h->tensor_min_batch,
                               (uint64_t)h->tensor_phase_growth, (uint64_t)h->profile,
-                              (uint64_t)(h->tensor_tune.pair * 64 + h->tensor_tune.epi_warps + 1024 * h->tensor_tune.debug) +
+                              (uint64_t)(h->tensor_tune.pair * 64 + h->tensor_tune.epi_warps + 1024 * h->tensor_tune.debug +
+                                          4096 * h->tensor_tune.use_leftover_sms) +
                                   ((uint64_t)h->tensor_sample_tiles << 32),
                               (uint64_t)(uintptr_t)h->dE, 0x486f7374ull /* host call */};
     hs = fnv(hs, misc, sizeof misc);
@@ -1155,7 +1156,8 @@ cx_status cx::index_search_device(cx_index* h, const float* d_queries, uint32_t 
                                (uint64_t)(uintptr_t)d_out_n,       (uint64_t)(uintptr_t)ws->hp,
                                (uint64_t)h->force_path,            (uint64_t)h->tensor_min_batch,
                                (uint64_t)h->tensor_phase_growth,   (uint64_t)h->profile,
-                               (uint64_t)(h->tensor_tune.pair * 64 + h->tensor_tune.epi_warps + 1024 * h->tensor_tune.debug) +
+                               (uint64_t)(h->tensor_tune.pair * 64 + h->tensor_tune.epi_warps + 1024 * h->tensor_tune.debug +
+                                          4096 * h->tensor_tune.use_leftover_sms) +
                                    ((uint64_t)h->tensor_sample_tiles << 32),
                                (uint64_t)t->fh.excl_rows.size()};
     hs = fnv(hs, misc, sizeof misc);

@@ -62,6 +62,7 @@ struct TensorParams {
   uint32_t n_slots;     // tiles visited: a contiguous tile range in SCAN mode, the sample size in DUMP mode
   uint32_t tile0;       // SCAN mode: first tile of this launch's range
   uint32_t n_qt, n_es;
+  uint32_t n_tail, n_rem;  // the last n_tail slots belong to the n_rem CTAs left over by the n_qt x n_es grid
   uint32_t nq_valid;
   uint32_t stages;
   uint32_t mode;
@@ -291,7 +292,8 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   const uint32_t bar_empty = smem_u32(bars + 1 + TC_MAX_STAGES);
   const uint32_t bar_tfull = smem_u32(bars + 1 + 2 * TC_MAX_STAGES);
   const uint32_t bar_tempty = smem_u32(bars + 3 + 2 * TC_MAX_STAGES);
-  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 5 + 2 * TC_MAX_STAGES);
+  const uint32_t bar_qfree = smem_u32(bars + 5 + 2 * TC_MAX_STAGES);
+  uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 6 + 2 * TC_MAX_STAGES);
 
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;   // 0 = leader
@@ -304,6 +306,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 
   if (tid == 0) {
     mbar_init(bar_q, 1);
+    mbar_init(bar_qfree, 1);
     for (uint32_t s = 0; s < S; ++s) {
       mbar_init(bar_full + 8 * s, 1);
       mbar_init(bar_empty + 8 * s, 1);
@@ -324,46 +327,72 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_s;
 
-  // this unit: query tile group g, slots [s_begin, s_end); slot -> tile is the identity in
-  // SCAN mode and a stride over the whole corpus in DUMP mode
-  const uint32_t g = unit % p.n_qt, es = unit / p.n_qt;
-  const uint32_t qt = PAIR ? 2 * g + rank : g;
-  const uint32_t s_begin = (uint32_t)(((uint64_t)es * p.n_slots) / p.n_es);
-  const uint32_t s_end = (uint32_t)(((uint64_t)(es + 1) * p.n_slots) / p.n_es);
-  const uint32_t n_my = s_end - s_begin;
+  // Work of this unit: segments (query tile, slots [s_begin, s_end)); slot -> tile is the identity in SCAN
+  // mode and a stride over the whole corpus in DUMP mode.  The n_qt x n_es units of the regular grid have one
+  // segment each (query tile group g, one of n_es shares of the first n_slots - n_tail slots).  When n_qt does
+  // not divide the SM count the n_rem CTAs left over share the last n_tail slots of EVERY query tile: unit j
+  // takes an equal run of the n_qt x n_tail tile jobs in query-tile-major order, i.e. a few query tiles one
+  // after the other over (part of) the tail rows, reloading its resident query tile in between.
+  const uint32_t n_main = p.n_slots - p.n_tail;
+  auto segment = [&](uint32_t i, uint32_t& qt, uint32_t& s_begin, uint32_t& s_end) -> bool {
+    const uint32_t n_full = p.n_qt * p.n_es;
+    if (unit < n_full) {
+      if (i) return false;
+      const uint32_t g = unit % p.n_qt, es = unit / p.n_qt;
+      qt = PAIR ? 2 * g + rank : g;
+      s_begin = (uint32_t)(((uint64_t)es * n_main) / p.n_es);
+      s_end = (uint32_t)(((uint64_t)(es + 1) * n_main) / p.n_es);
+      return s_end > s_begin;
+    }
+    if (PAIR) return false;
+    const uint64_t jobs = (uint64_t)p.n_qt * p.n_tail;
+    const uint64_t lo = ((uint64_t)(unit - n_full) * jobs) / p.n_rem, hi = ((uint64_t)(unit - n_full + 1) * jobs) / p.n_rem;
+    if (lo >= hi) return false;
+    const uint64_t t = lo / p.n_tail + i;  // i-th query tile this run touches
+    if (t * p.n_tail >= hi) return false;
+    const uint64_t a = lo > t * p.n_tail ? lo : t * p.n_tail, b = hi < (t + 1) * p.n_tail ? hi : (t + 1) * p.n_tail;
+    qt = (uint32_t)t;
+    s_begin = n_main + (uint32_t)(a - t * p.n_tail);
+    s_end = n_main + (uint32_t)(b - t * p.n_tail);
+    return true;
+  };
   auto tile_of = [&](uint32_t slot) {
     return p.mode == TC_MODE_SCAN ? p.tile0 + slot : (uint32_t)(((uint64_t)slot * p.n_tiles) / p.n_slots);
   };
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
-    if (lane == 0 && n_my) {
+    if (lane == 0) {
+      uint32_t qt, s_begin, s_end, it = 0;
       if (!PAIR) {
-        if (QRES) {
-          mbar_arrive_expect_tx(bar_q, p.n_kc * TC_QCHUNK_BYTES);
-          for (uint32_t kc = 0; kc < p.n_kc; ++kc)
-            tma_load_2d(smem_u32(sQ + (size_t)kc * TC_QCHUNK_BYTES), &tmQ, (int)(kc * TC_BK), (int)(qt * TC_BM),
-                        bar_q);
-        }
-        uint32_t it = 0;
-        for (uint32_t ti = 0; ti < n_my; ++ti) {
-          const int row0 = (int)(tile_of(s_begin + ti) * TC_BN);
-          for (uint32_t kc = 0; kc < p.n_kc; ++kc, ++it) {
-            const uint32_t stage = it % S;
-            if (it >= S) mbar_wait(bar_empty + 8 * stage, ((it / S) - 1) & 1);
-            if (p.debug & 4) {  // measurement: no E traffic at all, the MMAs reuse whatever the stage holds
-              mbar_arrive(bar_full + 8 * stage);
-              continue;
+        for (uint32_t si = 0; segment(si, qt, s_begin, s_end); ++si) {
+          if (QRES) {
+            // a later segment replaces the resident query tile once the MMAs that read the previous one retired
+            if (si) mbar_wait(bar_qfree, (si - 1) & 1);
+            mbar_arrive_expect_tx(bar_q, p.n_kc * TC_QCHUNK_BYTES);
+            for (uint32_t kc = 0; kc < p.n_kc; ++kc)
+              tma_load_2d(smem_u32(sQ + (size_t)kc * TC_QCHUNK_BYTES), &tmQ, (int)(kc * TC_BK), (int)(qt * TC_BM),
+                          bar_q);
+          }
+          for (uint32_t slot = s_begin; slot < s_end; ++slot) {
+            const int row0 = (int)(tile_of(slot) * TC_BN);
+            for (uint32_t kc = 0; kc < p.n_kc; ++kc, ++it) {
+              const uint32_t stage = it % S;
+              if (it >= S) mbar_wait(bar_empty + 8 * stage, ((it / S) - 1) & 1);
+              if (p.debug & 4) {  // measurement: no E traffic at all, the MMAs reuse whatever the stage holds
+                mbar_arrive(bar_full + 8 * stage);
+                continue;
+              }
+              mbar_arrive_expect_tx(bar_full + 8 * stage, STAGE_BYTES);
+              tma_load_2d(smem_u32(sE + (size_t)stage * STAGE_BYTES), &tmE, (int)(kc * TC_BK), row0,
+                          bar_full + 8 * stage);
+              if (!QRES)
+                tma_load_2d(smem_u32(sE + (size_t)stage * STAGE_BYTES + E_BYTES), &tmQ, (int)(kc * TC_BK),
+                            (int)(qt * TC_BM), bar_full + 8 * stage);
             }
-            mbar_arrive_expect_tx(bar_full + 8 * stage, STAGE_BYTES);
-            tma_load_2d(smem_u32(sE + (size_t)stage * STAGE_BYTES), &tmE, (int)(kc * TC_BK), row0,
-                        bar_full + 8 * stage);
-            if (!QRES)
-              tma_load_2d(smem_u32(sE + (size_t)stage * STAGE_BYTES + E_BYTES), &tmQ, (int)(kc * TC_BK),
-                          (int)(qt * TC_BM), bar_full + 8 * stage);
           }
         }
-      } else {
+      } else if (segment(0, qt, s_begin, s_end)) {
         // both CTAs load; every transfer completes on the LEADER's barrier, which the leader
         // arms with the bytes of both halves.  A CTA reuses a stage when its own empty barrier
         // (signalled in both CTAs by the leader's commit) says the MMAs that read it retired.
@@ -374,9 +403,8 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             tma_load_2d_pair(smem_u32(sQ + (size_t)kc * TC_QCHUNK_BYTES), &tmQ, (int)(kc * TC_BK),
                              (int)(qt * TC_BM), l_bar_q);
         }
-        uint32_t it = 0;
-        for (uint32_t ti = 0; ti < n_my; ++ti) {
-          const int row0 = (int)(tile_of(s_begin + ti) * TC_BN + rank * (TC_BN / 2));
+        for (uint32_t slot = s_begin; slot < s_end; ++slot) {
+          const int row0 = (int)(tile_of(slot) * TC_BN + rank * (TC_BN / 2));
           for (uint32_t kc = 0; kc < p.n_kc; ++kc, ++it) {
             const uint32_t stage = it % S;
             if (it >= S) mbar_wait(bar_empty + 8 * stage, ((it / S) - 1) & 1);
@@ -396,37 +424,40 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer (leader CTA of a pair) ----------
-    if (lane == 0 && n_my && rank == 0) {
-      if (QRES) {
-        mbar_wait(bar_q, 0);
-        tc_fence_after();
-      }
-      uint32_t it = 0;
-      for (uint32_t ti = 0; ti < n_my; ++ti) {
-        const uint32_t acc = ti & 1, use = ti >> 1;
-        if (use > 0) mbar_wait(bar_tempty + 8 * acc, (use - 1) & 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * TC_BN;
-        for (uint32_t kc = 0; kc < p.n_kc; ++kc, ++it) {
-          const uint32_t stage = it % S;
-          mbar_wait(bar_full + 8 * stage, (it / S) & 1);
+    if (lane == 0 && rank == 0) {
+      uint32_t qt, s_begin, s_end, it = 0, tcount = 0;
+      for (uint32_t si = 0; segment(si, qt, s_begin, s_end); ++si) {
+        if (QRES) {
+          mbar_wait(bar_q, si & 1);
           tc_fence_after();
-          const uint64_t adesc = make_sw128_desc(
-              smem_u32(QRES ? sQ + (size_t)kc * TC_QCHUNK_BYTES : sE + (size_t)stage * STAGE_BYTES + E_BYTES));
-          const uint64_t bdesc = make_sw128_desc(smem_u32(sE + (size_t)stage * STAGE_BYTES));
-#pragma unroll
-          for (uint32_t k = 0; k < TC_BK / TC_UK; ++k) {
-            // advance 16 bf16 = 32 B inside the swizzle atom: +2 in the (addr >> 4) field
-            if (PAIR) umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, TC_IDESC_PAIR, (kc | k) != 0 ? 1u : 0u);
-            else umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, TC_IDESC, (kc | k) != 0 ? 1u : 0u);
-          }
-          // frees the smem stage (in both CTAs) when these MMAs retire
-          if (PAIR) umma_commit_pair(bar_empty + 8 * stage);
-          else umma_commit(bar_empty + 8 * stage);
         }
-        // accumulator complete (in both CTAs' TMEM)
-        if (PAIR) umma_commit_pair(bar_tfull + 8 * acc);
-        else umma_commit(bar_tfull + 8 * acc);
+        for (uint32_t slot = s_begin; slot < s_end; ++slot, ++tcount) {
+          const uint32_t acc = tcount & 1, use = tcount >> 1;
+          if (use > 0) mbar_wait(bar_tempty + 8 * acc, (use - 1) & 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * TC_BN;
+          for (uint32_t kc = 0; kc < p.n_kc; ++kc, ++it) {
+            const uint32_t stage = it % S;
+            mbar_wait(bar_full + 8 * stage, (it / S) & 1);
+            tc_fence_after();
+            const uint64_t adesc = make_sw128_desc(
+                smem_u32(QRES ? sQ + (size_t)kc * TC_QCHUNK_BYTES : sE + (size_t)stage * STAGE_BYTES + E_BYTES));
+            const uint64_t bdesc = make_sw128_desc(smem_u32(sE + (size_t)stage * STAGE_BYTES));
+#pragma unroll
+            for (uint32_t k = 0; k < TC_BK / TC_UK; ++k) {
+              // advance 16 bf16 = 32 B inside the swizzle atom: +2 in the (addr >> 4) field
+              if (PAIR) umma_bf16_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, TC_IDESC_PAIR, (kc | k) != 0 ? 1u : 0u);
+              else umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, TC_IDESC, (kc | k) != 0 ? 1u : 0u);
+            }
+            // frees the smem stage (in both CTAs) when these MMAs retire
+            if (PAIR) umma_commit_pair(bar_empty + 8 * stage);
+            else umma_commit(bar_empty + 8 * stage);
+          }
+          // accumulator complete (in both CTAs' TMEM)
+          if (PAIR) umma_commit_pair(bar_tfull + 8 * acc);
+          else umma_commit(bar_tfull + 8 * acc);
+        }
+        if (QRES && !PAIR) umma_commit(bar_qfree);  // the resident query tile may be replaced
       }
     }
   } else if (warp >= TC_CTRL_WARPS) {
@@ -436,11 +467,13 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     constexpr uint32_t LIST_CAP = tc_list_cap(EW);
     constexpr uint32_t CH_PER_WARP = (TC_BN / 32) / (EW / 4);
     const uint32_t ew = warp & 3, part = (warp - TC_CTRL_WARPS) >> 2;
-    const uint32_t q = qt * TC_BM + ew * 32 + lane;
-    const bool valid = q < p.nq_valid;
     const uint32_t list_slot = blockIdx.x * (EW * 32) + (warp - TC_CTRL_WARPS) * 32;
     const uint32_t l_bar_tempty = PAIR ? mapa_u32(bar_tempty, 0) : bar_tempty;  // the MMA issuer's barrier
     uint64_t* myL = p.lists + ((size_t)list_slot + lane) * LIST_CAP;
+    uint32_t qt, s_begin, s_end, tcount = 0;
+    for (uint32_t si = 0; segment(si, qt, s_begin, s_end); ++si) {
+    const uint32_t q = qt * TC_BM + ew * 32 + lane;
+    const bool valid = q < p.nq_valid;
     uint32_t cnt = 0;
     uint64_t tau_key = 0ull;
     float tau = valid ? -INFINITY : INFINITY;
@@ -449,9 +482,9 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       if (tau_key != 0ull) tau = float_from_ord(key_ord(tau_key));
     }
 
-    for (uint32_t ti = 0; ti < n_my; ++ti) {
-      const uint32_t acc = ti & 1, use = ti >> 1;
-      const uint32_t row_base = tile_of(s_begin + ti) * TC_BN;
+    for (uint32_t slot = s_begin; slot < s_end; ++slot, ++tcount) {
+      const uint32_t acc = tcount & 1, use = tcount >> 1;
+      const uint32_t row_base = tile_of(slot) * TC_BN;
       mbar_wait(bar_tfull + 8 * acc, use & 1);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((ew * 32u) << 16) + acc * TC_BN;
@@ -480,7 +513,7 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const uint32_t r0 = row_base + ch * 32;
         if (p.mode == TC_MODE_DUMP) {
           if (valid) {
-            float* out = p.dump + (size_t)q * ((size_t)p.n_slots * TC_BN) + (size_t)(s_begin + ti) * TC_BN + ch * 32;
+            float* out = p.dump + (size_t)q * ((size_t)p.n_slots * TC_BN) + (size_t)slot * TC_BN + ch * 32;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               float4 o;
@@ -574,6 +607,8 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
       }
     }
+    __syncwarp();  // the private lists are reused by the next segment
+    }  // segments
   }
 
   tc_fence_before();
@@ -770,6 +805,19 @@ static cudaError_t launch_mode(const StoreView& st, const void* Q16, uint32_t q0
   p.n_kc = st.ld16 / TC_BK;
   p.n_qt = n_qt;
   p.n_es = n_es;
+  // SMs left over by the n_qt x n_es grid (8 query tiles on 148 SMs: 4) take an equal share of the work from the
+  // end of the slot range, every query tile of it (see the kernel)
+  p.n_tail = 0;
+  p.n_rem = 0;
+  if (!pair && tune.use_leftover_sms) {
+    const uint32_t n_full = n_qt * n_es;
+    const uint32_t rem = (uint32_t)sm_count > n_full ? (uint32_t)sm_count - n_full : 0u;
+    if (rem && p.n_slots >= 2u * (uint32_t)sm_count) {
+      p.n_tail = (uint32_t)(((uint64_t)p.n_slots * rem) / (n_full + rem));
+      if (p.n_tail) p.n_rem = rem;
+    }
+  }
+  const uint32_t units = n_qt * n_es + p.n_rem;
   p.nq_valid = nq;
   size_t smem;
   p.stages = tensor_stages(p.n_kc, pair, &smem);
@@ -798,9 +846,9 @@ static cudaError_t launch_mode(const StoreView& st, const void* Q16, uint32_t q0
   // bounds for the map and reads as zeros
   if (!encode_2d(&tmQ, qbase, st.ld16, (uint64_t)n_tiles_q * TC_BM, TC_BM)) return cudaErrorInvalidValue;
   if (!encode_2d(&tmE, st.E16, st.ld16, st.n_rows, pair ? TC_BN / 2 : TC_BN)) return cudaErrorInvalidValue;
-  if (!tensor_q_resident(p.n_kc)) return launch_kernel<8, false>(pair, n_qt * n_es, smem, s, tmQ, tmE, p);
-  return tune.epi_warps == 8 ? launch_kernel<8, true>(pair, n_qt * n_es, smem, s, tmQ, tmE, p)
-                             : launch_kernel<16, true>(pair, n_qt * n_es, smem, s, tmQ, tmE, p);
+  if (!tensor_q_resident(p.n_kc)) return launch_kernel<8, false>(pair, units, smem, s, tmQ, tmE, p);
+  return tune.epi_warps == 8 ? launch_kernel<8, true>(pair, units, smem, s, tmQ, tmE, p)
+                             : launch_kernel<16, true>(pair, units, smem, s, tmQ, tmE, p);
 }
 
 // Bootstrap: sample scores -> per-query cut-off in cv.gtau[q0 .. q0+nq).  dump holds

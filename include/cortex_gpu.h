@@ -286,9 +286,10 @@ cx_status cx_get_stats(const cx_index* h, cx_stats* out);
  * phase, default auto); "tensor_sample_tiles" row tiles sampled for the cut-off bootstrap (0 = auto); "shadow" 0 = keep no bf16 copy (disables the tensor pass; before the first
  * insert); "profile" 1 = bracket the scan-pass kernels (bootstrap included) with CUDA events on their
  * stream (cx_get_stats: pass_kernel_ns); "blocking_sync" 1 = search calls sleep on an event instead of
- * spinning while the GPU works; "graphs" 0 = never replay repeated device-resident search shapes as a
+ * spinning while the GPU works; "graphs" 0 = never replay repeated search shapes as a
  * CUDA graph; "tensor_pair" 1 = CTA-pair (cta_group::2) form of the tensor pass; "tensor_epi_warps"
- * 8 | 16.  Every option leaves results identical.  (The result-corrupting measurement hook
+ * 8 | 16; "tensor_leftover_sms" 0 = leave the SMs idle that the (query tiles x row splits) grid of the tensor
+ * pass does not cover (default 1: they take a share of the rows).  Every option leaves results identical.  (The result-corrupting measurement hook
  * "tensor_debug" exists only in -DCX_PROBE builds made by scripts/k2_probe.py, not in this library.) */
 cx_status cx_set_option(cx_index* h, const char* key, int64_t value);
 

@@ -27,6 +27,7 @@ ap.add_argument("--growth", default="8")
 ap.add_argument("--pairs", default="1,0")
 ap.add_argument("--epi", default="8")
 ap.add_argument("--sample", default="0")
+ap.add_argument("--leftover", default="1")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 corpus = bench.make_corpus_torch(a.rows, 384, bench.SEED, dev)
@@ -39,14 +40,16 @@ ix.insert_batch_device(ids, corpus)
 ix.set_option("profile", 1)
 ix.set_option("force_path", 2)
 out = None
-for pair, growth, epi, sample in [(int(p), int(g), int(e), int(sm)) for p in a.pairs.split(",")
-                                  for g in a.growth.split(",") for e in a.epi.split(",") for sm in a.sample.split(",")]:
+for pair, growth, epi, sample, leftover in [(int(p), int(g), int(e), int(sm), int(lo)) for p in a.pairs.split(",")
+                                            for g in a.growth.split(",") for e in a.epi.split(",")
+                                            for sm in a.sample.split(",") for lo in a.leftover.split(",")]:
     for dbg in [int(x) for x in a.debug_modes.split(",")]:
         ix.set_option("tensor_pair", pair)
         if growth >= 0:
             ix.set_option("tensor_phase_growth", growth)   # < 0: leave the automatic choice
         ix.set_option("tensor_epi_warps", epi)
         ix.set_option("tensor_sample_tiles", sample)
+        ix.set_option("tensor_leftover_sms", leftover)
         if dbg or a.debug_modes != "0":
             ix.set_option("tensor_debug", dbg)   # exists in the -DCX_PROBE build only
         reps = a.reps if dbg == 0 else 2
@@ -66,7 +69,7 @@ for pair, growth, epi, sample in [(int(p), int(g), int(e), int(sm)) for p in a.p
         tf = 2.0 * 384 * a.batch * a.rows / (us * 1e-6) / 1e12
         if dbg:
             ix.set_option("tensor_debug", -1)  # prints the effective SM clock of the last launch to stderr
-        print(json.dumps({"call_us": call_us, "sample": sample, "epi": epi, "pair": pair, "growth": growth, "debug": dbg, "fallbacks": s1["fallbacks"] - s0["fallbacks"], "us_per_launch": us, "tflops": tf, "launches": n,
+        print(json.dumps({"call_us": call_us, "sample": sample, "leftover": leftover, "epi": epi, "pair": pair, "growth": growth, "debug": dbg, "fallbacks": s1["fallbacks"] - s0["fallbacks"], "us_per_launch": us, "tflops": tf, "launches": n,
                           "batch": a.batch, "k": a.k}), flush=True)
 if a.debug_modes != "0":
     ix.set_option("tensor_debug", 0)
