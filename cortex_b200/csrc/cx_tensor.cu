@@ -472,143 +472,143 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     uint64_t* myL = p.lists + ((size_t)list_slot + lane) * LIST_CAP;
     uint32_t qt, s_begin, s_end, tcount = 0;
     for (uint32_t si = 0; segment(si, qt, s_begin, s_end); ++si) {
-    const uint32_t q = qt * TC_BM + ew * 32 + lane;
-    const bool valid = q < p.nq_valid;
-    uint32_t cnt = 0;
-    uint64_t tau_key = 0ull;
-    float tau = valid ? -INFINITY : INFINITY;
-    if (valid && p.mode == TC_MODE_SCAN) {
-      tau_key = *((volatile uint64_t*)(p.gtau + q));
-      if (tau_key != 0ull) tau = float_from_ord(key_ord(tau_key));
-    }
-
-    for (uint32_t slot = s_begin; slot < s_end; ++slot, ++tcount) {
-      const uint32_t acc = tcount & 1, use = tcount >> 1;
-      const uint32_t row_base = tile_of(slot) * TC_BN;
-      mbar_wait(bar_tfull + 8 * acc, use & 1);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((ew * 32u) << 16) + acc * TC_BN;
-      if (p.debug & 1) {
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-          if (PAIR) mbar_arrive_cluster(l_bar_tempty + 8 * acc);
-          else mbar_arrive(bar_tempty + 8 * acc);
-        }
-        continue;
+      const uint32_t q = qt * TC_BM + ew * 32 + lane;
+      const bool valid = q < p.nq_valid;
+      uint32_t cnt = 0;
+      uint64_t tau_key = 0ull;
+      float tau = valid ? -INFINITY : INFINITY;
+      if (valid && p.mode == TC_MODE_SCAN) {
+        tau_key = *((volatile uint64_t*)(p.gtau + q));
+        if (tau_key != 0ull) tau = float_from_ord(key_ord(tau_key));
       }
-#pragma unroll 1
-      for (uint32_t c = 0; c < CH_PER_WARP; ++c) {
-        const uint32_t ch = part * CH_PER_WARP + c;
-        float v[32];
-        tmem_ld32(taddr + ch * 32, v);
-        if (c == CH_PER_WARP - 1) {  // this warp's share of the accumulator is drained
+
+      for (uint32_t slot = s_begin; slot < s_end; ++slot, ++tcount) {
+        const uint32_t acc = tcount & 1, use = tcount >> 1;
+        const uint32_t row_base = tile_of(slot) * TC_BN;
+        mbar_wait(bar_tfull + 8 * acc, use & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((ew * 32u) << 16) + acc * TC_BN;
+        if (p.debug & 1) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) {
             if (PAIR) mbar_arrive_cluster(l_bar_tempty + 8 * acc);
             else mbar_arrive(bar_tempty + 8 * acc);
           }
-        }
-        const uint32_t r0 = row_base + ch * 32;
-        if (p.mode == TC_MODE_DUMP) {
-          if (valid) {
-            float* out = p.dump + (size_t)q * ((size_t)p.n_slots * TC_BN) + (size_t)slot * TC_BN + ch * 32;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 o;
-              float* po = reinterpret_cast<float*>(&o);
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const uint32_t row = r0 + j + u;
-                bool okr = row < p.n_rows;
-                if (okr && p.check_rows) okr = row_passes(p.flt, p.meta, p.agent, row);
-                po[u] = okr ? v[j + u] : -INFINITY;
-              }
-              *reinterpret_cast<float4*>(out + j) = o;
-            }
-          }
           continue;
         }
-        // common path: the largest of the 32 scores against the cut-off (group maxima of 8 are
-        // kept so that a hit is located without a per-score test; fmaxf drops NaN, padded
-        // lanes have tau = +inf)
-        float g8[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float a = fmaxf(fmaxf(v[8 * i], v[8 * i + 1]), v[8 * i + 2]);
-          const float b = fmaxf(fmaxf(v[8 * i + 3], v[8 * i + 4]), v[8 * i + 5]);
-          g8[i] = fmaxf(fmaxf(a, b), fmaxf(v[8 * i + 6], v[8 * i + 7]));
-        }
-        const bool hit = fmaxf(fmaxf(g8[0], g8[1]), fmaxf(g8[2], g8[3])) >= tau && !(p.debug & 2);
-        if (__any_sync(0xffffffffu, hit)) {
-          // make room first: a chunk can append up to 32 keys
-          uint32_t full = __ballot_sync(0xffffffffu, cnt + 32 > LIST_CAP);
-          if (p.static_tau) {
-            if (cnt + 32 > LIST_CAP) {
-              const uint32_t pos = atomicAdd(p.cnt + q, cnt);
-              uint64_t* out = p.keys + (size_t)q * p.cap;
-              for (uint32_t i = 0; i < cnt; ++i)
-                if (pos + i < p.cap) out[pos + i] = myL[i];
-              cnt = 0;
+#pragma unroll 1
+        for (uint32_t c = 0; c < CH_PER_WARP; ++c) {
+          const uint32_t ch = part * CH_PER_WARP + c;
+          float v[32];
+          tmem_ld32(taddr + ch * 32, v);
+          if (c == CH_PER_WARP - 1) {  // this warp's share of the accumulator is drained
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if (PAIR) mbar_arrive_cluster(l_bar_tempty + 8 * acc);
+              else mbar_arrive(bar_tempty + 8 * acc);
             }
-            full = 0;
           }
-          while (full) {
-            const uint32_t l = __ffs(full) - 1;
-            full &= full - 1;
-            __syncwarp();  // lane l's appended keys must be visible to the whole warp
-            const uint32_t n_l = __shfl_sync(0xffffffffu, cnt, l);
-            uint64_t kth =
-                warp_compact<(int)(LIST_CAP / 32)>(p.lists + ((size_t)list_slot + l) * LIST_CAP, n_l, p.KP, lane);
-            if (lane == l) {
-              cnt = n_l < p.KP ? n_l : p.KP;
-              if (kth > tau_key) {
-                tau_key = kth;
-                tau = float_from_ord(key_ord(kth));
-                atomicMax(reinterpret_cast<unsigned long long*>(p.gtau + q), (unsigned long long)kth);
+          const uint32_t r0 = row_base + ch * 32;
+          if (p.mode == TC_MODE_DUMP) {
+            if (valid) {
+              float* out = p.dump + (size_t)q * ((size_t)p.n_slots * TC_BN) + (size_t)slot * TC_BN + ch * 32;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4) {
+                float4 o;
+                float* po = reinterpret_cast<float*>(&o);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const uint32_t row = r0 + j + u;
+                  bool okr = row < p.n_rows;
+                  if (okr && p.check_rows) okr = row_passes(p.flt, p.meta, p.agent, row);
+                  po[u] = okr ? v[j + u] : -INFINITY;
+                }
+                *reinterpret_cast<float4*>(out + j) = o;
+              }
+            }
+            continue;
+          }
+          // common path: the largest of the 32 scores against the cut-off (group maxima of 8 are
+          // kept so that a hit is located without a per-score test; fmaxf drops NaN, padded
+          // lanes have tau = +inf)
+          float g8[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float a = fmaxf(fmaxf(v[8 * i], v[8 * i + 1]), v[8 * i + 2]);
+            const float b = fmaxf(fmaxf(v[8 * i + 3], v[8 * i + 4]), v[8 * i + 5]);
+            g8[i] = fmaxf(fmaxf(a, b), fmaxf(v[8 * i + 6], v[8 * i + 7]));
+          }
+          const bool hit = fmaxf(fmaxf(g8[0], g8[1]), fmaxf(g8[2], g8[3])) >= tau && !(p.debug & 2);
+          if (__any_sync(0xffffffffu, hit)) {
+            // make room first: a chunk can append up to 32 keys
+            uint32_t full = __ballot_sync(0xffffffffu, cnt + 32 > LIST_CAP);
+            if (p.static_tau) {
+              if (cnt + 32 > LIST_CAP) {
+                const uint32_t pos = atomicAdd(p.cnt + q, cnt);
+                uint64_t* out = p.keys + (size_t)q * p.cap;
+                for (uint32_t i = 0; i < cnt; ++i)
+                  if (pos + i < p.cap) out[pos + i] = myL[i];
+                cnt = 0;
+              }
+              full = 0;
+            }
+            while (full) {
+              const uint32_t l = __ffs(full) - 1;
+              full &= full - 1;
+              __syncwarp();  // lane l's appended keys must be visible to the whole warp
+              const uint32_t n_l = __shfl_sync(0xffffffffu, cnt, l);
+              uint64_t kth =
+                  warp_compact<(int)(LIST_CAP / 32)>(p.lists + ((size_t)list_slot + l) * LIST_CAP, n_l, p.KP, lane);
+              if (lane == l) {
+                cnt = n_l < p.KP ? n_l : p.KP;
+                if (kth > tau_key) {
+                  tau_key = kth;
+                  tau = float_from_ord(key_ord(kth));
+                  atomicMax(reinterpret_cast<unsigned long long*>(p.gtau + q), (unsigned long long)kth);
+                }
+              }
+            }
+            // hit mask (bit j: v[j] >= tau), then one loop iteration per hit; v[j] for a run-time j
+            // comes from a 5-level select tree so v never leaves the registers
+            uint32_t m = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) m |= (v[j] >= tau ? 1u : 0u) << j;
+            if (!hit) m = 0;
+            while (m) {
+              const uint32_t j = __ffs(m) - 1;
+              m &= m - 1;
+              const float sc = pick32(v, j);
+              const uint32_t row = r0 + j;
+              if (sc >= tau && row < p.n_rows) {
+                const uint64_t key = make_key(ord_from_float(sc), row);
+                if (key >= tau_key && (!p.check_rows || row_passes(p.flt, p.meta, p.agent, row))) myL[cnt++] = key;
               }
             }
           }
-          // hit mask (bit j: v[j] >= tau), then one loop iteration per hit; v[j] for a run-time j
-          // comes from a 5-level select tree so v never leaves the registers
-          uint32_t m = 0;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) m |= (v[j] >= tau ? 1u : 0u) << j;
-          if (!hit) m = 0;
-          while (m) {
-            const uint32_t j = __ffs(m) - 1;
-            m &= m - 1;
-            const float sc = pick32(v, j);
-            const uint32_t row = r0 + j;
-            if (sc >= tau && row < p.n_rows) {
-              const uint64_t key = make_key(ord_from_float(sc), row);
-              if (key >= tau_key && (!p.check_rows || row_passes(p.flt, p.meta, p.agent, row))) myL[cnt++] = key;
+        }
+      }
+
+      // final (SCAN): append what can still matter to the query's merged list
+      if (p.mode == TC_MODE_SCAN && valid && cnt) {
+        const uint64_t g = *((volatile uint64_t*)(p.gtau + q));
+        uint32_t m = 0;
+        for (uint32_t i = 0; i < cnt; ++i) m += myL[i] >= g;
+        if (m) {
+          uint32_t pos = atomicAdd(p.cnt + q, m);
+          uint64_t* out = p.keys + (size_t)q * p.cap;
+          for (uint32_t i = 0; i < cnt; ++i) {
+            const uint64_t key = myL[i];
+            if (key >= g) {
+              if (pos < p.cap) out[pos] = key;
+              ++pos;
             }
           }
         }
       }
+      __syncwarp();  // the private lists are reused by the next segment
     }
-
-    // final (SCAN): append what can still matter to the query's merged list
-    if (p.mode == TC_MODE_SCAN && valid && cnt) {
-      const uint64_t g = *((volatile uint64_t*)(p.gtau + q));
-      uint32_t m = 0;
-      for (uint32_t i = 0; i < cnt; ++i) m += myL[i] >= g;
-      if (m) {
-        uint32_t pos = atomicAdd(p.cnt + q, m);
-        uint64_t* out = p.keys + (size_t)q * p.cap;
-        for (uint32_t i = 0; i < cnt; ++i) {
-          const uint64_t key = myL[i];
-          if (key >= g) {
-            if (pos < p.cap) out[pos] = key;
-            ++pos;
-          }
-        }
-      }
-    }
-    __syncwarp();  // the private lists are reused by the next segment
-    }  // segments
   }
 
   tc_fence_before();

@@ -73,6 +73,27 @@ def test_cfg2_1m_tensor_pass_b1024_sampled(million):
 
 
 @pytest.mark.timeout(600)
+@pytest.mark.parametrize("b", [1024, 896, 640, 384])
+def test_cfg2_1m_tensor_pass_leftover_sms(million, b):
+    """Query-tile counts that do not divide the SM count (8, 7, 5, 3 tiles on 148 SMs): the CTAs left over by the
+    (query tiles x row splits) grid walk the tail rows of several query tiles one after the other.  Same results
+    as with those SMs idle, and as the oracle on a sample."""
+    g, o, corpus, Q, ids = million
+    q = Q[:b]
+    a = g.search_batch_arrays(q, 10)
+    g.set_option("tensor_leftover_sms", 0)
+    try:
+        ref = g.search_batch_arrays(q, 10)
+    finally:
+        g.set_option("tensor_leftover_sms", 1)
+    assert np.array_equal(a[0], ref[0]) and same_bits(a[1], ref[1]) and same_bits(a[2], ref[2])
+    assert np.array_equal(a[3], ref[3])
+    # queries of the first and the last tile, and of tiles a left-over CTA switches between
+    sample = np.unique(np.concatenate([np.arange(0, b, 97), [b - 1]]))
+    assert_batch_equal(g, o, q, 10, sample=sample)
+
+
+@pytest.mark.timeout(600)
 def test_cfg2_1m_self_match_and_tie_order(million):
     """Rows of the corpus as queries: the row itself (cosine 1 up to rounding) and its exact duplicates
     lead the list, duplicates in insertion order."""
