@@ -57,6 +57,7 @@ class CxStats(C.Structure):
         ("unverified_overflow", C.c_uint64),
         ("unverified_near_ties", C.c_uint64),
         ("unverified_other", C.c_uint64),
+        ("queries_stream_bf16", C.c_uint64),
     ]
 
 

@@ -1022,6 +1022,7 @@ extern "C" cx_status cx_load(const char* path, int device, cx_index** out) {
 void cx::index_add_stats(const cx_index* h, cx_stats* out) {
   out->kernel_launches += h->launches.load();
   out->queries_stream += h->q_stream.load();
+  out->queries_stream_bf16 += h->q_stream16.load();
   out->queries_tensor += h->q_tensor.load();
   out->queries_exact += h->q_exact.load();
   out->fallbacks += h->fallbacks.load();
@@ -1072,6 +1073,10 @@ cx_status cx::index_set_option(cx_index* h, const char* key, int64_t value) {
   }
   if (!strcmp(key, "tensor_pair")) {  // CTA-pair (cta_group::2) form of the tensor pass for batches of two or more query tiles
     h->tensor_tune.pair = value != 0;
+    return CX_OK;
+  }
+  if (!strcmp(key, "stream_bf16")) {  // 0: small batches stream the fp32 rows even when a bf16 shadow exists
+    h->stream_bf16 = value != 0;
     return CX_OK;
   }
   if (!strcmp(key, "tensor_leftover_sms")) {  // 0: only the regular (query tiles x row splits) grid of CTAs

@@ -206,6 +206,7 @@ struct cx_index {
   std::vector<cx::Workspace*> ws_free;
   // options
   int force_path = 0;
+  bool stream_bf16 = true;         // batches of up to four queries stream the bf16 shadow (K1, HALF variant)
   uint32_t tensor_min_batch = 5;   // query groups at least this large go to the tensor pass
   uint32_t tensor_phase_growth = 0xFFFFFFFFu; // tensor pass: each scan phase covers this many times the rows seen before
                                               // (0/1 = one phase; 0xFFFFFFFF = auto: one phase for B <= 256 and k <= 16, else 8 for k <= 16, 6 above)
@@ -215,7 +216,7 @@ struct cx_index {
   bool use_graphs = true;          // replay repeated device-resident search shapes as one CUDA graph launch
   cx::TensorTuning tensor_tune;    // CTA form / epilogue warps of the tensor pass (per index, read-only while searching)
   // stats
-  std::atomic<uint64_t> launches{0}, q_stream{0}, q_tensor{0}, q_exact{0}, fallbacks{0}, h2d{0}, d2h{0};
+  std::atomic<uint64_t> launches{0}, q_stream{0}, q_stream16{0}, q_tensor{0}, q_exact{0}, fallbacks{0}, h2d{0}, d2h{0};
   std::atomic<uint64_t> pass_ns{0}, pass_launches{0}, graph_launches{0}, grow_events{0};
 
   // non-null: this handle is a row-sharded index over several devices (cx_sharded.cu); none of the

@@ -87,12 +87,14 @@ void launch_prepare_queries(const float* Q, float* qnorm, float* rqnorm, uint32_
 // Returns the number of producer groups it will write (G) for a store of n_rows.
 uint32_t stream_scan_groups(uint32_t n_rows, int sm_count);
 size_t stream_scan_smem(uint32_t ld, uint32_t nq_pass, uint32_t KP);
+size_t stream_scan_half_smem(uint32_t ld16, uint32_t nq_pass, uint32_t KP);  // bf16-shadow variant (nq_pass <= 4)
 // qmap (device, optional, q0 must be 0): pass-local query b is query qmap[b]; its candidate list is slot b
 // thr_cos (optional): threshold mode -- every row whose approximate cosine reaches *thr_cos is nominated
 // (no top-KP cut-off; qv.qnorm must already hold the query norms); cv.gtau is not used.
 cudaError_t launch_stream_scan(const StoreView& st, const QueryView& qv, uint32_t q0, uint32_t nq_pass,
                                const DevFilter& flt, const CandView& cv, int sm_count, cudaStream_t s,
-                               const uint32_t* qmap = nullptr, const float* thr_cos = nullptr);
+                               const uint32_t* qmap = nullptr, const float* thr_cos = nullptr, bool half = false);
+// half: stream the normalised bf16 shadow (st.E16) instead of the fp32 rows; nq_pass <= 4, no threshold mode
 
 // K5 + K3: merge candidate lists, exact rescore, verify, emit results.
 // eps_cos: bound on |approx - reference| cosine for the pass that produced the candidates.

@@ -65,6 +65,9 @@ constexpr uint32_t RETRY_CHUNK = 256;  // unverified tensor-pass queries retried
 
 // bound on |approximate - reference| cosine for the fp32 streaming pass
 float eps_stream(uint32_t dim) { return (2.1f * (float)dim + 16.0f) * 5.9604645e-8f; }
+// ... and for the streaming pass over the bf16 shadow: the stored rows are rounded to bf16 (2^-9 relative per
+// element; Cauchy-Schwarz bounds the sum by the product of the norms), the query stays fp32
+float eps_stream_half(uint32_t dim) { return 0.001953125f * 1.02f + eps_stream(dim); }
 
 // Contiguous result block: one D2H copy brings everything the host needs.
 struct ResultBlock {
@@ -210,6 +213,7 @@ struct Plan {
   std::vector<uint32_t> groups;  // tensor pass: queries per launch group (tensor_groups)
   bool fast;          // a nominate + rescore pass is usable for this call
   bool tensor;        // ... and it is the tcgen05 pass (else the streaming pass)
+  bool half;          // streaming pass over the bf16 shadow (B <= 4)
   bool thr_fast;      // threshold scan served by nominate-all + rescore-all (else the exact path)
   uint32_t thr_cap;   // ... nominee capacity per query
 };
@@ -239,6 +243,7 @@ Plan make_plan(const cx_index* h, uint64_t B, uint32_t qlen, uint32_t ldq, uint3
            stream_scan_smem(h->ld, 8, p.KP) != 0 && select_smem(p.cap, h->ld) <= 227 * 1024 &&
            h->force_path != PATH_EXACT;
   p.tensor = false;
+  p.half = false;
   p.KPt = 0;
   p.n_slots = 0;
   p.KP_wide = 0;
@@ -296,6 +301,9 @@ Plan make_plan(const cx_index* h, uint64_t B, uint32_t qlen, uint32_t ldq, uint3
     if (cap > 16384) cap = 16384;
     p.cap = (uint32_t)cap;
   }
+  // up to four queries: the streaming pass reads the bf16 shadow (half the bytes of the fp32 rows)
+  p.half = p.fast && !p.tensor && B <= 4 && h->dE16 && h->stream_bf16 && h->force_path == PATH_AUTO &&
+           stream_scan_half_smem(h->ld16, (uint32_t)B, p.KP) != 0;
   return p;
 }
 
@@ -434,12 +442,13 @@ cx_status enqueue_topk(Launcher& L, const StoreView& st, const QueryView& qv, co
   } else {
     for (uint64_t q0 = 0; q0 < B; q0 += 8) {
       const uint32_t nq = (uint32_t)(B - q0 < 8 ? B - q0 : 8);
-      CU(launch_stream_scan(st, qv, (uint32_t)q0, nq, flt, cv, h->sm_count, s));
+      CU(launch_stream_scan(st, qv, (uint32_t)q0, nq, flt, cv, h->sm_count, s, nullptr, nullptr, pl.half));
       L.n_launch += 1;
     }
   }
   if (h->profile) CU(L.record(L.ws->ev1));
-  CU(launch_select_rescore(st, qv, 0, (uint32_t)B, cv, rv, pl.tensor ? eps_tensor(h->dim) : eps_stream(h->dim),
+  CU(launch_select_rescore(st, qv, 0, (uint32_t)B, cv, rv,
+                           pl.tensor ? eps_tensor(h->dim) : pl.half ? eps_stream_half(h->dim) : eps_stream(h->dim),
                            /*scale_by_rqn=*/pl.tensor ? 0 : 1, s));
   L.n_launch += 1;
   if (h_block) CU(cudaMemcpyAsync(h_block, sb.res, rb.total, cudaMemcpyDeviceToHost, s));
@@ -631,12 +640,13 @@ cx_status run_search(cx_index* h, Workspace* ws, const FilterHost& fh, const Sea
     for (uint64_t b = 0; b < B; ++b)
       if (!h_ok[b]) redo.push_back((uint32_t)b);
     (pl.tensor ? h->q_tensor : h->q_stream) += B - redo.size();
+    if (pl.half) h->q_stream16 += B - redo.size();
     h->fallbacks += redo.size();
     // Retry ladder for queries the primary pass could not verify: the fp32 streaming pass
     // (error bound ~100x tighter than the bf16 pass), four queries per pass over the matrix,
     // first with the normal keep count, then with a wide one (near-ties around rank k need
     // more rescored rows, not a different algorithm).  What still fails goes to the exact path.
-    const uint32_t ladder[2] = {pl.tensor ? pl.KP : 0u, pl.KP_wide > pl.KP ? pl.KP_wide : 0u};
+    const uint32_t ladder[2] = {(pl.tensor || pl.half) ? pl.KP : 0u, pl.KP_wide > pl.KP ? pl.KP_wide : 0u};
     bool retried = false;
     for (int tier = 0; tier < 2 && !redo.empty(); ++tier) {
       const uint32_t KPr = ladder[tier];
@@ -893,7 +903,7 @@ cx_status search_host(cx_index* h, const float* queries, uint64_t B, uint32_t ql
     hs = fnv(hs, &f.agent, sizeof f.agent);
     hs = fnv(hs, &f.has_kinds, sizeof f.has_kinds);
     hs = fnv(hs, &f.has_agent, sizeof f.has_agent);
-    const uint64_t misc[8] = {(uint64_t)(uintptr_t)h_block,  (uint64_t)h->force_path,      (uint64_t)h->tensor_min_batch,
+    const uint64_t misc[8] = {(uint64_t)(uintptr_t)h_block,  (uint64_t)h->force_path,      (uint64_t)h->tensor_min_batch + ((uint64_t)h->stream_bf16 << 40),
                               (uint64_t)h->tensor_phase_growth, (uint64_t)h->profile,
                               (uint64_t)(h->tensor_tune.pair * 64 + h->tensor_tune.epi_warps + 1024 * h->tensor_tune.debug +
                                           4096 * h->tensor_tune.use_leftover_sms) +
@@ -1154,7 +1164,7 @@ cx_status cx::index_search_device(cx_index* h, const float* d_queries, uint32_t 
     hs = fnv(hs, &f.has_agent, sizeof f.has_agent);
     const uint64_t misc[10] = {(uint64_t)(uintptr_t)d_out_distance, (uint64_t)(uintptr_t)d_out_ids,
                                (uint64_t)(uintptr_t)d_out_n,       (uint64_t)(uintptr_t)ws->hp,
-                               (uint64_t)h->force_path,            (uint64_t)h->tensor_min_batch,
+                               (uint64_t)h->force_path,            (uint64_t)h->tensor_min_batch + ((uint64_t)h->stream_bf16 << 40),
                                (uint64_t)h->tensor_phase_growth,   (uint64_t)h->profile,
                                (uint64_t)(h->tensor_tune.pair * 64 + h->tensor_tune.epi_warps + 1024 * h->tensor_tune.debug +
                                           4096 * h->tensor_tune.use_leftover_sms) +

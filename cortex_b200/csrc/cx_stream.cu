@@ -16,6 +16,11 @@
 // and verified by cx_select.cu.  The matrix is read exactly once per pass:
 //   algorithmic bytes per pass = n_rows * ld * 4   
 //
+// HALF variant (B <= 4 on an index that keeps the bf16 shadow): the same pipeline streams the NORMALISED bf16
+// copy of the rows instead (half the bytes: n_rows * ld16 * 2 per pass), widens the elements in registers and
+// needs no reciprocal norms.  Its scores carry the shadow's rounding error (2^-9 relative per row), which only
+// widens the band cx_select.cu rescores exactly.
+//
 // Call shapes served (reference): search() at B=1 (api.rs:117-125,
 // http/routes.rs:906-907, grpc/service.rs:673-675, gate/mod.rs:332) and small
 // search_batch() groups (vector/index.rs:390-410).
@@ -32,7 +37,7 @@ constexpr int SC_R = 4;                          // rows per warp per tile
 constexpr int SC_TILE_ROWS = SC_GW * SC_R;       // 32
 constexpr int SC_QUAD = 4;                       // tiles between list checks
 constexpr int SC_KSLICE = 384;                   // floats of a row per stage (<= 48 KB stages)
-constexpr int SC_MAX_STAGES = 4;
+constexpr int SC_MAX_STAGES = 8;                 // fp32 rows: 4 x 48 KB fit; bf16 rows: 8 x 24 KB
 constexpr size_t SC_SMEM_LIMIT = 227 * 1024;
 
 struct StreamParams {
@@ -91,12 +96,13 @@ struct StreamLayout {
   size_t tiles, rn, q, list, tau, cnt, bars, total;
 };
 
+// ld: elements per stored row (and per query row in shared memory); esize: bytes per stored element
 __host__ __device__ inline StreamLayout stream_layout(uint32_t ld, uint32_t nq, uint32_t C, uint32_t stages,
-                                                      uint32_t kslice) {
+                                                      uint32_t kslice, uint32_t esize) {
   StreamLayout L;
   size_t o = 0;
   L.tiles = o;
-  o += (size_t)stages * SC_TILE_ROWS * kslice * 4;
+  o += (size_t)stages * SC_TILE_ROWS * kslice * esize;
   L.rn = o;
   o += (size_t)SC_MAX_STAGES * SC_TILE_ROWS * 4;
   L.q = o;
@@ -116,11 +122,14 @@ __host__ __device__ inline StreamLayout stream_layout(uint32_t ld, uint32_t nq, 
 }
 
 // KC > 0: the slice is exactly KC chunks of 128 floats (fully unrolled inner loop)
-template <int NQ, int KC>
+// HALF: rows come from the normalised bf16 shadow (st.E16, ld16 elements per row)
+template <int NQ, int KC, bool HALF>
 __global__ void __launch_bounds__(SC_THREADS, 1) stream_scan_kernel(const StreamParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const StreamLayout L = stream_layout(p.st.ld, NQ, p.C, p.stages, p.kslice);
-  float* tiles = reinterpret_cast<float*>(smem_raw + L.tiles);
+  constexpr uint32_t ES = HALF ? 2u : 4u;  // bytes per stored element
+  const uint32_t ld = HALF ? p.st.ld16 : p.st.ld;
+  const StreamLayout L = stream_layout(ld, NQ, p.C, p.stages, p.kslice, ES);
+  unsigned char* tiles = smem_raw + L.tiles;
   float* rn_s = reinterpret_cast<float*>(smem_raw + L.rn);
   float* q_s = reinterpret_cast<float*>(smem_raw + L.q);
   uint64_t* list_s = reinterpret_cast<uint64_t*>(smem_raw + L.list);
@@ -131,8 +140,8 @@ __global__ void __launch_bounds__(SC_THREADS, 1) stream_scan_kernel(const Stream
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + L.bars);
 
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t ld = p.st.ld, ld4 = ld >> 2, S = p.stages;
-  const uint32_t tile_floats = SC_TILE_ROWS * p.kslice;
+  const uint32_t ld4 = ld >> 2, S = p.stages;
+  const uint32_t tile_bytes = SC_TILE_ROWS * p.kslice * ES;
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + SC_MAX_STAGES);
 
   if (tid == 0) {
@@ -144,7 +153,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) stream_scan_kernel(const Stream
   }
   for (uint32_t i = tid; i < NQ * ld; i += SC_THREADS) {
     uint32_t b = i / ld, d = i % ld;
-    q_s[i] = (b < p.nq_valid) ? p.Q[(size_t)(p.qmap ? p.qmap[b] : b) * p.ldq + d] : 0.0f;
+    q_s[i] = (b < p.nq_valid && d < p.ldq) ? p.Q[(size_t)(p.qmap ? p.qmap[b] : b) * p.ldq + d] : 0.0f;
   }
   for (uint32_t i = tid; i < NQ; i += SC_THREADS) {
     uint64_t t0 = 0;
@@ -176,20 +185,22 @@ __global__ void __launch_bounds__(SC_THREADS, 1) stream_scan_kernel(const Stream
           const uint32_t j = jbase + sl;
           const uint32_t stage = g * SG + (j % SG);
           if (j >= SG) mbar_wait(empty0 + 8 * stage, ((j / SG) - 1) & 1);
-          const uint32_t dst = smem_u32(tiles + (size_t)stage * tile_floats);
+          const uint32_t dst = smem_u32(tiles + (size_t)stage * tile_bytes);
           const uint32_t k0 = sl * p.kslice;
           const uint32_t klen = min(p.kslice, ld - k0);
           const uint32_t bar = full0 + 8 * stage;
-          const bool last = sl + 1 == p.n_slices;
+          const bool last = sl + 1 == p.n_slices && !HALF;  // the shadow's rows are normalised already
           const uint32_t rn_bytes = last ? ((rows_here + 3) & ~3u) * 4 : 0;
+          const unsigned char* src =
+              HALF ? reinterpret_cast<const unsigned char*>(p.st.E16) : reinterpret_cast<const unsigned char*>(p.st.E);
           if (p.n_slices == 1) {
-            const uint32_t bytes = rows_here * ld * 4;
+            const uint32_t bytes = rows_here * ld * ES;
             mbar_arrive_expect_tx(bar, bytes + rn_bytes);
-            bulk_g2s(dst, p.st.E + (size_t)r0 * ld, bytes, bar);
+            bulk_g2s(dst, src + (size_t)r0 * ld * ES, bytes, bar);
           } else {
-            mbar_arrive_expect_tx(bar, rows_here * klen * 4 + rn_bytes);
+            mbar_arrive_expect_tx(bar, rows_here * klen * ES + rn_bytes);
             for (uint32_t r = 0; r < rows_here; ++r)
-              bulk_g2s(dst + r * p.kslice * 4, p.st.E + (size_t)(r0 + r) * ld + k0, klen * 4, bar);
+              bulk_g2s(dst + r * p.kslice * ES, src + ((size_t)(r0 + r) * ld + k0) * ES, klen * ES, bar);
           }
           if (last) bulk_g2s(smem_u32(rn_s + stage * SC_TILE_ROWS), p.st.rnorm + r0, rn_bytes, bar);
         }
@@ -275,15 +286,23 @@ __global__ void __launch_bounds__(SC_THREADS, 1) stream_scan_kernel(const Stream
       const uint32_t j = (i / SC_GROUPS) * p.n_slices + sl;
       const uint32_t stage = grp * SG + (j % SG);
       mbar_wait(full0 + 8 * stage, (j / SG) & 1);
-      const float4* tile4 = reinterpret_cast<const float4*>(tiles + (size_t)stage * tile_floats) +
-                            (size_t)(gwarp * SC_R) * kslice4;
+      // four elements per lane and load: a float4 of an fp32 row, a uint2 (4 x bf16) of a shadow row
+      const unsigned char* tile_b = tiles + (size_t)stage * tile_bytes + (size_t)(gwarp * SC_R) * p.kslice * ES;
+      auto load4 = [&](uint32_t r, uint32_t c4) -> float4 {
+        if (HALF) {
+          const uint2 u = reinterpret_cast<const uint2*>(tile_b)[r * kslice4 + c4];
+          return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xFFFF0000u),
+                             __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xFFFF0000u));
+        }
+        return reinterpret_cast<const float4*>(tile_b)[r * kslice4 + c4];
+      };
       const uint32_t k0_4 = (sl * p.kslice) >> 2;
       if (KC > 0) {
 #pragma unroll
         for (int c = 0; c < (KC > 0 ? KC : 1); ++c) {
           float4 e[SC_R];
 #pragma unroll
-          for (int r = 0; r < SC_R; ++r) e[r] = tile4[r * kslice4 + c * 32 + lane];
+          for (int r = 0; r < SC_R; ++r) e[r] = load4(r, c * 32 + lane);
 #pragma unroll
           for (int b = 0; b < NQ; ++b) {
             const float4 qv = q4[b * ld4 + k0_4 + c * 32 + lane];
@@ -301,7 +320,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) stream_scan_kernel(const Stream
         for (uint32_t c = lane; c < klen4; c += 32) {
           float4 e[SC_R];
 #pragma unroll
-          for (int r = 0; r < SC_R; ++r) e[r] = tile4[r * kslice4 + c];
+          for (int r = 0; r < SC_R; ++r) e[r] = load4(r, c);
 #pragma unroll
           for (int b = 0; b < NQ; ++b) {
             const float4 qv = q4[b * ld4 + k0_4 + c];
@@ -315,7 +334,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) stream_scan_kernel(const Stream
           }
         }
       }
-      if (sl + 1 == p.n_slices) my_rn = rn_s[stage * SC_TILE_ROWS + gwarp * SC_R + my_r];
+      if (sl + 1 == p.n_slices) my_rn = HALF ? 1.0f : rn_s[stage * SC_TILE_ROWS + gwarp * SC_R + my_r];
       __syncwarp();
       if (lane == 0) mbar_arrive(empty0 + 8 * stage);
     }
@@ -418,11 +437,11 @@ static uint32_t stream_pick_kslice(uint32_t ld) {
 
 static uint32_t stream_list_cap(uint32_t KP) { return pow2_at_least(2 * KP + SC_QUAD * SC_TILE_ROWS); }
 
-static uint32_t stream_pick_stages(uint32_t ld, uint32_t nq, uint32_t KP, size_t* total) {
+static uint32_t stream_pick_stages(uint32_t ld, uint32_t nq, uint32_t KP, uint32_t esize, size_t* total) {
   uint32_t kslice = stream_pick_kslice(ld);
   uint32_t C = stream_list_cap(KP);
   for (uint32_t s = SC_MAX_STAGES; s >= 2; s -= SC_GROUPS) {  // even: each consumer group owns s/2 stages
-    StreamLayout L = stream_layout(ld, nq, C, s, kslice);
+    StreamLayout L = stream_layout(ld, nq, C, s, kslice, esize);
     if (L.total <= SC_SMEM_LIMIT) {
       *total = L.total;
       return s;
@@ -434,38 +453,49 @@ static uint32_t stream_pick_stages(uint32_t ld, uint32_t nq, uint32_t KP, size_t
 
 size_t stream_scan_smem(uint32_t ld, uint32_t nq_pass, uint32_t KP) {
   size_t total;
-  uint32_t s = stream_pick_stages(ld, nq_pass, KP, &total);
+  uint32_t s = stream_pick_stages(ld, nq_pass, KP, 4, &total);
   return s ? total : 0;
 }
 
-template <int NQ, int KC>
+// the bf16-shadow variant: ld16 elements per row, at most four queries per pass
+size_t stream_scan_half_smem(uint32_t ld16, uint32_t nq_pass, uint32_t KP) {
+  size_t total;
+  if (nq_pass > 4) return 0;
+  uint32_t s = stream_pick_stages(ld16, nq_pass, KP, 2, &total);
+  return s ? total : 0;
+}
+
+template <int NQ, int KC, bool HALF>
 static cudaError_t launch_one(const StreamParams& p, size_t smem, cudaStream_t s) {
-  cudaError_t e = raise_dynamic_smem<stream_scan_kernel<NQ, KC>>(smem);
+  cudaError_t e = raise_dynamic_smem<stream_scan_kernel<NQ, KC, HALF>>(smem);
   if (e != cudaSuccess) return e;
-  stream_scan_kernel<NQ, KC><<<p.G, SC_THREADS, smem, s>>>(p);
+  stream_scan_kernel<NQ, KC, HALF><<<p.G, SC_THREADS, smem, s>>>(p);
   return cudaGetLastError();
 }
 
-template <int NQ>
+template <int NQ, bool HALF>
 static cudaError_t launch_nq(const StreamParams& p, size_t smem, cudaStream_t s) {
-  // unrolled variants for slices that are exactly 1, 2 or 3 chunks of 128 floats
-  const bool even = (p.st.ld % p.kslice) == 0 && (p.kslice % 128) == 0;
+  // unrolled variants for slices that are exactly 1, 2 or 3 chunks of 128 elements
+  const uint32_t ld = HALF ? p.st.ld16 : p.st.ld;
+  const bool even = (ld % p.kslice) == 0 && (p.kslice % 128) == 0;
   const uint32_t kc = even ? p.kslice / 128 : 0;
   switch (kc) {
-    case 1: return launch_one<NQ, 1>(p, smem, s);
-    case 2: return launch_one<NQ, 2>(p, smem, s);
-    case 3: return launch_one<NQ, 3>(p, smem, s);
-    default: return launch_one<NQ, 0>(p, smem, s);
+    case 1: return launch_one<NQ, 1, HALF>(p, smem, s);
+    case 2: return launch_one<NQ, 2, HALF>(p, smem, s);
+    case 3: return launch_one<NQ, 3, HALF>(p, smem, s);
+    default: return launch_one<NQ, 0, HALF>(p, smem, s);
   }
 }
 
 cudaError_t launch_stream_scan(const StoreView& st, const QueryView& qv, uint32_t q0, uint32_t nq_pass,
                                const DevFilter& flt, const CandView& cv, int sm_count, cudaStream_t s,
-                               const uint32_t* qmap, const float* thr_cos) {
+                               const uint32_t* qmap, const float* thr_cos, bool half) {
   if (!st.n_rows || !nq_pass) return cudaSuccess;
   if (qmap && q0 != 0) return cudaErrorInvalidValue;
-  if (nq_pass > 8) return cudaErrorInvalidValue;
+  if (nq_pass > (half ? 4u : 8u)) return cudaErrorInvalidValue;
+  if (half && (!st.E16 || thr_cos)) return cudaErrorInvalidValue;
   const uint32_t nq_t = nq_pass <= 1 ? 1 : nq_pass <= 2 ? 2 : nq_pass <= 4 ? 4 : 8;
+  const uint32_t ld = half ? st.ld16 : st.ld;
   StreamParams p;
   p.st = st;
   p.Q = qv.Q + (size_t)q0 * qv.ldq;
@@ -484,17 +514,24 @@ cudaError_t launch_stream_scan(const StoreView& st, const QueryView& qv, uint32_
   p.gtau = cv.gtau + q0;
   p.C = stream_list_cap(cv.KP);
   p.n_tiles = (st.n_rows + SC_TILE_ROWS - 1) / SC_TILE_ROWS;
-  p.kslice = stream_pick_kslice(st.ld);
-  p.n_slices = (st.ld + p.kslice - 1) / p.kslice;
+  p.kslice = stream_pick_kslice(ld);
+  p.n_slices = (ld + p.kslice - 1) / p.kslice;
   size_t smem;
-  p.stages = stream_pick_stages(st.ld, nq_t, cv.KP, &smem);
+  p.stages = stream_pick_stages(ld, nq_t, cv.KP, half ? 2 : 4, &smem);
   if (!p.stages) return cudaErrorInvalidConfiguration;
   if (p.G != stream_scan_groups(st.n_rows, sm_count)) return cudaErrorInvalidValue;
+  if (half) {
+    switch (nq_t) {
+      case 1: return launch_nq<1, true>(p, smem, s);
+      case 2: return launch_nq<2, true>(p, smem, s);
+      default: return launch_nq<4, true>(p, smem, s);
+    }
+  }
   switch (nq_t) {
-    case 1: return launch_nq<1>(p, smem, s);
-    case 2: return launch_nq<2>(p, smem, s);
-    case 4: return launch_nq<4>(p, smem, s);
-    default: return launch_nq<8>(p, smem, s);
+    case 1: return launch_nq<1, false>(p, smem, s);
+    case 2: return launch_nq<2, false>(p, smem, s);
+    case 4: return launch_nq<4, false>(p, smem, s);
+    default: return launch_nq<8, false>(p, smem, s);
   }
 }
 

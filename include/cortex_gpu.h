@@ -58,7 +58,7 @@ typedef struct cx_filter {
 /* Counters for tests / bench (gpu_launches, which pass served a query). */
 typedef struct cx_stats {
   uint64_t kernel_launches;     /* kernels launched by this index since creation */
-  uint64_t queries_stream;      /* queries answered by the fp32 streaming pass (K1) */
+  uint64_t queries_stream;      /* queries answered by the streaming pass (K1), fp32 rows or bf16 shadow */
   uint64_t queries_tensor;      /* queries answered by the tcgen05 pass (K2) */
   uint64_t queries_exact;       /* queries answered by the exact path */
   uint64_t fallbacks;           /* queries whose fast-pass result failed verification */
@@ -77,6 +77,7 @@ typedef struct cx_stats {
   /* why fast-pass results failed verification (and were redone on a tighter path), on this device since
    * process start: candidate list overflow / near-ties around rank k denser than the rescored band / other */
   uint64_t unverified_overflow, unverified_near_ties, unverified_other;
+  uint64_t queries_stream_bf16; /* of queries_stream: answered by the streaming pass over the bf16 shadow (B <= 4) */
 } cx_stats;
 
 /* HnswIndex::new(dimension), index.rs:204-211.  device = CUDA ordinal. */
@@ -288,7 +289,8 @@ cx_status cx_get_stats(const cx_index* h, cx_stats* out);
  * stream (cx_get_stats: pass_kernel_ns); "blocking_sync" 1 = search calls sleep on an event instead of
  * spinning while the GPU works; "graphs" 0 = never replay repeated search shapes as a
  * CUDA graph; "tensor_pair" 1 = CTA-pair (cta_group::2) form of the tensor pass; "tensor_epi_warps"
- * 8 | 16; "tensor_leftover_sms" 0 = leave the SMs idle that the (query tiles x row splits) grid of the tensor
+ * 8 | 16; "stream_bf16" 0 = batches of up to four queries stream the fp32 rows instead of the
+ * bf16 shadow (twice the bytes per pass; default 1 while the index keeps a shadow); "tensor_leftover_sms" 0 = leave the SMs idle that the (query tiles x row splits) grid of the tensor
  * pass does not cover (default 1: they take a share of the rows).  Every option leaves results identical.  (The result-corrupting measurement hook
  * "tensor_debug" exists only in -DCX_PROBE builds made by scripts/k2_probe.py, not in this library.) */
 cx_status cx_set_option(cx_index* h, const char* key, int64_t value);

@@ -40,6 +40,7 @@ pub struct cx_stats {
     pub unverified_overflow: u64,
     pub unverified_near_ties: u64,
     pub unverified_other: u64,
+    pub queries_stream_bf16: u64,
 }
 
 #[repr(C)]

@@ -14,7 +14,9 @@ echo "launch list rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:tensor_scan_kernel -s 12 -c 4 -f -o gpurun_out/prof_k2_b1024 $B > gpurun_out/ncu_k2.log 2>&1
 echo "k2 capture rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:stream_scan_kernel -s 3 -c 2 -f -o gpurun_out/prof_k1_b1 $B > gpurun_out/ncu_k1.log 2>&1
-echo "k1 capture rc=$?"
+echo "k1 (bf16 shadow) capture rc=$?"
+ncu --set full --clock-control none --import-source on -k regex:stream_scan_kernel -s 3 -c 2 -f -o gpurun_out/prof_k1_b1_fp32 $B --opt stream_bf16=0 > gpurun_out/ncu_k1f.log 2>&1
+echo "k1 (fp32 rows) capture rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:select_rescore_kernel -s 6 -c 2 -f -o gpurun_out/prof_select_b1024 $B > gpurun_out/ncu_sel.log 2>&1
 echo "select capture rc=$?"
 # the auto-link shape (k=100): one call = bootstrap + phases of tensor_scan_kernel; capture the second call

@@ -53,7 +53,8 @@ def traffic(argv):
     import re
     out = {}
     for spec in argv:
-        name, batch, rep, how = spec.split(":")  # how = sum (launches are the phases of one scan) | mean
+        name, batch, rep, how, *key = spec.split(":")  # how = sum (launches are the phases of one scan) | mean;
+        key = key[0] if key else name                  # optional 5th field: the key of the entry
         raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
         rows = list(csv.reader(io.StringIO(raw)))
         head, units, data = rows[0], rows[1], rows[2:]
@@ -66,7 +67,7 @@ def traffic(argv):
                 v, u = float(r[col[k]]), units[col[k]].lower()
                 tot += v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[u]
             n += 1
-        out[name] = {"batch": int(batch), "dram_bytes_per_launch": tot if how == "sum" else tot / max(n, 1),
+        out[key] = {"batch": int(batch), "dram_bytes_per_launch": tot if how == "sum" else tot / max(n, 1),
                      "captured_kernel_launches": n,
                      "source": rep + " (ncu --set full --clock-control none; " +
                                ("the captured launches are the bootstrap + phases of one scan, summed)" if how == "sum"
