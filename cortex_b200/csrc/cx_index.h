@@ -207,7 +207,8 @@ struct cx_index {
   // options
   int force_path = 0;
   bool stream_bf16 = true;         // batches of up to four queries stream the bf16 shadow (K1, HALF variant)
-  uint32_t tensor_min_batch = 5;   // query groups at least this large go to the tensor pass
+  uint32_t tensor_min_batch = 3;   // query groups at least this large go to the tensor pass (measured: K1 over the
+                                   // bf16 shadow wins at B = 1 and 2, the tensor pass from B = 3)
   uint32_t tensor_phase_growth = 0xFFFFFFFFu; // tensor pass: each scan phase covers this many times the rows seen before
                                               // (0/1 = one phase; 0xFFFFFFFF = auto: one phase for B <= 256 and k <= 16, else 8 for k <= 16, 6 above)
   uint32_t tensor_sample_tiles = 0;  // row tiles sampled for the cut-off bootstrap (0 = auto)

@@ -34,8 +34,12 @@ constexpr int SC_CW = SC_GW * SC_GROUPS;         // consumer warps
 constexpr int SC_CT = SC_CW * 32;                // consumer threads
 constexpr int SC_THREADS = SC_CT + 32;           // + 1 producer warp
 constexpr int SC_R = 4;                          // rows per warp per tile
-constexpr int SC_TILE_ROWS = SC_GW * SC_R;       // 32
+constexpr int SC_TILE_ROWS = SC_GW * SC_R;       // 32: rows of a tile of the fp32 variant (one group's share)
+// The bf16 variant's tiles are 64 rows (the same bytes per stage as 32 fp32 rows): BOTH groups work on every
+// tile, 32 rows each, so they reach the list checkpoints together instead of waiting a tile time for each other.
+__host__ __device__ constexpr int sc_tile_rows(bool half) { return half ? SC_TILE_ROWS * SC_GROUPS : SC_TILE_ROWS; }
 constexpr int SC_QUAD = 4;                       // tiles between list checks
+constexpr uint32_t SC_EARLY_TILES = 16;          // bf16 variant: tiles checked at the short interval
 constexpr int SC_KSLICE = 384;                   // floats of a row per stage (<= 48 KB stages)
 constexpr int SC_MAX_STAGES = 8;                 // fp32 rows: 4 x 48 KB fit; bf16 rows: 8 x 24 KB
 constexpr size_t SC_SMEM_LIMIT = 227 * 1024;
@@ -51,6 +55,8 @@ struct StreamParams {
   uint32_t cap;
   const uint32_t* qmap;  // optional: pass-local query b is query qmap[b] (Q row, cnt, gtau); its list slot stays b
   uint32_t G, KP, C, n_tiles, stages, kslice, n_slices;
+  uint32_t quad;         // bf16 variant: most tiles between two list checks (what the list capacity allows); the
+                         // first SC_EARLY_TILES tiles are checked every second tile so the cut-off settles fast
   // threshold mode (search_threshold, index.rs:376-388): instead of a running top-KP cut-off every
   // row whose approximate cosine reaches thr_cos is nominated; full lists are flushed, not compacted
   uint32_t thr_mode;
@@ -99,10 +105,11 @@ struct StreamLayout {
 // ld: elements per stored row (and per query row in shared memory); esize: bytes per stored element
 __host__ __device__ inline StreamLayout stream_layout(uint32_t ld, uint32_t nq, uint32_t C, uint32_t stages,
                                                       uint32_t kslice, uint32_t esize) {
+  const uint32_t tile_rows = sc_tile_rows(esize == 2);
   StreamLayout L;
   size_t o = 0;
   L.tiles = o;
-  o += (size_t)stages * SC_TILE_ROWS * kslice * esize;
+  o += (size_t)stages * tile_rows * kslice * esize;
   L.rn = o;
   o += (size_t)SC_MAX_STAGES * SC_TILE_ROWS * 4;
   L.q = o;
@@ -127,6 +134,8 @@ template <int NQ, int KC, bool HALF>
 __global__ void __launch_bounds__(SC_THREADS, 1) stream_scan_kernel(const StreamParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr uint32_t ES = HALF ? 2u : 4u;  // bytes per stored element
+  constexpr uint32_t TR = sc_tile_rows(HALF);   // rows per tile
+  const uint32_t QUAD = HALF ? p.quad : (uint32_t)SC_QUAD;  // tiles between list checks
   const uint32_t ld = HALF ? p.st.ld16 : p.st.ld;
   const StreamLayout L = stream_layout(ld, NQ, p.C, p.stages, p.kslice, ES);
   unsigned char* tiles = smem_raw + L.tiles;
@@ -141,13 +150,13 @@ __global__ void __launch_bounds__(SC_THREADS, 1) stream_scan_kernel(const Stream
 
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t ld4 = ld >> 2, S = p.stages;
-  const uint32_t tile_bytes = SC_TILE_ROWS * p.kslice * ES;
+  const uint32_t tile_bytes = TR * p.kslice * ES;
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + SC_MAX_STAGES);
 
   if (tid == 0) {
     for (uint32_t s = 0; s < S; ++s) {
       mbar_init(full0 + 8 * s, 1);
-      mbar_init(empty0 + 8 * s, SC_GW);
+      mbar_init(empty0 + 8 * s, HALF ? SC_CW : SC_GW);  // consumer warps that read a stage
     }
     fence_mbar_init();
   }
@@ -166,21 +175,23 @@ __global__ void __launch_bounds__(SC_THREADS, 1) stream_scan_kernel(const Stream
     cnt_s[i] = 0;
     cur_s[i] = 0;
   }
+  if (tid < 4) flag_s[tid] = 0;
   __syncthreads();
 
-  const uint32_t my_tiles = (p.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  const uint32_t my_tiles = blockIdx.x < p.n_tiles ? (p.n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
 
   if (warp == SC_CW) {
     // ---------------- producer ----------------
     if (lane == 0) {
       // Each consumer group owns its own sub-ring of S/2 stages, so a stage's barriers are
       // only ever waited on by one group and phases cannot be skipped (parity would alias).
-      const uint32_t SG = S / SC_GROUPS;
+      // (The bf16 variant's tiles are shared by both groups: one ring of S stages.)
+      const uint32_t SG = HALF ? S : S / SC_GROUPS;
       for (uint32_t i = 0; i < my_tiles; ++i) {
         const uint32_t t = blockIdx.x + i * gridDim.x;
-        const uint32_t r0 = t * SC_TILE_ROWS;
-        const uint32_t rows_here = min((uint32_t)SC_TILE_ROWS, p.st.n_rows - r0);
-        const uint32_t g = i % SC_GROUPS, jbase = (i / SC_GROUPS) * p.n_slices;
+        const uint32_t r0 = t * TR;
+        const uint32_t rows_here = min(TR, p.st.n_rows - r0);
+        const uint32_t g = HALF ? 0u : i % SC_GROUPS, jbase = (HALF ? i : i / SC_GROUPS) * p.n_slices;
         for (uint32_t sl = 0; sl < p.n_slices; ++sl) {
           const uint32_t j = jbase + sl;
           const uint32_t stage = g * SG + (j % SG);
@@ -270,9 +281,14 @@ __global__ void __launch_bounds__(SC_THREADS, 1) stream_scan_kernel(const Stream
     csync();
   };
 
-  const uint32_t n_quads = my_tiles / SC_QUAD;  // full quads: both groups see the same count
+  const uint32_t n_quads = my_tiles / QUAD;  // full quads: both groups see the same count
+  uint32_t ck = 0;                           // bf16 variant: checkpoints passed
+  // this warp's rows inside a tile, and its position in the ring (kept incrementally: no division per slice)
+  const uint32_t rblock = (HALF ? grp * SC_GW + gwarp : gwarp) * SC_R;
+  const uint32_t SGc = HALF ? S : S / SC_GROUPS, stage0 = HALF ? 0u : grp * SGc;
+  uint32_t slot = 0, phase = 0;
 
-  for (uint32_t i = grp; i < my_tiles; i += SC_GROUPS) {
+  for (uint32_t i = HALF ? 0u : grp; i < my_tiles; i += HALF ? 1u : (uint32_t)SC_GROUPS) {
     const uint32_t t = blockIdx.x + i * gridDim.x;
     float acc[SC_R][NQ];
 #pragma unroll
@@ -282,12 +298,14 @@ __global__ void __launch_bounds__(SC_THREADS, 1) stream_scan_kernel(const Stream
 
     float my_rn = 0.0f;
     for (uint32_t sl = 0; sl < p.n_slices; ++sl) {
-      const uint32_t SG = S / SC_GROUPS;  // this group's sub-ring (see the producer)
-      const uint32_t j = (i / SC_GROUPS) * p.n_slices + sl;
-      const uint32_t stage = grp * SG + (j % SG);
-      mbar_wait(full0 + 8 * stage, (j / SG) & 1);
+      const uint32_t stage = stage0 + slot;  // this group's sub-ring (see the producer)
+      mbar_wait(full0 + 8 * stage, phase);
+      if (++slot == SGc) {
+        slot = 0;
+        phase ^= 1u;
+      }
       // four elements per lane and load: a float4 of an fp32 row, a uint2 (4 x bf16) of a shadow row
-      const unsigned char* tile_b = tiles + (size_t)stage * tile_bytes + (size_t)(gwarp * SC_R) * p.kslice * ES;
+      const unsigned char* tile_b = tiles + (size_t)stage * tile_bytes + (size_t)rblock * p.kslice * ES;
       auto load4 = [&](uint32_t r, uint32_t c4) -> float4 {
         if (HALF) {
           const uint2 u = reinterpret_cast<const uint2*>(tile_b)[r * kslice4 + c4];
@@ -346,7 +364,7 @@ __global__ void __launch_bounds__(SC_THREADS, 1) stream_scan_kernel(const Stream
       for (int b = 0; b < NQ; ++b) v[r * NQ + b] = acc[r][b];
     const float total = warp_transpose_reduce<NV>(v, lane);
 
-    const uint32_t row = t * SC_TILE_ROWS + gwarp * SC_R + my_r;
+    const uint32_t row = t * TR + rblock + my_r;
     if (leader && row < p.st.n_rows && my_b < p.nq_valid) {
       // cosine up to the query's own (positive) norm, which cannot change the order
       // within a query; cx_select.cu applies it when it compares against eps
@@ -364,25 +382,51 @@ __global__ void __launch_bounds__(SC_THREADS, 1) stream_scan_kernel(const Stream
     }
 
     // checkpoint after the last tile of every full quad (tile i%4 == 2 for group 0, 3 for group 1)
-    if ((i % SC_QUAD) == (SC_QUAD - SC_GROUPS + grp) && (i / SC_QUAD) < n_quads) {
-      csync();
-      if (ctid < NQ && !p.thr_mode) {
-        const uint64_t g = *((volatile uint64_t*)(p.gtau + gq(ctid)));
-        if (g > tau_s[ctid]) tau_s[ctid] = g;
-      }
-      if (ctid == 0) {
-        uint32_t m = 0;
-        for (uint32_t b = 0; b < NQ; ++b)
-          if ((!p.thr_mode && cnt_s[b] >= 2 * KP) || cnt_s[b] + SC_QUAD * SC_TILE_ROWS > C) m |= 1u << b;
-        *flag_s = m;
-      }
-      csync();
-      const uint32_t m = *flag_s;
-      for (uint32_t b = 0; b < NQ; ++b)
-        if (m & (1u << b)) {
-          if (p.thr_mode) flush(b);
-          else compact(b);
+    // (bf16 variant: every second tile at first, then every QUAD-th; every warp walks every tile, so all agree)
+    const bool check = HALF ? (i < SC_EARLY_TILES ? (i & 1u) == 1u : ((i - SC_EARLY_TILES) % QUAD) == QUAD - 1) && i + 1 < my_tiles
+                            : (i % QUAD) == (QUAD - SC_GROUPS + grp) && (i / QUAD) < n_quads;
+    if (check) {
+      if (HALF) {
+        // One barrier per checkpoint: which lists to compact was decided (by thread 0) right after the PREVIOUS
+        // checkpoint, from counts that can only have been too high; a list is flagged while two more quads of
+        // appends might not fit, so it can never overrun before the flag takes effect (C >= 2 KP + 2 quads).
+        csync();
+        const uint32_t m = flag_s[(ck & 1u) ? 3 : 0];
+        if (ctid < NQ) {
+          const uint64_t g = *((volatile uint64_t*)(p.gtau + gq(ctid)));
+          if (g > tau_s[ctid]) tau_s[ctid] = g;
         }
+        for (uint32_t b = 0; b < NQ; ++b)
+          if (m & (1u << b)) compact(b);
+        if (ctid == 0) {
+          uint32_t nm = 0;
+          for (uint32_t b = 0; b < NQ; ++b) {
+            const uint32_t c = *((volatile uint32_t*)(cnt_s + b));
+            if (c >= 2 * KP || c + 2 * QUAD * TR > C) nm |= 1u << b;
+          }
+          flag_s[((ck + 1) & 1u) ? 3 : 0] = nm;
+        }
+        ++ck;
+      } else {
+        csync();
+        if (ctid < NQ && !p.thr_mode) {
+          const uint64_t g = *((volatile uint64_t*)(p.gtau + gq(ctid)));
+          if (g > tau_s[ctid]) tau_s[ctid] = g;
+        }
+        if (ctid == 0) {
+          uint32_t m = 0;
+          for (uint32_t b = 0; b < NQ; ++b)
+            if ((!p.thr_mode && cnt_s[b] >= 2 * KP) || cnt_s[b] + SC_QUAD * SC_TILE_ROWS > C) m |= 1u << b;
+          *flag_s = m;
+        }
+        csync();
+        const uint32_t m = *flag_s;
+        for (uint32_t b = 0; b < NQ; ++b)
+          if (m & (1u << b)) {
+            if (p.thr_mode) flush(b);
+            else compact(b);
+          }
+      }
     }
   }
 
@@ -435,12 +479,20 @@ static uint32_t stream_pick_kslice(uint32_t ld) {
   return SC_KSLICE;
 }
 
-static uint32_t stream_list_cap(uint32_t KP) { return pow2_at_least(2 * KP + SC_QUAD * SC_TILE_ROWS); }
+// entries of a per-query list in shared memory: the kept keys twice over plus what can arrive between two
+// checks (one quad = 128 rows; the bf16 variant decides one check ahead, so two)
+static uint32_t stream_list_cap(uint32_t KP, bool half, uint32_t quad = 2) {
+  if (half) return (2 * KP + 2 * quad * sc_tile_rows(true) + 63) & ~63u;
+  return pow2_at_least(2 * KP + SC_QUAD * SC_TILE_ROWS);
+}
 
-static uint32_t stream_pick_stages(uint32_t ld, uint32_t nq, uint32_t KP, uint32_t esize, size_t* total) {
+static uint32_t stream_pick_stages(uint32_t ld, uint32_t nq, uint32_t KP, uint32_t esize, size_t* total,
+                                   uint32_t quad = 2) {
   uint32_t kslice = stream_pick_kslice(ld);
-  uint32_t C = stream_list_cap(KP);
-  for (uint32_t s = SC_MAX_STAGES; s >= 2; s -= SC_GROUPS) {  // even: each consumer group owns s/2 stages
+  const bool half = esize == 2;
+  uint32_t C = stream_list_cap(KP, half, quad);
+  // fp32 variant: even (each consumer group owns s/2 stages); bf16 variant: one ring shared by both groups
+  for (uint32_t s = SC_MAX_STAGES; s >= 2; s -= half ? 1 : SC_GROUPS) {
     StreamLayout L = stream_layout(ld, nq, C, s, kslice, esize);
     if (L.total <= SC_SMEM_LIMIT) {
       *total = L.total;
@@ -512,13 +564,26 @@ cudaError_t launch_stream_scan(const StoreView& st, const QueryView& qv, uint32_
   p.keys = cv.keys + (size_t)(q0 - cv.q_base) * cv.cap;
   p.cnt = cv.cnt + q0;
   p.gtau = cv.gtau + q0;
-  p.C = stream_list_cap(cv.KP);
-  p.n_tiles = (st.n_rows + SC_TILE_ROWS - 1) / SC_TILE_ROWS;
+  p.C = stream_list_cap(cv.KP, half);
+  p.n_tiles = (st.n_rows + sc_tile_rows(half) - 1) / sc_tile_rows(half);
   p.kslice = stream_pick_kslice(ld);
   p.n_slices = (ld + p.kslice - 1) / p.kslice;
   size_t smem;
   p.stages = stream_pick_stages(ld, nq_t, cv.KP, half ? 2 : 4, &smem);
   if (!p.stages) return cudaErrorInvalidConfiguration;
+  p.quad = 2;
+  if (half) {
+    // rarer list checks (each is a barrier over all consumer warps) while the longer lists cost no ring stage
+    for (uint32_t quad = 8; quad > 2; quad >>= 1) {
+      size_t t;
+      if (stream_pick_stages(ld, nq_t, cv.KP, 2, &t, quad) == p.stages) {
+        p.quad = quad;
+        smem = t;
+        break;
+      }
+    }
+    p.C = stream_list_cap(cv.KP, true, p.quad);
+  }
   if (p.G != stream_scan_groups(st.n_rows, sm_count)) return cudaErrorInvalidValue;
   if (half) {
     switch (nq_t) {

@@ -283,7 +283,7 @@ cx_status cx_apply_score_decay(cx_index* h, const cx_decay_config* cfg, float re
 cx_status cx_get_stats(const cx_index* h, cx_stats* out);
 /* Tuning / test hooks, all per index; set them while no search is running on the handle.
  * "force_path" 0 auto, 1 stream (K1), 2 tensor (K2), 3 exact; "tensor_min_batch" smallest query batch
- * the tensor pass serves (default 5); "tensor_phase_growth" growth factor of the scan phases (0/1 = one
+ * the tensor pass serves (default 3); "tensor_phase_growth" growth factor of the scan phases (0/1 = one
  * phase, default auto); "tensor_sample_tiles" row tiles sampled for the cut-off bootstrap (0 = auto); "shadow" 0 = keep no bf16 copy (disables the tensor pass; before the first
  * insert); "profile" 1 = bracket the scan-pass kernels (bootstrap included) with CUDA events on their
  * stream (cx_get_stats: pass_kernel_ns); "blocking_sync" 1 = search calls sleep on an event instead of

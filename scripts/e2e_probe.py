@@ -14,7 +14,9 @@ ids[:, 8:] = np.arange(rows, dtype=np.uint64).astype(">u8").view(np.uint8).resha
 ix = GpuVectorIndex(384); ix.reserve(rows); ix.insert_batch_device(ids, corpus)
 graphs = int(os.environ.get("CX_GRAPHS", "1"))
 ix.set_option("graphs", graphs)
-for B in (1, 2, 4, 8, 64, 1024):
+if "CX_TMB" in os.environ:
+    ix.set_option("tensor_min_batch", int(os.environ["CX_TMB"]))
+for B in [int(x) for x in os.environ.get("CX_BATCHES", "1,2,4,8,64,1024").split(",")]:
     hq = q_all[:B].cpu().numpy()
     hp = torch.empty((B, 384), dtype=torch.float32).pin_memory(); hp.copy_(q_all[:B]); hpn = hp.numpy()
     for name, buf in (("pageable", hq), ("pinned", hpn)):

@@ -51,9 +51,23 @@ def test_cfg2_1m_streaming_pass_b1_b4(million):
     g, o, corpus, Q, ids = million
     st0 = g.stats()
     assert_batch_equal(g, o, Q[:1], 10)
-    assert_batch_equal(g, o, Q[1:5], 10)
+    assert_batch_equal(g, o, Q[1:3], 10)
     st1 = g.stats()
-    assert st1["queries_stream"] - st0["queries_stream"] == 5, (st0, st1)
+    assert st1["queries_stream"] - st0["queries_stream"] == 3, (st0, st1)
+    assert st1["queries_stream_bf16"] - st0["queries_stream_bf16"] == 3, (st0, st1)  # over the bf16 shadow
+    # the same from the fp32 rows, and four queries per pass (what the retry ladder and shadow-less indexes use)
+    g.set_option("stream_bf16", 0)
+    g.set_option("force_path", 1)
+    try:
+        assert_batch_equal(g, o, Q[:1], 10)
+        assert_batch_equal(g, o, Q[1:5], 10)
+    finally:
+        g.set_option("stream_bf16", 1)
+        g.set_option("force_path", 0)
+    st2 = g.stats()
+    assert st2["queries_stream"] - st1["queries_stream"] == 5 and st2["queries_stream_bf16"] == st1["queries_stream_bf16"]
+    assert_batch_equal(g, o, Q[5:9], 10)   # B = 4: the tensor pass
+    assert g.stats()["queries_tensor"] - st2["queries_tensor"] == 4
 
 
 @pytest.mark.timeout(600)

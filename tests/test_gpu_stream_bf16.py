@@ -47,9 +47,27 @@ def test_batches_of_one_to_four(b):
     corpus = synth.make_corpus(30_000, 384, dup_frac=0.05, seed=21)
     Q = synth.make_queries(corpus, b, seed=22 + b)
     g, o, _ = build_pair(corpus)
+    g.set_option("tensor_min_batch", 5)  # by default three and four queries go to the tensor pass (below)
     both_ways(g, o, Q, 10)
     st = g.stats()
     assert st["queries_tensor"] == 0 and st["queries_exact"] == 0, st
+
+
+def test_default_routing_of_small_batches():
+    """B = 1, 2: streaming pass over the shadow; B >= 3: tensor pass; k beyond the tensor pass's keep lists
+    (k > 112): the streaming pass again, four queries per pass"""
+    corpus = synth.make_corpus(20_000, 384, seed=33)
+    g, o, _ = build_pair(corpus)
+    small = synth.make_corpus(3000, 384, seed=34)   # few enough producer groups for keep lists of 120+
+    gs, os_, _ = build_pair(small)
+    for gg, oo, c, b, k, key in ((g, o, corpus, 1, 10, "queries_stream_bf16"), (g, o, corpus, 2, 10, "queries_stream_bf16"),
+                                 (g, o, corpus, 3, 10, "queries_tensor"), (g, o, corpus, 4, 10, "queries_tensor"),
+                                 (gs, os_, small, 4, 120, "queries_stream_bf16")):
+        Q = synth.make_queries(c, b, seed=40 + b)
+        s0 = gg.stats()
+        assert_batch_equal(gg, oo, Q, k)
+        s1 = gg.stats()
+        assert s1[key] - s0[key] == b, (b, k, key, s0, s1)
 
 
 @pytest.mark.parametrize("n,d,k", [
@@ -61,6 +79,7 @@ def test_shapes(n, d, k):
     corpus = synth.make_corpus(n, d, seed=n + d)
     Q = synth.make_queries(corpus, 3, seed=k)
     g, o, _ = build_pair(corpus)
+    g.set_option("tensor_min_batch", 5)
     both_ways(g, o, Q, k)
 
 
@@ -68,6 +87,7 @@ def test_non_normalised_rows_and_scaled_queries():
     corpus = synth.make_corpus(8000, 384, normalise=False, dup_frac=0.2, seed=7)
     Q = synth.make_queries(corpus, 4, seed=7) * np.float32(3.0)
     g, o, _ = build_pair(corpus)
+    g.set_option("tensor_min_batch", 5)
     both_ways(g, o, Q, 20)
 
 

@@ -42,7 +42,7 @@ def check_batch(g, o, Q, thr, cap, gflt=None, oflt=None):
 
 @pytest.mark.parametrize("n,d,b", [(4000, 384, 1), (9000, 384, 4), (6000, 128, 7), (5000, 768, 3)])
 def test_threshold_streaming_pass(n, d, b):
-    """Small batches: K1 in threshold mode nominates (B < 5), the rescoring kernel decides."""
+    """Small batches: K1 in threshold mode nominates (B < 3), the rescoring kernel decides."""
     corpus = synth.make_corpus(n, d, zero_row=True, seed=21 + n)
     Q = synth.make_queries(corpus, b, seed=n)
     g, o, _ = build_pair(corpus)
@@ -50,14 +50,20 @@ def test_threshold_streaming_pass(n, d, b):
         st0 = g.stats()
         check_batch(g, o, Q, thr, 512)
         st1 = g.stats()
-        key = "queries_stream" if b < 5 else "queries_tensor"  # tensor_min_batch = 5
+        key = "queries_stream" if b < 3 else "queries_tensor"  # tensor_min_batch = 3
         assert st1[key] - st0[key] == b, (thr, st0, st1)  # the fast path served them
         assert st1["queries_exact"] == st0["queries_exact"]
+    # the streaming pass in threshold mode with up to eight queries per pass (what indexes without a shadow use)
+    g.set_option("force_path", 1)
+    st0 = g.stats()
+    check_batch(g, o, Q, 0.75, 512)
+    st1 = g.stats()
+    assert st1["queries_stream"] - st0["queries_stream"] == b and st1["queries_exact"] == st0["queries_exact"]
 
 
 @pytest.mark.parametrize("n,d,b", [(20_000, 384, 64), (30_000, 384, 300), (8000, 256, 129)])
 def test_threshold_tensor_pass(n, d, b):
-    """B >= 5: the tcgen05 pass with a fixed cut-off nominates."""
+    """B >= 3: the tcgen05 pass with a fixed cut-off nominates."""
     corpus = synth.make_corpus(n, d, zero_row=True, seed=5 + n)
     Q = synth.make_queries(corpus, b, seed=n + 2)
     g, o, _ = build_pair(corpus)
