@@ -28,22 +28,28 @@ for s0 in range(0, rows, 625_000):
     del c
 s = torch.cuda.current_stream().cuda_stream
 ix.set_option("profile", 1)
-for force in (0, 1):
-    if force:
-        ix.set_option("force_path", 1)
+import os
+pairs = [int(x) for x in os.environ.get("CX_PAIRS", "0").split(",")]
+epis = [int(x) for x in os.environ.get("CX_EPI", "8").split(",")]
+for force, pair, epi in [(0, p_, e_) for p_ in pairs for e_ in epis] + ([(1, 0, 8)] if os.environ.get("CX_FORCE_STREAM") else []):
+    ix.set_option("force_path", force)
+    ix.set_option("tensor_pair", pair)
+    ix.set_option("tensor_epi_warps", epi)
     out = None
     for _ in range(2):
         out = ix.search_batch_device(q, k, stream=s, out=out)
     torch.cuda.synchronize()
     st0 = ix.stats()
     t0 = time.perf_counter()
-    for _ in range(3):
+    reps = 6
+    for _ in range(reps):
         out = ix.search_batch_device(q, k, stream=s, out=out)
     torch.cuda.synchronize()
-    dt = (time.perf_counter() - t0) / 3 * 1e3
+    dt = (time.perf_counter() - t0) / reps * 1e3
     st1 = ix.stats()
-    print(json.dumps({"force_path": force, "ms": dt, **{kk: (st1[kk] - st0[kk]) / 3 for kk in
+    scan_us = (st1["pass_kernel_ns"] - st0["pass_kernel_ns"]) * 1e-3 / max(1, st1["pass_kernel_launches"] - st0["pass_kernel_launches"])
+    print(json.dumps({"force_path": force, "pair": pair, "epi": epi, "ms": dt, "scan_us": scan_us,
+                      "tflops": 2.0 * d * B * rows / (scan_us * 1e-6) / 1e12,
+                      **{kk: (st1[kk] - st0[kk]) / reps for kk in
                       ("fallbacks", "queries_stream", "queries_tensor", "queries_exact", "kernel_launches")},
                       "why": [st1[w] - st0[w] for w in ("unverified_overflow", "unverified_near_ties", "unverified_other")]}), flush=True)
-    sc = out[1].cpu().numpy()
-    print("score range of the 100 results, first 6 queries:", [(float(sc[i, 0]), float(sc[i, 99])) for i in range(6)])
