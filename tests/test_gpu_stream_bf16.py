@@ -126,6 +126,30 @@ def test_identical_rows_and_near_ties_fall_back_to_tighter_passes():
     both_ways(g, o, q[None, :], 10, expect_half=False)
 
 
+@pytest.mark.timeout(600)
+def test_every_row_beats_the_cut_off():
+    """Rows ordered by ASCENDING similarity to the query: every row a CTA meets clears its running cut-off, so the
+    shared-memory lists fill at the highest possible rate between two checks (the worst case of the capacity
+    argument of the one-barrier checkpoints, with the long check interval).  The best rows come last; a dropped
+    append would lose exactly them."""
+    rng = np.random.default_rng(11)
+    n, d = 300_000, 384
+    q = rng.standard_normal(d).astype(np.float32)
+    q /= np.linalg.norm(q)
+    noise = rng.standard_normal((n, d)).astype(np.float32)
+    noise -= np.outer(noise @ q, q)                      # orthogonal to q
+    noise /= np.linalg.norm(noise, axis=1, keepdims=True)
+    # less and less noise: cosine 0.32 ... 0.69 over the bulk, then 150 well separated rows up to 0.999 (the
+    # results must be verifiable from the shadow's approximate scores, or the call falls back to a tighter pass)
+    w = np.concatenate([np.linspace(3.0, 1.05, n - 150), np.linspace(1.0, 0.05, 150)]).astype(np.float32)[:, None]
+    corpus = (q[None, :] + w * noise).astype(np.float32)
+    g, o, _ = build_pair(corpus)
+    Q = np.stack([q, (q + 0.01 * noise[5]).astype(np.float32)])
+    both_ways(g, o, Q[:1], 10)
+    both_ways(g, o, Q, 10)
+    both_ways(g, o, Q[:1], 100)
+
+
 def test_degenerate_queries():
     corpus = synth.make_corpus(5000, 384, seed=3)
     g, o, _ = build_pair(corpus)
