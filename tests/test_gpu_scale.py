@@ -108,6 +108,34 @@ def test_cfg2_1m_tensor_pass_leftover_sms(million, b):
 
 
 @pytest.mark.timeout(600)
+def test_cfg2_1m_threshold_scan_with_leftover_sms(million):
+    """search_threshold for 384 queries at 0.75 over 1 M rows: the tensor pass with a fixed cut-off, three query
+    tiles (49 row splits + one left-over CTA that walks the tail rows for all three); 12 sampled queries against
+    the reference loop (index.rs:376-388), the rest against the run with the left-over SMs idle."""
+    g, o, corpus, Q, ids = million
+    q = Q[:384]
+    st0 = g.stats()
+    a = g.search_threshold_batch_arrays(q, 0.75, 256)
+    st1 = g.stats()
+    assert st1["queries_tensor"] - st0["queries_tensor"] >= 380, (st0, st1)
+    g.set_option("tensor_leftover_sms", 0)
+    try:
+        ref = g.search_threshold_batch_arrays(q, 0.75, 256)
+    finally:
+        g.set_option("tensor_leftover_sms", 1)
+    for x, y in zip(a, ref):
+        assert np.array_equal(np.asarray(x).view(np.uint8), np.asarray(y).view(np.uint8))
+    gi, gs, gd, gn, gt = a
+    assert int(gt.max()) > 0, "the corpus is clustered: some queries must have partners above 0.75"
+    for b in range(0, 384, 33):
+        exp = o.search_threshold(q[b], 0.75)
+        m = min(256, len(exp.ids))
+        assert int(gt[b]) == len(exp.ids) and int(gn[b]) == m
+        assert np.array_equal(gi[b, :m], exp.ids[:m]) and same_bits(gs[b, :m], exp.score[:m])
+        assert same_bits(gd[b, :m], exp.distance[:m])
+
+
+@pytest.mark.timeout(600)
 def test_cfg2_1m_self_match_and_tie_order(million):
     """Rows of the corpus as queries: the row itself (cosine 1 up to rounding) and its exact duplicates
     lead the list, duplicates in insertion order."""

@@ -148,6 +148,11 @@ def test_every_row_beats_the_cut_off():
     both_ways(g, o, Q[:1], 10)
     both_ways(g, o, Q, 10)
     both_ways(g, o, Q[:1], 100)
+    # the same corpus through the tensor pass (private lists per epilogue thread, warp-cooperative compaction)
+    Q8 = np.stack([(q + 0.01 * noise[i]).astype(np.float32) for i in range(8)])
+    s0 = g.stats()
+    assert_batch_equal(g, o, Q8, 10)
+    assert g.stats()["queries_tensor"] - s0["queries_tensor"] == 8
 
 
 def test_degenerate_queries():
