@@ -166,10 +166,16 @@ __global__ void __launch_bounds__(SelShape<SMALL>::T, SMALL ? 5 : 2) select_resc
     const unsigned long long left = (unsigned long long)cut << 32;  // what is left behind scores below `cut`
     if (left > U) U = left;
   }
-  for (uint32_t i = tid; i < n_src; i += SEL_THREADS) {
-    const uint64_t key = src[i];
-    if (key >= gt && key_ord(key) >= cut) {
-      const uint32_t pos = atomicAdd(&s_m, 1u);
+  for (uint32_t i0 = 0; i0 < n_src; i0 += SEL_THREADS) {  // one counter update per warp
+    const uint32_t i = i0 + tid;
+    const uint64_t key = i < n_src ? src[i] : 0ull;
+    const bool keep = i < n_src && key >= gt && key_ord(key) >= cut;
+    const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+    uint32_t base = 0;
+    if ((tid & 31u) == 0 && bal) base = atomicAdd(&s_m, (uint32_t)__popc(bal));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (keep) {
+      const uint32_t pos = base + (uint32_t)__popc(bal & ((1u << (tid & 31u)) - 1u));
       if (pos < SEL_K2) keys[pos] = key;
     }
   }
