@@ -339,6 +339,7 @@ extern "C" cx_status cx_extract_embeddings(const uint8_t* values, const uint64_t
                                            int device, uint8_t* out_ids, float* out_rows, int64_t* out_created_ns,
                                            int64_t* out_last_accessed_ns, uint64_t* out_access_count,
                                            uint8_t* out_status) {
+  cx::CallerDevice keep_callers_device;
   if (!n) return CX_OK;
   if (!values || !offsets || !out_status) return fail(CX_ERR_VALIDATION, "null argument");
   int n_dev = 0;
@@ -384,6 +385,7 @@ extern "C" cx_status cx_extract_embeddings(const uint8_t* values, const uint64_t
 // redb_storage.rs:728); the embeddings go from the uploaded blob into the store on the device.
 extern "C" cx_status cx_load_nodes(cx_index* h, const uint8_t* values, const uint64_t* offsets, uint64_t n,
                                    uint8_t* out_status, uint64_t out_counts[6]) {
+  cx::CallerDevice keep_callers_device;
   if (!h) return fail(CX_ERR_VALIDATION, "null index");
   if (out_counts) memset(out_counts, 0, 6 * sizeof(uint64_t));
   if (!n) return CX_OK;
@@ -425,6 +427,7 @@ extern "C" cx_status cx_apply_score_decay(cx_index* h, const cx_decay_config* cf
                                           uint32_t seg_len, const float* raw_score, const int64_t* idle_seconds,
                                           const uint64_t* access_count, const double* kind_rate, float* out_score,
                                           uint32_t* out_order) {
+  cx::CallerDevice keep_callers_device;
   if (!h || !cfg) return fail(CX_ERR_VALIDATION, "null argument");
   if (!n) return CX_OK;
   if (!raw_score || !idle_seconds || !access_count || !kind_rate || !out_score)

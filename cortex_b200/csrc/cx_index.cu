@@ -508,11 +508,13 @@ cx_status cx::index_create(uint32_t dimension, int device, bool with_seq, cx_ind
 }
 
 extern "C" cx_status cx_index_create(uint32_t dimension, int device, cx_index** out) {
+  cx::CallerDevice keep_callers_device;
   if (!out) return fail(CX_ERR_VALIDATION, "out is null");
   return index_create(dimension, device, false, out);
 }
 
 extern "C" void cx_index_destroy(cx_index* h) {
+  cx::CallerDevice keep_callers_device;
   if (!h) return;
   if (h->shards) {
     shard_destroy(h);
@@ -533,6 +535,7 @@ extern "C" void cx_index_destroy(cx_index* h) {
 }
 
 extern "C" cx_status cx_reserve(cx_index* h, uint64_t n_rows) {
+  cx::CallerDevice keep_callers_device;
   if (!h) return fail(CX_ERR_VALIDATION, "null index");
   if (h->shards) return shard_reserve(h, n_rows);
   CU(cudaSetDevice(h->device));
@@ -679,6 +682,7 @@ cx_status cx::index_insert(cx_index* h, const uint8_t* ids, const float* rows, u
 
 extern "C" cx_status cx_insert_batch(cx_index* h, const uint8_t* ids, const float* rows, uint64_t n,
                                      uint32_t len) {
+  cx::CallerDevice keep_callers_device;
   if (!h) return fail(CX_ERR_VALIDATION, "null index");
   if (h->shards) return shard_insert(h, ids, rows, n, len, false);
   return index_insert(h, ids, rows, n, len, false, nullptr);
@@ -688,12 +692,14 @@ extern "C" cx_status cx_insert_batch(cx_index* h, const uint8_t* ids, const floa
 // "mmap'd vectors bulk-uploaded once" path of the north star without a host round trip.
 extern "C" cx_status cx_insert_batch_device(cx_index* h, const uint8_t* ids, const float* d_rows, uint64_t n,
                                             uint32_t len) {
+  cx::CallerDevice keep_callers_device;
   if (!h) return fail(CX_ERR_VALIDATION, "null index");
   if (h->shards) return shard_insert(h, ids, d_rows, n, len, true);
   return index_insert(h, ids, d_rows, n, len, true, nullptr);
 }
 
 extern "C" cx_status cx_insert(cx_index* h, const uint8_t id[16], const float* embedding, uint32_t len) {
+  cx::CallerDevice keep_callers_device;
   return cx_insert_batch(h, id, embedding, 1, len);
 }
 
@@ -719,6 +725,7 @@ cx_status cx::index_remove(cx_index* h, const uint8_t id[16]) {
 }
 
 extern "C" cx_status cx_remove(cx_index* h, const uint8_t id[16]) {
+  cx::CallerDevice keep_callers_device;
   if (!h || !id) return fail(CX_ERR_VALIDATION, "null argument");
   if (h->shards) return shard_remove(h, id);
   return index_remove(h, id);
@@ -751,12 +758,14 @@ cx_status cx::index_set_metadata(cx_index* h, const uint8_t id[16], const char* 
 }
 
 extern "C" cx_status cx_set_metadata(cx_index* h, const uint8_t id[16], const char* kind, const char* agent) {
+  cx::CallerDevice keep_callers_device;
   if (!h || !id || !kind || !agent) return fail(CX_ERR_VALIDATION, "null argument");
   if (h->shards) return shard_set_metadata(h, id, kind, agent);
   return index_set_metadata(h, id, kind, agent);
 }
 
 extern "C" uint64_t cx_len(const cx_index* h) {
+  cx::CallerDevice keep_callers_device;
   if (!h) return 0;
   return h->shards ? shard_len(h) : h->n_live;
 }
@@ -857,12 +866,14 @@ cx_status cx::index_rebuild(cx_index* h) {
 }
 
 extern "C" cx_status cx_rebuild(cx_index* h) {
+  cx::CallerDevice keep_callers_device;
   if (!h) return fail(CX_ERR_VALIDATION, "null index");
   if (h->shards) return shard_rebuild(h);
   return index_rebuild(h);
 }
 
 extern "C" cx_status cx_row_id(const cx_index* h, uint32_t row, uint8_t out_id[16]) {
+  cx::CallerDevice keep_callers_device;
   if (!h || !out_id) return fail(CX_ERR_VALIDATION, "null argument");
   if (h->shards) return fail(CX_ERR_VALIDATION, "cx_row_id: a multi-device index returns ids, not rows");
   if (row >= h->n_rows) return fail(CX_ERR_VALIDATION, "row %u out of range", row);
@@ -928,6 +939,7 @@ bool cx::index_save_meta(const cx_index* h, FILE* fp) {
 }
 
 extern "C" cx_status cx_save(const cx_index* hc, const char* path) {
+  cx::CallerDevice keep_callers_device;
   cx_index* h = const_cast<cx_index*>(hc);
   if (!h || !path) return fail(CX_ERR_VALIDATION, "null argument");
   if (h->shards) return shard_save(h, path);
@@ -1013,6 +1025,7 @@ cx_status cx::index_load_into(const char* path, cx_status (*make)(uint32_t, void
 }
 
 extern "C" cx_status cx_load(const char* path, int device, cx_index** out) {
+  cx::CallerDevice keep_callers_device;
   if (!path || !out) return fail(CX_ERR_VALIDATION, "null argument");
   auto make = [](uint32_t dim, void* ctx, cx_index** o) { return cx_index_create(dim, *(int*)ctx, o); };
   return index_load_into(path, make, &device, out);
@@ -1041,6 +1054,7 @@ void cx::index_add_stats(const cx_index* h, cx_stats* out) {
 }
 
 extern "C" cx_status cx_get_stats(const cx_index* hc, cx_stats* out) {
+  cx::CallerDevice keep_callers_device;
   cx_index* h = const_cast<cx_index*>(hc);
   if (!h || !out) return fail(CX_ERR_VALIDATION, "null argument");
   memset(out, 0, sizeof *out);
@@ -1123,6 +1137,7 @@ cx_status cx::index_set_option(cx_index* h, const char* key, int64_t value) {
 }
 
 extern "C" cx_status cx_set_option(cx_index* h, const char* key, int64_t value) {
+  cx::CallerDevice keep_callers_device;
   if (!h || !key) return fail(CX_ERR_VALIDATION, "null argument");
   if (h->shards) return shard_set_option(h, key, value);
   return index_set_option(h, key, value);

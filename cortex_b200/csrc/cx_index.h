@@ -27,6 +27,24 @@ const char* last_error();
                       __LINE__, #expr);                                                              \
   } while (0)
 
+// The library switches the calling thread's current device as it works (cudaSetDevice in the entry points, the
+// shards of a multi-device handle one after the other).  Every C-ABI entry point puts the caller's device back
+// on return, so the library can share a thread with other CUDA users (a Rust host with its own kernels, torch).
+struct CallerDevice {
+  int dev = -1;
+  CallerDevice() {
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+      dev = -1;
+      (void)cudaGetLastError();
+    }
+  }
+  ~CallerDevice() {
+    if (dev >= 0) (void)cudaSetDevice(dev);
+  }
+  CallerDevice(const CallerDevice&) = delete;
+  CallerDevice& operator=(const CallerDevice&) = delete;
+};
+
 struct Id128 {
   uint64_t a, b;
   bool operator==(const Id128& o) const { return a == o.a && b == o.b; }

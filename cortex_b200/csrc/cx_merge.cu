@@ -240,6 +240,7 @@ using namespace cx;
 extern "C" cx_status cx_pack_topk_device(const uint32_t* d_rows, const float* d_score, const float* d_distance,
                                          const uint32_t* d_n, const uint32_t* d_ok, uint64_t B, uint64_t k,
                                          uint64_t row_offset, uint64_t* d_payload, void* stream) {
+  cx::CallerDevice keep_callers_device;
   if (!d_rows || !d_score || !d_distance || !d_n || !d_payload) return fail(CX_ERR_VALIDATION, "null device buffer");
   if (!B || !k) return CX_OK;
   const uint64_t total = B * k;
@@ -253,6 +254,7 @@ extern "C" cx_status cx_pack_topk_device(const uint32_t* d_rows, const float* d_
 extern "C" cx_status cx_merge_topk_device(const uint64_t* d_gathered, uint32_t world, uint64_t B, uint64_t k,
                                           int64_t* d_out_rows, float* d_out_score, float* d_out_distance,
                                           uint32_t* d_out_n, uint64_t* d_out_unverified, void* stream) {
+  cx::CallerDevice keep_callers_device;
   if (!d_gathered || !d_out_rows || !d_out_score || !d_out_distance || !d_out_n)
     return fail(CX_ERR_VALIDATION, "null device buffer");
   if (!B || !k || !world) return CX_OK;
@@ -270,6 +272,7 @@ extern "C" cx_status cx_autolink_filter_device(const int64_t* d_rows, const floa
                                                const int64_t* d_self_rows, uint64_t B, uint64_t k, float threshold,
                                                uint32_t max_edges_per_node, int64_t* d_out_rows, float* d_out_score,
                                                uint32_t* d_out_n, void* stream) {
+  cx::CallerDevice keep_callers_device;
   if (!d_rows || !d_score || !d_n || !d_out_rows || !d_out_score || !d_out_n)
     return fail(CX_ERR_VALIDATION, "null device buffer");
   if (!B) return CX_OK;

@@ -977,12 +977,14 @@ extern "C" cx_status cx_debug_tensor_plan(uint64_t n_queries, uint64_t n_rows, i
 extern "C" cx_status cx_search(cx_index* h, const float* query, uint32_t qlen, uint64_t k,
                                const cx_filter* filter, uint8_t* out_ids, float* out_score, float* out_distance,
                                uint64_t* out_n) {
+  cx::CallerDevice keep_callers_device;
   return search_host(h, query, 1, qlen, k, filter, false, 0.0f, out_ids, out_score, out_distance, out_n, nullptr);
 }
 
 extern "C" cx_status cx_search_batch(cx_index* h, const float* queries, uint64_t B, uint32_t qlen, uint64_t k,
                                      const cx_filter* filter, uint8_t* out_ids, float* out_score,
                                      float* out_distance, uint64_t* out_n) {
+  cx::CallerDevice keep_callers_device;
   return search_host(h, queries, B, qlen, k, filter, false, 0.0f, out_ids, out_score, out_distance, out_n,
                      nullptr);
 }
@@ -991,6 +993,7 @@ extern "C" cx_status cx_search_threshold(cx_index* h, const float* query, uint32
                                          const cx_filter* filter, uint64_t cap, uint8_t* out_ids,
                                          float* out_score, float* out_distance, uint64_t* out_n,
                                          uint64_t* out_total) {
+  cx::CallerDevice keep_callers_device;
   uint64_t total = 0;
   cx_status st = search_host(h, query, 1, qlen, cap, filter, true, threshold, out_ids, out_score, out_distance,
                              out_n, &total);
@@ -1002,6 +1005,7 @@ extern "C" cx_status cx_search_threshold_batch(cx_index* h, const float* queries
                                                float threshold, const cx_filter* filter, uint64_t cap,
                                                uint8_t* out_ids, float* out_score, float* out_distance,
                                                uint64_t* out_n, uint64_t* out_total) {
+  cx::CallerDevice keep_callers_device;
   return search_host(h, queries, B, qlen, cap, filter, true, threshold, out_ids, out_score, out_distance, out_n,
                      out_total);
 }
@@ -1020,6 +1024,7 @@ extern "C" cx_status cx_search_threshold_batch(cx_index* h, const float* queries
 extern "C" cx_status cx_dedup_scan(cx_index* h, float threshold, uint32_t per_node_cap, uint64_t max_pairs,
                                    uint8_t* out_a_ids, uint8_t* out_b_ids, float* out_score, uint64_t* out_n,
                                    uint64_t* out_total) {
+  cx::CallerDevice keep_callers_device;
   if (!h) return fail(CX_ERR_VALIDATION, "null index");
   if (!out_n) return fail(CX_ERR_VALIDATION, "null out_n");
   *out_n = 0;
@@ -1198,6 +1203,7 @@ extern "C" cx_status cx_search_batch_device(cx_index* h, const float* d_queries,
                                             const cx_filter* filter, uint32_t* d_out_rows, float* d_out_score,
                                             float* d_out_distance, uint8_t* d_out_ids, uint32_t* d_out_n,
                                             void* stream) {
+  cx::CallerDevice keep_callers_device;
   if (h && h->shards)
     return shard_search_device(h, d_queries, B, k, filter, d_out_rows, d_out_score, d_out_distance, d_out_ids, d_out_n,
                                stream, nullptr);
@@ -1209,6 +1215,7 @@ extern "C" cx_status cx_search_batch_device_begin(cx_index* h, const float* d_qu
                                                   const cx_filter* filter, uint32_t* d_out_rows,
                                                   float* d_out_score, float* d_out_distance, uint8_t* d_out_ids,
                                                   uint32_t* d_out_n, void* stream, void** ticket) {
+  cx::CallerDevice keep_callers_device;
   if (!ticket) return fail(CX_ERR_VALIDATION, "null ticket");
   if (h && h->shards)
     return shard_search_device(h, d_queries, B, k, filter, d_out_rows, d_out_score, d_out_distance, d_out_ids, d_out_n,
@@ -1224,6 +1231,7 @@ extern "C" cx_status cx_search_ticket_ok(void* ticket, const uint32_t** d_ok) {
 }
 
 extern "C" cx_status cx_search_batch_device_end(cx_index* h, void* ticket, uint64_t* n_redone) {
+  cx::CallerDevice keep_callers_device;
   if (n_redone) *n_redone = 0;
   if (!ticket) return CX_OK;  // _begin already ran the call to completion
   if (!h) return fail(CX_ERR_VALIDATION, "null index");
@@ -1250,6 +1258,7 @@ extern "C" cx_status cx_autolink_batch_device(cx_index* h, const float* d_embedd
                                               float* d_scratch_score, float* d_scratch_distance,
                                               uint32_t* d_scratch_n, uint32_t* d_out_rows, float* d_out_score,
                                               uint8_t* d_out_ids, uint32_t* d_out_n, void* stream) {
+  cx::CallerDevice keep_callers_device;
   if (!h) return fail(CX_ERR_VALIDATION, "null index");
   if (h->shards)
     return fail(CX_ERR_VALIDATION, "cx_autolink_batch_device: use cx_autolink_batch on a multi-device index");
@@ -1280,6 +1289,7 @@ extern "C" cx_status cx_autolink_batch_device(cx_index* h, const float* d_embedd
 extern "C" cx_status cx_autolink_batch(cx_index* h, const uint8_t* new_ids, const float* embeddings, uint64_t B,
                                        uint32_t len, uint64_t k, float threshold, uint32_t max_edges_per_node,
                                        uint8_t* out_to_ids, float* out_score, uint32_t* out_n) {
+  cx::CallerDevice keep_callers_device;
   if (!h) return fail(CX_ERR_VALIDATION, "null index");
   if (!out_n || (B && (!embeddings || !out_to_ids || !out_score))) return fail(CX_ERR_VALIDATION, "null argument");
   if (len != h->dim)

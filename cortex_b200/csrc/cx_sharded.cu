@@ -1110,6 +1110,7 @@ using namespace cx;
 
 extern "C" cx_status cx_index_create_sharded(uint32_t dimension, const int* devices, uint32_t n_devices,
                                              cx_index** out) {
+  cx::CallerDevice keep_callers_device;
   if (!out) return fail(CX_ERR_VALIDATION, "out is null");
   *out = nullptr;
   if (!devices || n_devices == 0 || n_devices > 64) return fail(CX_ERR_VALIDATION, "need 1..64 devices");
@@ -1165,6 +1166,7 @@ extern "C" uint32_t cx_shard_count(const cx_index* h) {
 }
 
 extern "C" cx_status cx_load_sharded(const char* path, const int* devices, uint32_t n_devices, cx_index** out) {
+  cx::CallerDevice keep_callers_device;
   if (!path || !out) return fail(CX_ERR_VALIDATION, "null argument");
   struct Ctx {
     const int* dev;

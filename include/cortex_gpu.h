@@ -20,6 +20,10 @@
  *    serve.rs:101, routes.rs:906); mutators (insert/remove/set_metadata/rebuild)
  *    must be externally serialised against everything else, which the caller's
  *    write guard already does.
+ *  - every function leaves the calling thread's current CUDA device as it found
+ *    it (an index may live on any device, a multi-device handle on several); the
+ *    stream / pointer arguments of the *_device functions belong to the index's
+ *    device (devices[0] of a multi-device handle).
  *  - there is no CPU fallback: without a CUDA device cx_index_create fails with
  *    CX_ERR_CUDA.
  */

@@ -201,3 +201,13 @@ def test_real_devices_bulk_device_insert():
     o = OracleIndex(384, faithful_copy=False)
     o.insert_batch(ids, corpus)
     assert_batch_equal(g, o, synth.make_queries(corpus, 130, seed=1), 10)
+    # the library works on other devices than the caller's current one and puts the caller's device back
+    assert torch.cuda.current_device() == 0
+    g1 = GpuVectorIndex(384, device=n_dev - 1)
+    g1.insert_batch(ids[:4000], corpus[:4000])
+    o1 = OracleIndex(384, faithful_copy=False)
+    o1.insert_batch(ids[:4000], corpus[:4000])
+    assert_batch_equal(g1, o1, synth.make_queries(corpus, 40, seed=2), 10)
+    assert torch.cuda.current_device() == 0
+    del g, g1
+    assert torch.cuda.current_device() == 0
