@@ -380,6 +380,16 @@ uint64_t fnv(uint64_t hsh, const void* p, size_t n) {
   return hsh;
 }
 
+// every option that shapes the kernels of a search or their arguments (part of a GraphKey)
+uint64_t hash_options(uint64_t hsh, const cx_index* h) {
+  const uint64_t o[10] = {(uint64_t)h->force_path,           (uint64_t)h->tensor_min_batch,
+                          (uint64_t)h->stream_bf16,          (uint64_t)h->tensor_phase_growth,
+                          (uint64_t)h->profile,              (uint64_t)h->tensor_sample_tiles,
+                          (uint64_t)h->tensor_tune.pair,     (uint64_t)h->tensor_tune.epi_warps,
+                          (uint64_t)h->tensor_tune.debug,    (uint64_t)h->tensor_tune.use_leftover_sms};
+  return fnv(hsh, o, sizeof o);
+}
+
 // Upload of the query batch of a host call, enqueued (and recorded) with the kernels it feeds.
 struct HostCopy {
   void* dst;
@@ -903,13 +913,9 @@ cx_status search_host(cx_index* h, const float* queries, uint64_t B, uint32_t ql
     hs = fnv(hs, &f.agent, sizeof f.agent);
     hs = fnv(hs, &f.has_kinds, sizeof f.has_kinds);
     hs = fnv(hs, &f.has_agent, sizeof f.has_agent);
-    const uint64_t misc[8] = {(uint64_t)(uintptr_t)h_block,  (uint64_t)h->force_path,      (uint64_t)h->tensor_min_batch + ((uint64_t)h->stream_bf16 << 40),
-                              (uint64_t)h->tensor_phase_growth, (uint64_t)h->profile,
-                              (uint64_t)(h->tensor_tune.pair * 64 + h->tensor_tune.epi_warps + 1024 * h->tensor_tune.debug +
-                                          4096 * h->tensor_tune.use_leftover_sms) +
-                                  ((uint64_t)h->tensor_sample_tiles << 32),
-                              (uint64_t)(uintptr_t)h->dE, 0x486f7374ull /* host call */};
+    const uint64_t misc[3] = {(uint64_t)(uintptr_t)h_block, (uint64_t)(uintptr_t)h->dE, 0x486f7374ull /* host call */};
     hs = fnv(hs, misc, sizeof misc);
+    hs = hash_options(hs, h);
     gk.w[0] = B;
     gk.w[1] = kd | ((uint64_t)qlen << 32);
     gk.w[2] = h->n_rows;
@@ -1167,15 +1173,11 @@ cx_status cx::index_search_device(cx_index* h, const float* d_queries, uint32_t 
     hs = fnv(hs, &f.agent, sizeof f.agent);
     hs = fnv(hs, &f.has_kinds, sizeof f.has_kinds);
     hs = fnv(hs, &f.has_agent, sizeof f.has_agent);
-    const uint64_t misc[10] = {(uint64_t)(uintptr_t)d_out_distance, (uint64_t)(uintptr_t)d_out_ids,
-                               (uint64_t)(uintptr_t)d_out_n,       (uint64_t)(uintptr_t)ws->hp,
-                               (uint64_t)h->force_path,            (uint64_t)h->tensor_min_batch + ((uint64_t)h->stream_bf16 << 40),
-                               (uint64_t)h->tensor_phase_growth,   (uint64_t)h->profile,
-                               (uint64_t)(h->tensor_tune.pair * 64 + h->tensor_tune.epi_warps + 1024 * h->tensor_tune.debug +
-                                          4096 * h->tensor_tune.use_leftover_sms) +
-                                   ((uint64_t)h->tensor_sample_tiles << 32),
-                               (uint64_t)t->fh.excl_rows.size()};
+    const uint64_t misc[5] = {(uint64_t)(uintptr_t)d_out_distance, (uint64_t)(uintptr_t)d_out_ids,
+                              (uint64_t)(uintptr_t)d_out_n, (uint64_t)(uintptr_t)ws->hp,
+                              (uint64_t)t->fh.excl_rows.size()};
     hs = fnv(hs, misc, sizeof misc);
+    hs = hash_options(hs, h);
     gk.w[0] = B;
     gk.w[1] = kd | ((uint64_t)qlen << 32);
     gk.w[2] = h->n_rows;

@@ -381,10 +381,11 @@ __global__ void __launch_bounds__(SC_THREADS, 1) stream_scan_kernel(const Stream
       }
     }
 
-    // checkpoint after the last tile of every full quad (tile i%4 == 2 for group 0, 3 for group 1)
-    // (bf16 variant: every second tile at first, then every QUAD-th; every warp walks every tile, so all agree)
-    const bool check = HALF ? (i < SC_EARLY_TILES ? (i & 1u) == 1u : ((i - SC_EARLY_TILES) % QUAD) == QUAD - 1) && i + 1 < my_tiles
-                            : (i % QUAD) == (QUAD - SC_GROUPS + grp) && (i / QUAD) < n_quads;
+    // List check.  fp32 variant: after the last tile of every full quad (tile i%4 == 2 for group 0, 3 for group 1).
+    // bf16 variant: every second tile at first, then every QUAD-th (every warp walks every tile, so all agree).
+    bool check;
+    if (HALF) check = (i < SC_EARLY_TILES ? (i & 1u) == 1u : ((i - SC_EARLY_TILES) % QUAD) == QUAD - 1) && i + 1 < my_tiles;
+    else check = (i % QUAD) == (QUAD - SC_GROUPS + grp) && (i / QUAD) < n_quads;
     if (check) {
       if (HALF) {
         // One barrier per checkpoint: which lists to compact was decided (by thread 0) right after the PREVIOUS
