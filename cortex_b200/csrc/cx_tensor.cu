@@ -628,8 +628,11 @@ tensor_scan_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 }
 
 // ---- cut-off from the sampled scores: tau0[q] = KP-th largest of dump[q][0..S) --------
-__global__ void __launch_bounds__(256) tau_select_kernel(const float* __restrict__ dump, uint32_t S, uint32_t KP,
-                                                         uint64_t* __restrict__ gtau) {
+// (NT threads per query: 1024 when few queries leave most SMs idle anyway -- the kernel is then a latency chain
+// of block-wide passes over the sample -- 256 when there is a block per SM and more)
+template <int NT>
+__global__ void __launch_bounds__(NT) tau_select_kernel(const float* __restrict__ dump, uint32_t S, uint32_t KP,
+                                                        uint64_t* __restrict__ gtau) {
   __shared__ uint32_t scratch[260];
   __shared__ uint32_t stage[4096];
   const uint32_t q = blockIdx.x, tid = threadIdx.x;
@@ -640,7 +643,7 @@ __global__ void __launch_bounds__(256) tau_select_kernel(const float* __restrict
     const float x = d[i];
     return x > -INFINITY ? ord_from_float(x) : 0u;
   };
-  const uint32_t t = S >= KP ? block_kth_largest(get, S, KP, scratch, stage, 4096u, tid, 256) : 0u;
+  const uint32_t t = S >= KP ? block_kth_largest(get, S, KP, scratch, stage, 4096u, tid, NT) : 0u;
   if (tid == 0) gtau[q] = (uint64_t)t << 32;  // the lowest key with that score (0 = none)
 }
 
@@ -860,7 +863,8 @@ cudaError_t launch_tensor_bootstrap(const StoreView& st, const void* Q16, uint32
   cudaError_t e =
       launch_mode(st, Q16, q0, nq, flt, check_rows, cv, nullptr, dump, n_slots, 0, TC_MODE_DUMP, sm_count, s, tune);
   if (e != cudaSuccess) return e;
-  tau_select_kernel<<<nq, 256, 0, s>>>(dump, n_slots * TC_BN, cv.KP, cv.gtau + q0);
+  if (nq <= (uint32_t)sm_count) tau_select_kernel<1024><<<nq, 1024, 0, s>>>(dump, n_slots * TC_BN, cv.KP, cv.gtau + q0);
+  else tau_select_kernel<256><<<nq, 256, 0, s>>>(dump, n_slots * TC_BN, cv.KP, cv.gtau + q0);
   return cudaGetLastError();
 }
 
