@@ -815,7 +815,9 @@ static cudaError_t launch_mode(const StoreView& st, const void* Q16, uint32_t q0
   if (!pair && tune.use_leftover_sms) {
     const uint32_t n_full = n_qt * n_es;
     const uint32_t rem = (uint32_t)sm_count > n_full ? (uint32_t)sm_count - n_full : 0u;
-    if (rem && p.n_slots >= 2u * (uint32_t)sm_count) {
+    // ... when every left-over CTA then gets WHOLE query tiles: they walk the tail rows in step (one HBM read,
+    // the later walks from L2) like the CTAs of the regular grid; uneven shares would scatter them over the tail
+    if (rem && n_qt % rem == 0 && p.n_slots >= 2u * (uint32_t)sm_count) {
       p.n_tail = (uint32_t)(((uint64_t)p.n_slots * rem) / (n_full + rem));
       if (p.n_tail) p.n_rem = rem;
     }
