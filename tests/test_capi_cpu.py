@@ -39,6 +39,25 @@ def test_rust_ffi_crate_declares_exactly_the_header_symbols():
     assert rust == header_symbols(), (sorted(header_symbols() - rust), sorted(rust - header_symbols()))
 
 
+def test_every_option_and_stats_field_is_documented_and_mirrored():
+    """cx_set_option keys accepted by the library are all described in the header (the probe-only measurement
+    hook is described as such), and the cx_stats fields of the header, the ctypes mirror and the Rust mirror
+    are the same list in the same order (the struct is filled positionally across the FFI)."""
+    hdr = open(os.path.join(ROOT, "include", "cortex_gpu.h")).read()
+    src = open(os.path.join(ROOT, "cortex_b200", "csrc", "cx_index.cu")).read()
+    keys = set(re.findall(r'strcmp\(key, "([a-z_0-9]+)"\)', src))
+    assert len(keys) >= 10
+    for k in keys:
+        assert f'"{k}"' in hdr, f"option {k} is accepted by cx_set_option but not documented in cortex_gpu.h"
+    body = re.search(r"typedef struct cx_stats \{(.*?)\} cx_stats;", hdr, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = [f.strip() for decl in re.findall(r"uint64_t\s+([^;]+);", body) for f in decl.split(",")]
+    assert [n for n, _ in _capi.CxStats._fields_] == fields
+    rs = open(os.path.join(ROOT, "rust", "cortex-gpu-sys", "src", "lib.rs")).read()
+    rs_body = re.search(r"pub struct cx_stats \{(.*?)\}", rs, flags=re.S).group(1)
+    assert re.findall(r"pub ([a-z_0-9]+): u64", rs_body) == fields
+
+
 def test_version_and_error_strings(lib):
     assert b"sm_100a" in lib.cx_version()
     assert isinstance(lib.cx_last_error(), bytes)
