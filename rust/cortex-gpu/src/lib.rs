@@ -155,6 +155,18 @@ impl GpuVectorIndex {
     pub fn shard_count(&self) -> usize {
         unsafe { sys::cx_shard_count(self.h) as usize }
     }
+    /// Counters of the index (which pass served how many queries, fallbacks, bytes copied, store growth).
+    pub fn stats(&self) -> Result<sys::cx_stats> {
+        let mut st: sys::cx_stats = unsafe { std::mem::zeroed() };
+        check(unsafe { sys::cx_get_stats(self.h, &mut st) })?;
+        Ok(st)
+    }
+    /// Tuning hooks of cortex_gpu.h (`"graphs"`, `"stream_bf16"`, `"tensor_min_batch"`, ...); results are the
+    /// same with every setting.  Call it while no search runs on the index (it takes `&mut self`).
+    pub fn set_option(&mut self, key: &str, value: i64) -> Result<()> {
+        let k = CString::new(key).unwrap();
+        check(unsafe { sys::cx_set_option(self.h, k.as_ptr(), value) })
+    }
     /// HnswIndex::set_metadata, index.rs:219-222
     pub fn set_metadata(&mut self, id: NodeId, kind: NodeKind, source_agent: String) {
         let k = CString::new(kind.as_str()).unwrap();
